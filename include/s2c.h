@@ -1,0 +1,130 @@
+/*
+ * s2c.h -- C ABI of libs2c.so, the sm_100a (B200) implementation of the Scan2Cap
+ * point-cloud -> caption hot path.
+ *
+ * This is the drop-in boundary: every entry point below replaces one function of the
+ * reference's pybind module `pointnet2._ext` (lib/pointnet2/_ext_src/src/bindings.cpp:6-19)
+ * or one Python-level step of the reference models, and takes only plain device pointers,
+ * sizes and a CUDA stream -- no torch types.  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions (all entry points)
+ *   - every pointer is a DEVICE pointer to a dense, contiguous array in the layout quoted;
+ *     float = IEEE fp32, int = int32, unless stated otherwise;
+ *   - outputs are CALLER-allocated.  Where the reference relies on zero-filled outputs
+ *     (torch::zeros in its C++ wrappers) the kernel here writes every element itself, so the
+ *     caller does not need to clear them, except for the *_grad functions whose `accumulate`
+ *     semantics are stated per function;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); work is
+ *     enqueued asynchronously on it, there is no hidden synchronisation and no global state;
+ *   - return value: 0 = S2C_OK, otherwise an S2C_ERR_* code; s2c_last_error() returns a
+ *     thread-local human-readable message for the last failing call of this thread.
+ *     (The reference prints and calls exit(-1): include/cuda_utils.h:30-39.)
+ */
+#ifndef S2C_H_
+#define S2C_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define S2C_API __attribute__((visibility("default")))
+#else
+#define S2C_API
+#endif
+
+#define S2C_OK 0
+#define S2C_ERR_INVALID_ARGUMENT 1
+#define S2C_ERR_CUDA 2
+#define S2C_ERR_UNSUPPORTED 3
+
+/* Library / ABI version (major*10000 + minor*100 + patch). */
+S2C_API int s2c_version(void);
+/* Message of the last error raised on the calling thread ("" if none). */
+S2C_API const char *s2c_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * furthest_point_sampling -- replaces _ext.furthest_point_sampling
+ *   reference: src/sampling.cpp:66-87, src/sampling_gpu.cu:59-229
+ *   xyz (B,N,3) f32  ->  idx (B,m) int32.   idx[:,0] = 0; bit-exact with the reference,
+ *   including its tie-breaking (shared-memory tree order) and the |p|^2 <= 1e-3 skip rule.
+ *   No scratch buffer is needed (the reference's (B,N) `temp` lives in registers here).
+ *   new_xyz (B,m,3) f32 may be NULL; if given, the sampled coordinates xyz[b, idx[b,j]] are
+ *   written too (fuses the gather_points call of pointnet2_modules.py:238-240).
+ * ---------------------------------------------------------------------------------------- */
+S2C_API int s2c_furthest_point_sampling(const float *xyz, int B, int N, int m, int *idx, float *new_xyz,
+                                void *stream);
+
+/* gather_points -- replaces _ext.gather_points (src/sampling.cpp:15-40, sampling_gpu.cu:8-30)
+ *   points (B,C,N), idx (B,m) -> out (B,C,m) */
+S2C_API int s2c_gather_points(const float *points, const int *idx, int B, int C, int N, int m, float *out,
+                      void *stream);
+
+/* gather_points_grad -- replaces _ext.gather_points_grad (sampling.cpp:41-65, sampling_gpu.cu:34-57)
+ *   grad_out (B,C,m), idx (B,m) -> grad_points (B,C,N).  The output is zero-filled by this call
+ *   (as torch::zeros does in the reference) and then accumulated with float atomics. */
+S2C_API int s2c_gather_points_grad(const float *grad_out, const int *idx, int B, int C, int N, int m,
+                           float *grad_points, void *stream);
+
+/* ball_query -- replaces _ext.ball_query (src/ball_query.cpp:8-32, ball_query_gpu.cu:9-54)
+ *   new_xyz (B,M,3), xyz (B,n,3) -> idx (B,M,nsample) int32: the first `nsample` point indices
+ *   (in index order) with d2 < radius*radius (fp32); unfilled slots repeat the first hit; an
+ *   empty ball gives zeros.  Bit-exact with the reference.  1 <= nsample <= 1024.
+ *   cnt (B,M) int32 may be NULL; if given it receives min(#hits, nsample) per centre. */
+S2C_API int s2c_ball_query(const float *new_xyz, const float *xyz, int B, int n, int M, float radius,
+                   int nsample, int *idx, int *cnt, void *stream);
+
+/* group_points -- replaces _ext.group_points (src/group_points.cpp:12-36, group_points_gpu.cu:8-28)
+ *   points (B,C,N), idx (B,np,ns) -> out (B,C,np,ns) */
+S2C_API int s2c_group_points(const float *points, const int *idx, int B, int C, int N, int npoints,
+                     int nsample, float *out, void *stream);
+
+/* group_points_grad -- replaces _ext.group_points_grad (group_points.cpp:38-62, group_points_gpu.cu:43-64)
+ *   grad_out (B,C,np,ns), idx (B,np,ns) -> grad_points (B,C,N); zero-filled by this call, then
+ *   accumulated with float atomics (order unspecified, as in the reference). */
+S2C_API int s2c_group_points_grad(const float *grad_out, const int *idx, int B, int C, int N, int npoints,
+                          int nsample, float *grad_points, void *stream);
+
+/* three_nn -- replaces _ext.three_nn (src/interpolate.cpp:14-40, interpolate_gpu.cu:9-68)
+ *   unknown (B,n,3), known (B,m,3) -> dist2 (B,n,3) f32 (SQUARED distances, as the extension
+ *   returns them), idx (B,n,3) int32.  Bit-exact (strict <, first index wins, double bests). */
+S2C_API int s2c_three_nn(const float *unknown, const float *known, int B, int n, int m, float *dist2,
+                 int *idx, void *stream);
+
+/* three_interpolate -- replaces _ext.three_interpolate (interpolate.cpp:42-68, interpolate_gpu.cu:72-112)
+ *   points (B,C,m), idx (B,n,3), weight (B,n,3) -> out (B,C,n) */
+S2C_API int s2c_three_interpolate(const float *points, const int *idx, const float *weight, int B, int C,
+                          int m, int n, float *out, void *stream);
+
+/* three_interpolate_grad -- replaces _ext.three_interpolate_grad (interpolate.cpp:70-99, interpolate_gpu.cu:116-154)
+ *   grad_out (B,C,n), idx, weight (B,n,3) -> grad_points (B,C,m); zero-filled by this call. */
+S2C_API int s2c_three_interpolate_grad(const float *grad_out, const int *idx, const float *weight, int B,
+                               int C, int n, int m, float *grad_points, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * query_and_group -- one fused call for QueryAndGroup.forward (lib/pointnet2/pointnet2_utils.py:317-376
+ *   with use_xyz=True, ret_grouped_xyz=True, normalize_xyz as given), i.e. ball_query ->
+ *   group_points(xyz^T) - new_xyz -> (/ radius) -> group_points(features) -> cat.
+ *     xyz       (B,n,3)
+ *     new_xyz   (B,M,3)
+ *     features  per-point features, C channels (C may be 0, then features may be NULL):
+ *                 feat_layout 0: (B,C,n)  channel-major, the reference's layout
+ *                 feat_layout 1: (B,n,C)  point-major with row stride feat_stride floats
+ *                                (lets the caller pass point_clouds[...,3:] without a transpose)
+ *     idx       (B,M,nsample) int32 out (same values as s2c_ball_query)
+ *     grouped   out, 3+C channels, xyz channels first:
+ *                 out_layout 0: (B,3+C,M,nsample)   the reference's layout
+ *                 out_layout 1: (B,M,nsample,3+C)   channels-last (what the grouped-MLP kernels eat)
+ *   normalize_xyz != 0 multiplies the relative coordinates by the fp32 reciprocal of radius
+ *   (what torch's CUDA div-by-python-scalar does).
+ * ---------------------------------------------------------------------------------------- */
+S2C_API int s2c_query_and_group(const float *xyz, const float *new_xyz, const float *features, int B, int n,
+                        int M, int C, int feat_layout, long long feat_stride, float radius,
+                        int nsample, int normalize_xyz, int out_layout, int *idx, float *grouped,
+                        void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S2C_H_ */

@@ -1,0 +1,60 @@
+"""ctypes binding of libs2c.so -- the only way the Python host code reaches the CUDA kernels.
+
+There is NO fallback: if the library is missing, unloadable or lacks a symbol, importing this
+module (and therefore using any op of the package) raises immediately.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libs2c.so")
+
+c_int, c_float, c_void_p, c_ll = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_longlong
+P = c_void_p
+
+# name -> argtypes, exactly include/s2c.h
+SIGNATURES = {
+    "s2c_furthest_point_sampling": [P, c_int, c_int, c_int, P, P, P],
+    "s2c_gather_points": [P, P, c_int, c_int, c_int, c_int, P, P],
+    "s2c_gather_points_grad": [P, P, c_int, c_int, c_int, c_int, P, P],
+    "s2c_ball_query": [P, P, c_int, c_int, c_int, c_float, c_int, P, P, P],
+    "s2c_group_points": [P, P, c_int, c_int, c_int, c_int, c_int, P, P],
+    "s2c_group_points_grad": [P, P, c_int, c_int, c_int, c_int, c_int, P, P],
+    "s2c_three_nn": [P, P, c_int, c_int, c_int, P, P, P],
+    "s2c_three_interpolate": [P, P, P, c_int, c_int, c_int, c_int, P, P],
+    "s2c_three_interpolate_grad": [P, P, P, c_int, c_int, c_int, c_int, P, P],
+    "s2c_query_and_group": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_ll, c_float, c_int, c_int, c_int,
+                            P, P, P],
+}
+
+
+class S2CError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "scan2cap_b200: %s not found -- build it with `python -m scan2cap_b200.build` "
+            "(there is no CPU or PyTorch fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.s2c_version.restype = c_int
+    lib.s2c_last_error.restype = ctypes.c_char_p
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    return lib
+
+
+LIB = _load()
+
+
+def check(rc, name):
+    if rc != 0:
+        msg = LIB.s2c_last_error().decode("utf-8", "replace")
+        raise S2CError("%s failed (code %d): %s" % (name, rc, msg))
+
+
+def call(name, *args):
+    check(getattr(LIB, name)(*args), name)

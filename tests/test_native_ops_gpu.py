@@ -1,0 +1,208 @@
+"""Parity of libs2c's native ops (through the C ABI) against the CPU oracle and, when it is present,
+against the UNMODIFIED reference CUDA extension (oracle/_ref).  Integer outputs: bit-exact.
+Float outputs of gather/group/interpolate/three_nn: bit-exact too (pure copies / fixed fma order);
+atomically accumulated gradients: 1e-5 relative (summation order is unspecified in the reference)."""
+import numpy as np
+import pytest
+import torch
+
+import golden_cases as gc
+from scan2cap_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+# ------------------------------------------------------------------ FPS
+@pytest.mark.parametrize("name", sorted(gc.fps_cases().keys()))
+def test_fps_golden_cases(name, ext, oracle, ref_ext):
+    xyz, m = gc.fps_cases()[name]
+    got = N(ext.furthest_point_sampling(T(xyz), m))
+    np.testing.assert_array_equal(got, oracle.furthest_point_sampling(xyz, m))
+    if ref_ext is not None:
+        np.testing.assert_array_equal(got, N(ref_ext.furthest_point_sampling(T(xyz), m)))
+
+
+@pytest.mark.parametrize("n,m,B", [(40000, 2048, 2), (2048, 1024, 3), (1024, 512, 2), (512, 256, 2), (1024, 256, 2),
+                                   (10000, 512, 1), (20000, 300, 1), (8192, 128, 1), (9000, 64, 2), (100000, 64, 1)])
+def test_fps_scene_sizes(n, m, B, ext, oracle, ref_ext):
+    pc, _ = synthetic.make_point_clouds(B, n, use_height=False, seed=n + m)
+    xyz = pc[..., :3].copy()
+    idx, new_xyz = ext.furthest_point_sampling_with_xyz(T(xyz), m)
+    got = N(idx)
+    np.testing.assert_array_equal(got, oracle.furthest_point_sampling(xyz, m))
+    np.testing.assert_array_equal(N(new_xyz), np.take_along_axis(xyz, got[..., None].astype(np.int64), 1))
+    if ref_ext is not None:
+        np.testing.assert_array_equal(got, N(ref_ext.furthest_point_sampling(T(xyz), m)))
+
+
+@pytest.mark.parametrize("cl", [1, 2, 4, 8, 16])
+def test_fps_every_cluster_size(cl, oracle, monkeypatch):
+    """Same answer whatever the CTA-cluster decomposition (run in a subprocess: the override is read once)."""
+    import subprocess, sys, os
+    code = (
+        "import numpy as np, torch, sys; sys.path.insert(0, %r)\n"
+        "from scan2cap_b200.lib.pointnet2 import _ext\n"
+        "from scan2cap_b200 import synthetic\n"
+        "pc,_ = synthetic.make_point_clouds(2, 12000, use_height=False, seed=3)\n"
+        "idx = _ext.furthest_point_sampling(torch.from_numpy(pc[..., :3].copy()).cuda(), 400)\n"
+        "np.save(sys.argv[1], idx.cpu().numpy())\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "idx.npy")
+        env = dict(os.environ, S2C_FPS_CLUSTER=str(cl))
+        subprocess.check_call([sys.executable, "-c", code, out], env=env)
+        got = np.load(out)
+    pc, _ = synthetic.make_point_clouds(2, 12000, use_height=False, seed=3)
+    np.testing.assert_array_equal(got, oracle.furthest_point_sampling(pc[..., :3].copy(), 400))
+
+
+# ------------------------------------------------------------------ ball query
+@pytest.mark.parametrize("name", sorted(gc.ball_cases().keys()))
+def test_ball_query_golden_cases(name, ext, oracle, ref_ext):
+    new_xyz, xyz, r, ns = gc.ball_cases()[name]
+    got = N(ext.ball_query(T(new_xyz), T(xyz), r, ns))
+    np.testing.assert_array_equal(got, oracle.ball_query(new_xyz, xyz, r, ns))
+    if ref_ext is not None:
+        np.testing.assert_array_equal(got, N(ref_ext.ball_query(T(new_xyz), T(xyz), r, ns)))
+
+
+@pytest.mark.parametrize("n,M,r,ns", [(40000, 2048, 0.2, 64), (2048, 1024, 0.4, 32), (1024, 512, 0.8, 16),
+                                      (512, 256, 1.2, 16), (1024, 256, 0.3, 16), (5000, 33, 0.25, 7)])
+def test_ball_query_sa_shapes(n, M, r, ns, ext, oracle, ref_ext):
+    pc, _ = synthetic.make_point_clouds(2, n, use_height=False, seed=n)
+    xyz = pc[..., :3].copy()
+    new_xyz = xyz[:, :M].copy()
+    got = N(ext.ball_query(T(new_xyz), T(xyz), r, ns))
+    np.testing.assert_array_equal(got, oracle.ball_query(new_xyz, xyz, r, ns))
+    if ref_ext is not None:
+        np.testing.assert_array_equal(got, N(ref_ext.ball_query(T(new_xyz), T(xyz), r, ns)))
+
+
+@pytest.mark.parametrize("feat_pm", [False, True])
+@pytest.mark.parametrize("cl", [False, True])
+@pytest.mark.parametrize("C,normalize", [(0, True), (1, True), (4, False), (37, True)])
+def test_query_and_group_fused(feat_pm, cl, C, normalize, ext, oracle):
+    n, M, r, ns = 3000, 200, 0.3, 32
+    pc, _ = synthetic.make_point_clouds(2, n, use_height=False, seed=11)
+    xyz = pc[..., :3].copy()
+    rng = np.random.default_rng(5)
+    new_xyz = xyz[:, rng.permutation(n)[:M]].copy()
+    feats_pm = rng.standard_normal((2, n, C)).astype(np.float32)  # point-major
+    feats_cm = np.ascontiguousarray(feats_pm.transpose(0, 2, 1))  # (B,C,n)
+    # oracle composition = QueryAndGroup.forward (pointnet2_utils.py:334-357)
+    idx = oracle.ball_query(new_xyz, xyz, r, ns)
+    g_xyz = oracle.group_points(np.ascontiguousarray(xyz.transpose(0, 2, 1)), idx)
+    g_xyz = g_xyz - new_xyz.transpose(0, 2, 1)[..., None]
+    if normalize:
+        g_xyz = g_xyz * (np.float32(1.0) / np.float32(r))
+    want = np.concatenate([g_xyz, oracle.group_points(feats_cm, idx)], 1) if C else g_xyz
+    f = None
+    if C:
+        if feat_pm:
+            full = T(np.concatenate([xyz, feats_pm], -1))  # like point_clouds (B,n,3+C)
+            f = full[..., 3:]
+        else:
+            f = T(feats_cm)
+    grouped, gidx = ext.query_and_group(T(xyz), T(new_xyz), f, r, ns, normalize, feat_point_major=feat_pm,
+                                        channels_last=cl)
+    np.testing.assert_array_equal(N(gidx), idx)
+    assert grouped.shape == (2, 3 + C, M, ns)
+    np.testing.assert_array_equal(N(grouped), want)
+
+
+# ------------------------------------------------------------------ three_nn / interpolate / gather / group
+@pytest.mark.parametrize("name", sorted(gc.nn_cases().keys()))
+def test_three_nn_golden_cases(name, ext, oracle, ref_ext):
+    u, k = gc.nn_cases()[name]
+    d2, idx = ext.three_nn(T(u), T(k))
+    od2, oidx = oracle.three_nn(u, k)
+    np.testing.assert_array_equal(N(idx), oidx)
+    np.testing.assert_array_equal(N(d2), od2)
+    if ref_ext is not None:
+        rd2, ridx = ref_ext.three_nn(T(u), T(k))
+        np.testing.assert_array_equal(N(idx), N(ridx))
+        np.testing.assert_array_equal(N(d2), N(rd2))
+
+
+@pytest.mark.parametrize("n,m", [(512, 256), (1024, 512), (3000, 2500)])
+def test_three_nn_fp_shapes(n, m, ext, oracle, ref_ext):
+    pc, _ = synthetic.make_point_clouds(2, n + m, use_height=False, seed=n)
+    u, k = pc[:, :n, :3].copy(), pc[:, n:, :3].copy()
+    d2, idx = ext.three_nn(T(u), T(k))
+    od2, oidx = oracle.three_nn(u, k)
+    np.testing.assert_array_equal(N(idx), oidx)
+    np.testing.assert_array_equal(N(d2), od2)
+    if ref_ext is not None:
+        rd2, ridx = ref_ext.three_nn(T(u), T(k))
+        np.testing.assert_array_equal(N(idx), N(ridx))
+        np.testing.assert_array_equal(N(d2), N(rd2))
+
+
+def test_feature_ops(ext, oracle, ref_ext):
+    f = gc.feature_case()
+    Nn, m = f["feats"].shape[2], f["known"].shape[2]
+    pairs = [
+        ("group_points", (f["feats"], f["idx"]), True),
+        ("gather_points", (f["feats"], f["idx1"]), True),
+        ("three_interpolate", (f["known"], f["idx3"], f["w3"]), True),
+        ("group_points_grad", (f["grad4"], f["idx"], Nn), False),
+        ("gather_points_grad", (f["grad3"], f["idx1"], Nn), False),
+        ("three_interpolate_grad", (f["gradn"], f["idx3"], f["w3"], m), False),
+    ]
+    for name, args, exact in pairs:
+        targs = [T(a) if isinstance(a, np.ndarray) else a for a in args]
+        got = N(getattr(ext, name)(*targs))
+        want = getattr(oracle, name)(*args)
+        if exact:
+            np.testing.assert_array_equal(got, want, err_msg=name)
+        else:
+            np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6, err_msg=name)
+        if ref_ext is not None:
+            ref = N(getattr(ref_ext, name)(*targs))
+            if exact:
+                np.testing.assert_array_equal(got, ref, err_msg=name + " vs reference ext")
+            else:
+                np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-6, err_msg=name + " vs reference ext")
+
+
+def test_three_interpolate_reference_kat(ext):
+    """The reference's only test (lib/pointnet2/pointnet2_test.py:18-30): fixed idx/weight; analytic
+    values out[:,:,0] = f0+f1+f2, out[:,:,1] = 2*(f1+f2+f3)."""
+    torch.manual_seed(0)
+    feats = torch.randn(1, 2, 4, device=DEV)
+    idx = torch.tensor([[[0, 1, 2], [1, 2, 3]]], dtype=torch.int32, device=DEV)
+    w = torch.tensor([[[1., 1., 1.], [2., 2., 2.]]], device=DEV)
+    out = ext.three_interpolate(feats, idx, w)
+    f = feats[0]
+    want = torch.stack([f[:, 0] + f[:, 1] + f[:, 2], 2 * (f[:, 1] + f[:, 2] + f[:, 3])], -1)[None]
+    torch.testing.assert_close(out, want, rtol=1e-5, atol=1e-6)
+
+
+def test_large_group_and_grad_sa1_shape(ext, oracle):
+    B, C, n, M, ns = 2, 4, 40000, 2048, 64
+    rng = np.random.default_rng(0)
+    feats = rng.standard_normal((B, C, n)).astype(np.float32)
+    idx = rng.integers(0, n, (B, M, ns)).astype(np.int32)
+    np.testing.assert_array_equal(N(ext.group_points(T(feats), T(idx))), oracle.group_points(feats, idx))
+    g = rng.standard_normal((B, C, M, ns)).astype(np.float32)
+    np.testing.assert_allclose(N(ext.group_points_grad(T(g), T(idx), n)), oracle.group_points_grad(g, idx, n),
+                               rtol=1e-4, atol=1e-5)
+
+
+def test_errors_raise(ext):
+    x = torch.zeros(1, 8, 3)
+    with pytest.raises(RuntimeError):
+        ext.furthest_point_sampling(x, 4)  # CPU tensor: "CPU not supported"
+    with pytest.raises(RuntimeError):
+        ext.ball_query(x.cuda(), x.cuda().transpose(1, 2), 0.1, 4)  # non-contiguous
+    with pytest.raises(RuntimeError):
+        ext.ball_query(x.cuda(), x.cuda(), 0.1, 0)  # nsample out of range -> S2C_ERR_INVALID_ARGUMENT

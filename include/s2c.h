@@ -124,6 +124,26 @@ S2C_API int s2c_query_and_group(const float *xyz, const float *new_xyz, const fl
                         int nsample, int normalize_xyz, int out_layout, int *idx, float *grouped,
                         void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * knn_adjacency -- replaces the 256-iteration Python loop GraphModule._create_adjacent_mat /
+ *   _query_locals (models/graph_module.py:182-233) and its copy in the caption module
+ *   (models/caption_module.py:322-381): for every (scene, target) pair, the indicator row of the
+ *   `num_locals` proposals closest to the target box.
+ *     corners    (B,K,8,3) FLOAT64 box corners (data_dict["bbox_corner"])
+ *     mask       (B,K) int64, 0 = invalid proposal (data_dict["bbox_mask"])
+ *     targets    (B,T) int64 target proposal ids, or NULL: T must be K and target t is box t
+ *     corner_mode   1: query_mode "corner" (min over the target's 8 corners), 0: "center"
+ *     include_self  1: D[target] = 0, 0: D[target] = 1e30   (applied after the other masks)
+ *     iou_threshold CONF.TRAIN.OVERLAID_THRESHOLD (0.5)
+ *     adjacent   (B,T,K) f32 out, exactly num_locals ones per row
+ *     neighbours (B,T,num_locals) int32 out (may be NULL): the selected ids in ascending order
+ *   Distances are float64 like the reference's; ties (only the 1e30 sentinels in practice) go to
+ *   the smaller index (torch.topk leaves them implementation-defined).  K <= 1024.
+ * ---------------------------------------------------------------------------------------- */
+S2C_API int s2c_knn_adjacency(const double *corners, const long long *mask, const long long *targets, int B,
+                              int K, int T, int num_locals, int corner_mode, int include_self,
+                              double iou_threshold, float *adjacent, int *neighbours, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

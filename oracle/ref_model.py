@@ -1,0 +1,745 @@
+"""TEST INFRASTRUCTURE ONLY -- literal PyTorch restatement of the reference's Python layers of the hot path.
+
+Nothing under scan2cap_b200/ imports this file.  It exists so that (a) the product (fused, batched, sync-free)
+can be checked against the reference's own op-by-op arithmetic on the GPU box, where /root/reference does not
+exist, and (b) `bench.py --impl reference` / `cpu_baseline` have the reference's stock code path to time:
+unfused Conv2d -> BatchNorm2d -> ReLU -> max_pool2d, the 256-iteration adjacency loop, per-scene graphs,
+per-scene .item() target selection, map_feat recomputed at every decoder step.
+
+Every class cites the reference lines it follows.  Deviations from the reference text, all forced:
+  * hard-coded ``.cuda()`` calls become ``.to(<input device>)`` so the same code runs on CPU and GPU;
+  * the native ops come from a pluggable backend (``set_backend``): the reference's own CUDA kernels
+    (oracle/_ref/pointnet2_ref_ext.so) on a GPU, the C oracle (oracle/native.py) on CPU;
+  * torch_geometric (absent here, version unpinned by the reference) is restated: EdgeConv.propagate is
+    gather x[col] / x[row] -> message -> index_add_ at col, and from_scipy_sparse_matrix is stack([row, col])
+    of the COO matrix (scipy itself is used as in the reference).
+
+Parity status: the graph / caption / loss part is PINNED against the reference's own modules imported from
+/root/reference (oracle/validate_vs_reference.py, fixtures in tests/golden/ref_python_*.npz); PyG's EdgeConv
+itself is "parity unpinned" (no reference test or vector exists for it).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from scipy.sparse import coo_matrix
+from torch.autograd import Function
+
+# ------------------------------------------------------------------------------------------- backend
+_BACKEND = None
+
+
+class _NumpyBackend(object):
+    """C oracle (CPU) behind the reference's _ext function names."""
+
+    def __init__(self):
+        from . import native
+        self.n = native
+
+    def _t(self, a, like):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(like.device)
+
+    def __getattr__(self, name):
+        fn = getattr(self.n, name)
+
+        def call(*args):
+            like = next(a for a in args if isinstance(a, torch.Tensor))
+            out = fn(*[a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a for a in args])
+            if isinstance(out, tuple):
+                return [self._t(o, like) for o in out]
+            return self._t(out, like)
+        return call
+
+
+def set_backend(ext=None):
+    """ext: a module with the nine pointnet2._ext functions (e.g. the reference extension) or None = C oracle."""
+    global _BACKEND
+    _BACKEND = ext if ext is not None else _NumpyBackend()
+
+
+def _ext():
+    if _BACKEND is None:
+        set_backend(None)
+    return _BACKEND
+
+
+# --------------------------------------------------------------- lib/pointnet2/pointnet2_utils.py:51-291
+class FurthestPointSampling(Function):
+    @staticmethod
+    def forward(ctx, xyz, npoint):
+        inds = _ext().furthest_point_sampling(xyz, npoint)
+        ctx.mark_non_differentiable(inds)
+        return inds
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return None, None
+
+
+class GatherOperation(Function):
+    @staticmethod
+    def forward(ctx, features, idx):
+        ctx.for_backwards = (idx, features.size(1), features.size(2))
+        return _ext().gather_points(features, idx)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, C, N = ctx.for_backwards
+        return _ext().gather_points_grad(grad_out.contiguous(), idx, N), None
+
+
+class ThreeNN(Function):
+    @staticmethod
+    def forward(ctx, unknown, known):
+        dist2, idx = _ext().three_nn(unknown, known)
+        return torch.sqrt(dist2), idx
+
+    @staticmethod
+    def backward(ctx, a=None, b=None):
+        return None, None
+
+
+class ThreeInterpolate(Function):
+    @staticmethod
+    def forward(ctx, features, idx, weight):
+        ctx.saved = (idx, weight, features.size(2))
+        return _ext().three_interpolate(features, idx, weight)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, weight, m = ctx.saved
+        return _ext().three_interpolate_grad(grad_out.contiguous(), idx, weight, m), None, None
+
+
+class GroupingOperation(Function):
+    @staticmethod
+    def forward(ctx, features, idx):
+        ctx.for_backwards = (idx, features.size(2))
+        return _ext().group_points(features, idx)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, N = ctx.for_backwards
+        return _ext().group_points_grad(grad_out.contiguous(), idx, N), None
+
+
+class BallQuery(Function):
+    @staticmethod
+    def forward(ctx, radius, nsample, xyz, new_xyz):
+        inds = _ext().ball_query(new_xyz, xyz, radius, nsample)
+        ctx.mark_non_differentiable(inds)
+        return inds
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return None, None, None, None
+
+
+furthest_point_sample = FurthestPointSampling.apply
+gather_operation = GatherOperation.apply
+three_nn = ThreeNN.apply
+three_interpolate = ThreeInterpolate.apply
+grouping_operation = GroupingOperation.apply
+ball_query = BallQuery.apply
+
+
+# torch's CUDA `tensor /= python_scalar` multiplies by the fp32 reciprocal (ATen div_true_kernel_cuda), its CPU
+# kernel divides.  The reference only ever runs on CUDA, so the oracle multiplies by the reciprocal on every
+# device (pointnet2_utils.py:352); validate_vs_reference.py flips this to compare with the reference on CPU.
+NORMALIZE_BY_RECIPROCAL = True
+
+
+class QueryAndGroup(nn.Module):  # pointnet2_utils.py:294-376 (sample_uniformly=False)
+    def __init__(self, radius, nsample, use_xyz=True, ret_grouped_xyz=False, normalize_xyz=False):
+        super().__init__()
+        self.radius, self.nsample, self.use_xyz = radius, nsample, use_xyz
+        self.ret_grouped_xyz, self.normalize_xyz = ret_grouped_xyz, normalize_xyz
+
+    def forward(self, xyz, new_xyz, features=None):
+        idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
+        xyz_trans = xyz.transpose(1, 2).contiguous()
+        grouped_xyz = grouping_operation(xyz_trans, idx)
+        grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)
+        if self.normalize_xyz:
+            if NORMALIZE_BY_RECIPROCAL:
+                grouped_xyz = grouped_xyz * torch.tensor(np.float32(1.0) / np.float32(self.radius), device=xyz.device)
+            else:
+                grouped_xyz = grouped_xyz / self.radius
+        if features is not None:
+            grouped_features = grouping_operation(features, idx)
+            new_features = torch.cat([grouped_xyz, grouped_features], dim=1) if self.use_xyz else grouped_features
+        else:
+            new_features = grouped_xyz
+        return (new_features, grouped_xyz) if self.ret_grouped_xyz else new_features
+
+
+# --------------------------------------------------------------- lib/pointnet2/pytorch_utils.py:11-188
+class _BN2d(nn.Sequential):
+    def __init__(self, c):
+        super().__init__()
+        self.add_module("bn", nn.BatchNorm2d(c))
+
+
+class _Conv2d(nn.Sequential):
+    def __init__(self, cin, cout, bn=True):
+        super().__init__()
+        conv = nn.Conv2d(cin, cout, kernel_size=(1, 1), bias=not bn)
+        nn.init.kaiming_normal_(conv.weight)
+        self.add_module("conv", conv)
+        if bn:
+            self.add_module("bn", _BN2d(cout))
+        self.add_module("activation", nn.ReLU(inplace=True))
+
+
+class SharedMLP(nn.Sequential):
+    def __init__(self, args, bn=True):
+        super().__init__()
+        for i in range(len(args) - 1):
+            self.add_module("layer{}".format(i), _Conv2d(args[i], args[i + 1], bn=bn))
+
+
+# --------------------------------------------------------------- lib/pointnet2/pointnet2_modules.py:164-272, 356-416
+class PointnetSAModuleVotes(nn.Module):
+    def __init__(self, *, mlp, npoint, radius, nsample, use_xyz=True, normalize_xyz=False):
+        super().__init__()
+        self.npoint, self.radius, self.nsample = npoint, radius, nsample
+        self.grouper = QueryAndGroup(radius, nsample, use_xyz=use_xyz, ret_grouped_xyz=True, normalize_xyz=normalize_xyz)
+        mlp_spec = list(mlp)
+        if use_xyz and len(mlp_spec) > 0:
+            mlp_spec[0] += 3
+        self.mlp_module = SharedMLP(mlp_spec, bn=True)
+
+    def forward(self, xyz, features=None, inds=None):
+        xyz_flipped = xyz.transpose(1, 2).contiguous()
+        if inds is None:
+            inds = furthest_point_sample(xyz, self.npoint)
+        new_xyz = gather_operation(xyz_flipped, inds).transpose(1, 2).contiguous()
+        grouped_features, grouped_xyz = self.grouper(xyz, new_xyz, features)
+        new_features = self.mlp_module(grouped_features)
+        new_features = F.max_pool2d(new_features, kernel_size=[1, new_features.size(3)])
+        return new_xyz, new_features.squeeze(-1), inds
+
+
+class PointnetFPModule(nn.Module):
+    def __init__(self, *, mlp):
+        super().__init__()
+        self.mlp = SharedMLP(mlp, bn=True)
+
+    def forward(self, unknown, known, unknow_feats, known_feats):
+        dist, idx = three_nn(unknown, known)
+        dist_recip = 1.0 / (dist + 1e-8)
+        norm = torch.sum(dist_recip, dim=2, keepdim=True)
+        weight = dist_recip / norm
+        interpolated_feats = three_interpolate(known_feats, idx, weight)
+        new_features = torch.cat([interpolated_feats, unknow_feats], dim=1) if unknow_feats is not None else interpolated_feats
+        return self.mlp(new_features.unsqueeze(-1)).squeeze(-1)
+
+
+# --------------------------------------------------------------- models/backbone_module.py:11-128
+class Pointnet2Backbone(nn.Module):
+    def __init__(self, input_feature_dim=0):
+        super().__init__()
+        self.sa1 = PointnetSAModuleVotes(npoint=2048, radius=0.2, nsample=64, mlp=[input_feature_dim, 64, 64, 128], normalize_xyz=True)
+        self.sa2 = PointnetSAModuleVotes(npoint=1024, radius=0.4, nsample=32, mlp=[128, 128, 128, 256], normalize_xyz=True)
+        self.sa3 = PointnetSAModuleVotes(npoint=512, radius=0.8, nsample=16, mlp=[256, 128, 128, 256], normalize_xyz=True)
+        self.sa4 = PointnetSAModuleVotes(npoint=256, radius=1.2, nsample=16, mlp=[256, 128, 128, 256], normalize_xyz=True)
+        self.fp1 = PointnetFPModule(mlp=[256 + 256, 256, 256])
+        self.fp2 = PointnetFPModule(mlp=[256 + 256, 256, 256])
+
+    def forward(self, data_dict):
+        pc = data_dict["point_clouds"]
+        xyz = pc[..., :3].contiguous()
+        features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
+        xyz, features, fps_inds = self.sa1(xyz, features)
+        data_dict["sa1_inds"], data_dict["sa1_xyz"], data_dict["sa1_features"] = fps_inds, xyz, features
+        xyz, features, fps_inds = self.sa2(xyz, features)
+        data_dict["sa2_inds"], data_dict["sa2_xyz"], data_dict["sa2_features"] = fps_inds, xyz, features
+        xyz, features, fps_inds = self.sa3(xyz, features)
+        data_dict["sa3_xyz"], data_dict["sa3_features"] = xyz, features
+        xyz, features, fps_inds = self.sa4(xyz, features)
+        data_dict["sa4_xyz"], data_dict["sa4_features"] = xyz, features
+        features = self.fp1(data_dict["sa3_xyz"], data_dict["sa4_xyz"], data_dict["sa3_features"], data_dict["sa4_features"])
+        features = self.fp2(data_dict["sa2_xyz"], data_dict["sa3_xyz"], data_dict["sa2_features"], features)
+        data_dict["fp2_features"] = features
+        data_dict["fp2_xyz"] = data_dict["sa2_xyz"]
+        num_seed = data_dict["fp2_xyz"].shape[1]
+        data_dict["fp2_inds"] = data_dict["sa1_inds"][:, 0:num_seed]
+        return data_dict
+
+
+# --------------------------------------------------------------- models/voting_module.py:9-60
+class VotingModule(nn.Module):
+    def __init__(self, vote_factor, seed_feature_dim):
+        super().__init__()
+        self.vote_factor, self.in_dim, self.out_dim = vote_factor, seed_feature_dim, seed_feature_dim
+        self.conv1 = nn.Conv1d(self.in_dim, self.in_dim, 1)
+        self.conv2 = nn.Conv1d(self.in_dim, self.in_dim, 1)
+        self.conv3 = nn.Conv1d(self.in_dim, (3 + self.out_dim) * self.vote_factor, 1)
+        self.bn1 = nn.BatchNorm1d(self.in_dim)
+        self.bn2 = nn.BatchNorm1d(self.in_dim)
+
+    def forward(self, seed_xyz, seed_features):
+        batch_size, num_seed = seed_xyz.shape[0], seed_xyz.shape[1]
+        num_vote = num_seed * self.vote_factor
+        net = F.relu(self.bn1(self.conv1(seed_features)))
+        net = F.relu(self.bn2(self.conv2(net)))
+        net = self.conv3(net)
+        net = net.transpose(2, 1).view(batch_size, num_seed, self.vote_factor, 3 + self.out_dim)
+        offset = net[:, :, :, 0:3]
+        vote_xyz = seed_xyz.contiguous().unsqueeze(2) + offset.contiguous()
+        vote_xyz = vote_xyz.contiguous().view(batch_size, num_vote, 3)
+        residual_features = net[:, :, :, 3:]
+        vote_features = seed_features.transpose(2, 1).unsqueeze(2) + residual_features
+        vote_features = vote_features.contiguous().view(batch_size, num_vote, self.out_dim)
+        return vote_xyz, vote_features.transpose(2, 1).contiguous()
+
+
+# --------------------------------------------------------------- utils/box_util.py:183-248, 323-383
+def box3d_iou_batch_tensor(corners1, corners2):
+    def mm(c):
+        mn, _ = c.min(dim=1)
+        mx, _ = c.max(dim=1)
+        return mn[:, 0], mx[:, 0], mn[:, 1], mx[:, 1], mn[:, 2], mx[:, 2]
+    x_min_1, x_max_1, y_min_1, y_max_1, z_min_1, z_max_1 = mm(corners1)
+    x_min_2, x_max_2, y_min_2, y_max_2, z_min_2, z_max_2 = mm(corners2)
+    xA, yA, zA = torch.max(x_min_1, x_min_2), torch.max(y_min_1, y_min_2), torch.max(z_min_1, z_min_2)
+    xB, yB, zB = torch.min(x_max_1, x_max_2), torch.min(y_max_1, y_max_2), torch.min(z_max_1, z_max_2)
+    zeros = corners1.new_zeros(xA.shape)
+    inter_vol = torch.max((xB - xA), zeros) * torch.max((yB - yA), zeros) * torch.max((zB - zA), zeros)
+    box_vol_1 = (x_max_1 - x_min_1) * (y_max_1 - y_min_1) * (z_max_1 - z_min_1)
+    box_vol_2 = (x_max_2 - x_min_2) * (y_max_2 - y_min_2) * (z_max_2 - z_min_2)
+    return inter_vol / (box_vol_1 + box_vol_2 - inter_vol + 1e-8)
+
+
+def roty_batch(t):
+    out = np.zeros(tuple(list(t.shape) + [3, 3]))
+    c, s = np.cos(t), np.sin(t)
+    out[..., 0, 0] = c
+    out[..., 0, 2] = s
+    out[..., 1, 1] = 1
+    out[..., 2, 0] = -s
+    out[..., 2, 2] = c
+    return out
+
+
+def get_3d_box_batch(box_size, heading_angle, center):
+    input_shape = heading_angle.shape
+    R = roty_batch(heading_angle)
+    l = np.expand_dims(box_size[..., 0], -1)
+    w = np.expand_dims(box_size[..., 1], -1)
+    h = np.expand_dims(box_size[..., 2], -1)
+    corners_3d = np.zeros(tuple(list(input_shape) + [8, 3]))
+    corners_3d[..., :, 0] = np.concatenate((l / 2, l / 2, -l / 2, -l / 2, l / 2, l / 2, -l / 2, -l / 2), -1)
+    corners_3d[..., :, 1] = np.concatenate((w / 2, -w / 2, -w / 2, w / 2, w / 2, -w / 2, -w / 2, w / 2), -1)
+    corners_3d[..., :, 2] = np.concatenate((h / 2, h / 2, h / 2, h / 2, -h / 2, -h / 2, -h / 2, -h / 2), -1)
+    tlist = [i for i in range(len(input_shape))] + [len(input_shape) + 1, len(input_shape)]
+    corners_3d = np.matmul(corners_3d, np.transpose(R, tuple(tlist)))
+    corners_3d += np.expand_dims(center, -2)
+    return corners_3d
+
+
+# --------------------------------------------------------------- models/proposal_module.py:21-144
+class ProposalModule(nn.Module):
+    def __init__(self, num_class, num_heading_bin, num_size_cluster, mean_size_arr, num_proposal, sampling, seed_feat_dim=256):
+        super().__init__()
+        self.num_class, self.num_heading_bin, self.num_size_cluster = num_class, num_heading_bin, num_size_cluster
+        self.mean_size_arr, self.num_proposal = mean_size_arr, num_proposal
+        self.vote_aggregation = PointnetSAModuleVotes(npoint=num_proposal, radius=0.3, nsample=16,
+                                                      mlp=[seed_feat_dim, 128, 128, 128], normalize_xyz=True)
+        self.proposal = nn.Sequential(
+            nn.Conv1d(128, 128, 1, bias=False), nn.BatchNorm1d(128), nn.ReLU(),
+            nn.Conv1d(128, 128, 1, bias=False), nn.BatchNorm1d(128), nn.ReLU(),
+            nn.Conv1d(128, 2 + 3 + num_heading_bin * 2 + num_size_cluster * 4 + num_class, 1))
+
+    def forward(self, xyz, features, data_dict):
+        xyz, features, fps_inds = self.vote_aggregation(xyz, features)
+        data_dict["aggregated_vote_xyz"] = xyz
+        data_dict["aggregated_vote_features"] = features.permute(0, 2, 1).contiguous()
+        data_dict["aggregated_vote_inds"] = fps_inds
+        net = self.proposal(features)
+        return self.decode_scores(net, data_dict)
+
+    def decode_pred_box(self, data_dict):  # :80-103 -- device -> numpy float64 -> device
+        dev = data_dict["center"].device
+        pred_center = data_dict["center"].detach().cpu().numpy()
+        pred_size_class = torch.argmax(data_dict["size_scores"], -1)
+        pred_size_residual = torch.gather(data_dict["size_residuals"], 2,
+                                          pred_size_class.unsqueeze(-1).unsqueeze(-1).repeat(1, 1, 1, 3))
+        pred_size_class = pred_size_class.detach().cpu().numpy()
+        pred_size_residual = pred_size_residual.squeeze(2).detach().cpu().numpy()
+        out = []
+        for i in range(pred_center.shape[0]):
+            n = pred_center.shape[1]
+            obb = np.zeros((n, 7))
+            obb[:, 0:3] = pred_center[i, :, 0:3]
+            obb[:, 3:6] = self.mean_size_arr[pred_size_class[i]] + pred_size_residual[i]
+            obb[:, 6] = np.zeros(n) * -1
+            out.append(torch.from_numpy(get_3d_box_batch(obb[:, 3:6], obb[:, 6], obb[:, 0:3])).to(dev).unsqueeze(0))
+        return torch.cat(out, dim=0)
+
+    def decode_scores(self, net, data_dict):
+        NH, NS = self.num_heading_bin, self.num_size_cluster
+        net_transposed = net.transpose(2, 1).contiguous()
+        batch_size, num_proposal = net_transposed.shape[0], net_transposed.shape[1]
+        objectness_scores = net_transposed[:, :, 0:2]
+        center = data_dict["aggregated_vote_xyz"] + net_transposed[:, :, 2:5]
+        data_dict["objectness_scores"] = objectness_scores
+        data_dict["center"] = center
+        data_dict["heading_scores"] = net_transposed[:, :, 5:5 + NH]
+        hrn = net_transposed[:, :, 5 + NH:5 + NH * 2]
+        data_dict["heading_residuals_normalized"] = hrn
+        data_dict["heading_residuals"] = hrn * (np.pi / NH)
+        data_dict["size_scores"] = net_transposed[:, :, 5 + NH * 2:5 + NH * 2 + NS]
+        srn = net_transposed[:, :, 5 + NH * 2 + NS:5 + NH * 2 + NS * 4].view([batch_size, num_proposal, NS, 3])
+        data_dict["size_residuals_normalized"] = srn
+        data_dict["size_residuals"] = srn * torch.from_numpy(self.mean_size_arr.astype(np.float32)).to(net.device).unsqueeze(0).unsqueeze(0)
+        sem = net_transposed[:, :, 5 + NH * 2 + NS * 4:]
+        data_dict["sem_cls_scores"] = sem
+        data_dict["bbox_corner"] = self.decode_pred_box(data_dict)
+        data_dict["bbox_feature"] = data_dict["aggregated_vote_features"]
+        data_dict["bbox_mask"] = objectness_scores.argmax(-1)
+        data_dict["bbox_sems"] = sem.argmax(-1)
+        data_dict["sem_cls"] = sem.argmax(-1)
+        return data_dict
+
+
+# --------------------------------------------------------------- models/graph_module.py:22-316
+OVERLAID_THRESHOLD = 0.5   # lib/config.py:65
+MIN_IOU_THRESHOLD = 0.25   # lib/config.py:66
+MAX_DES_LEN = 30           # lib/config.py:63
+
+
+class EdgeConv(nn.Module):
+    """graph_module.py:22-115 on top of PyG MessagePassing(aggr), flow source_to_target:
+    x_j = x[edge_index[0]], x_i = x[edge_index[1]], aggregation index = edge_index[1]."""
+
+    def __init__(self, in_size, out_size, aggregation="add"):
+        super().__init__()
+        assert aggregation == "add"
+        self.map_edge = nn.Sequential(nn.Linear(2 * in_size, out_size), nn.ReLU(), nn.Linear(out_size, out_size))
+
+    def forward(self, x, edge_index):
+        x_j, x_i = x[edge_index[0]], x[edge_index[1]]
+        message = self.map_edge(torch.cat([x_i, x_j - x_i], dim=1))
+        out = torch.zeros(x.shape[0], message.shape[1], dtype=message.dtype, device=x.device)
+        out = out.index_add(0, edge_index[1], message)
+        return out, message
+
+
+def _nn_distance_dense(pc1, pc2):  # graph_module.py:154-174
+    N, M = pc1.shape[1], pc2.shape[1]
+    pc_diff = pc1.unsqueeze(2).repeat(1, 1, M, 1) - pc2.unsqueeze(1).repeat(1, N, 1, 1)
+    return torch.sqrt(torch.sum(pc_diff ** 2, dim=-1) + 1e-8)
+
+
+def query_locals(corners, num_proposals, num_locals, query_mode, target_ids, object_masks, include_self=True,
+                 overlay_threshold=OVERLAID_THRESHOLD):
+    """graph_module.py:182-222 == caption_module.py:339-381."""
+    coord_min = torch.min(corners, dim=2)[0]
+    coord_max = torch.max(corners, dim=2)[0]
+    centers = (coord_min + coord_max) / 2
+    batch_size = centers.shape[0]
+    target_centers = torch.gather(centers, 1, target_ids.view(-1, 1, 1).repeat(1, 1, 3))
+    target_corners = torch.gather(corners, 1, target_ids.view(-1, 1, 1, 1).repeat(1, 1, 8, 3))
+    if query_mode == "center":
+        pc_dist = _nn_distance_dense(target_centers, centers).squeeze(1)
+    elif query_mode == "corner":
+        pc_dist = _nn_distance_dense(target_corners.squeeze(1), centers)
+        pc_dist, _ = torch.min(pc_dist, dim=1)
+    else:
+        raise ValueError("invalid distance mode")
+    pc_dist.masked_fill_(object_masks == 0, float("1e30"))
+    iou = box3d_iou_batch_tensor(target_corners.repeat(1, num_proposals, 1, 1).view(-1, 8, 3),
+                                 corners.view(-1, 8, 3)).view(batch_size, num_proposals)
+    pc_dist.masked_fill_(iou >= overlay_threshold, float("1e30"))
+    self_dist = 0 if include_self else float("1e30")
+    self_masks = torch.zeros(batch_size, num_proposals, device=corners.device)
+    self_masks.scatter_(1, target_ids.view(-1, 1), 1)
+    pc_dist.masked_fill_(self_masks == 1, self_dist)
+    _, topk_ids = torch.topk(pc_dist, num_locals, largest=False, dim=1)
+    local_masks = torch.zeros(batch_size, num_proposals, device=corners.device)
+    local_masks.scatter_(1, topk_ids, 1)
+    return local_masks
+
+
+class GraphModule(nn.Module):
+    def __init__(self, in_size, out_size, num_layers, num_proposals, feat_size, num_locals, query_mode="corner",
+                 graph_mode="edge_conv", return_edge=False, graph_aggr="add", return_orientation=False, num_bins=6,
+                 return_distance=False):
+        super().__init__()
+        assert graph_mode == "edge_conv"
+        self.in_size, self.out_size, self.num_proposals, self.feat_size = in_size, out_size, num_proposals, feat_size
+        self.num_locals, self.query_mode, self.num_bins = num_locals, query_mode, num_bins
+        self.return_orientation = return_orientation
+        self.gc_layers = nn.ModuleList([EdgeConv(in_size, out_size, graph_aggr) for _ in range(num_layers)])
+        if return_orientation:
+            self.edge_layer = EdgeConv(in_size, out_size, graph_aggr)
+            self.edge_predict = nn.Linear(out_size, num_bins + 1)
+
+    def _create_adjacent_mat(self, data_dict, object_masks):  # :224-233, the 256-iteration loop
+        batch_size, num_objects = object_masks.shape
+        dev = object_masks.device
+        adjacent_mat = torch.zeros(batch_size, num_objects, num_objects, device=dev)
+        for obj_id in range(num_objects):
+            target_ids = torch.LongTensor([obj_id for _ in range(batch_size)]).to(dev)
+            adjacent_mat[:, obj_id] = query_locals(data_dict["bbox_corner"], self.num_proposals, self.num_locals,
+                                                   self.query_mode, target_ids, object_masks, include_self=False)
+        return adjacent_mat
+
+    def forward(self, data_dict):  # :247-316
+        obj_feats = data_dict["bbox_feature"]
+        object_masks = data_dict["bbox_mask"]
+        dev = obj_feats.device
+        batch_size, num_objects, _ = obj_feats.shape
+        adjacent_mat = self._create_adjacent_mat(data_dict, object_masks)
+        new_obj_feats = torch.zeros(batch_size, num_objects, self.feat_size, device=dev)
+        edge_indices = torch.zeros(batch_size, 2, num_objects * self.num_locals, device=dev)
+        edge_feats = torch.zeros(batch_size, num_objects, self.num_locals, self.out_size, device=dev)
+        edge_preds = torch.zeros(batch_size, num_objects * self.num_locals, self.num_bins + 1, device=dev)
+        num_sources = torch.zeros(batch_size, device=dev).long()
+        num_targets = torch.zeros(batch_size, device=dev).long()
+        for batch_id in range(batch_size):
+            batch_object_masks = object_masks[batch_id]
+            batch_adjacent_mat = adjacent_mat[batch_id]
+            batch_adjacent_mat = batch_adjacent_mat[batch_object_masks == 1, :][:, batch_object_masks == 1]
+            sparse_mat = coo_matrix(batch_adjacent_mat.detach().cpu().numpy())
+            batch_edge_index = torch.from_numpy(np.vstack([sparse_mat.row, sparse_mat.col])).long().to(dev)
+            batch_obj_feats = obj_feats[batch_id, batch_object_masks == 1]
+            node_feat, edge_feat = batch_obj_feats, None
+            for layer in self.gc_layers:
+                node_feat, edge_feat = layer(node_feat, batch_edge_index)
+            if self.return_orientation:
+                try:
+                    num_src_objects = len(set(batch_edge_index[0].cpu().numpy()))
+                    num_tar_objects = int(edge_feat.shape[0] / num_src_objects)
+                    num_sources[batch_id] = num_src_objects
+                    num_targets[batch_id] = num_tar_objects
+                    edge_feat = edge_feat[:num_src_objects * num_tar_objects]
+                    edge_feats[batch_id, :num_src_objects, :num_tar_objects] = edge_feat.view(num_src_objects, num_tar_objects, self.out_size)
+                    edge_indices[batch_id, :, :num_src_objects * num_tar_objects] = batch_edge_index[:, :num_src_objects * num_tar_objects]
+                    _, edge_feat = self.edge_layer(node_feat, batch_edge_index)
+                    edge_pred = self.edge_predict(edge_feat)
+                    edge_preds[batch_id, :num_src_objects * num_tar_objects] = edge_pred
+                except Exception:
+                    pass  # the reference prints "error occurs when dealing with graph, skipping..." (:299-300)
+            batch_obj_feats = batch_obj_feats + node_feat
+            new_obj_feats[batch_id, batch_object_masks == 1] = batch_obj_feats
+        data_dict["bbox_feature"] = new_obj_feats
+        data_dict["adjacent_mat"] = adjacent_mat
+        data_dict["edge_index"] = edge_indices
+        data_dict["edge_feature"] = edge_feats
+        data_dict["num_edge_source"] = num_sources
+        data_dict["num_edge_target"] = num_targets
+        data_dict["edge_orientations"] = edge_preds[:, :, :-1]
+        data_dict["edge_distances"] = edge_preds[:, :, -1]
+        return data_dict
+
+
+# --------------------------------------------------------------- models/caption_module.py:16-38, 202-592
+def select_target(data_dict):
+    pred_bbox = data_dict["bbox_corner"]
+    batch_size, num_proposals, _, _ = pred_bbox.shape
+    gt_bbox = data_dict["ref_box_corner_label"]
+    target_ids, target_ious = [], []
+    for i in range(batch_size):
+        gt = gt_bbox[i].unsqueeze(0).repeat(num_proposals, 1, 1)
+        ious = box3d_iou_batch_tensor(pred_bbox[i], gt)
+        target_id = ious.argmax().item()
+        target_ids.append(target_id)
+        target_ious.append(ious[target_id])
+    dev = pred_bbox.device
+    return torch.LongTensor(target_ids).to(dev), torch.FloatTensor(target_ious).to(dev)
+
+
+class TopDownSceneCaptionModule(nn.Module):
+    def __init__(self, vocabulary, embeddings, emb_size=300, feat_size=128, hidden_size=512, num_proposals=256,
+                 num_locals=-1, query_mode="corner", use_relation=False, use_oracle=False):
+        super().__init__()
+        self.vocabulary, self.embeddings = vocabulary, embeddings
+        self.num_vocabs = len(vocabulary["word2idx"])
+        self.emb_size, self.feat_size, self.hidden_size = emb_size, feat_size, hidden_size
+        self.num_proposals, self.num_locals, self.query_mode = num_proposals, num_locals, query_mode
+        self.use_relation, self.use_oracle = use_relation, use_oracle
+        self.map_topdown = nn.Sequential(nn.Linear(hidden_size + feat_size + emb_size, emb_size), nn.ReLU())
+        self.recurrent_cell_1 = nn.GRUCell(input_size=emb_size, hidden_size=hidden_size)
+        self.map_feat = nn.Linear(feat_size, hidden_size, bias=False)
+        self.map_hidd = nn.Linear(hidden_size, hidden_size, bias=False)
+        self.attend = nn.Linear(hidden_size, 1, bias=False)
+        self.map_lang = nn.Sequential(nn.Linear(feat_size + hidden_size, emb_size), nn.ReLU())
+        self.recurrent_cell_2 = nn.GRUCell(input_size=emb_size, hidden_size=hidden_size)
+        self.classifier = nn.Linear(hidden_size, self.num_vocabs)
+
+    def _step(self, step_input, target_feat, obj_feats, hidden_1, hidden_2, object_masks):  # :250-292
+        step_input = torch.cat([step_input, hidden_2, target_feat], dim=-1)
+        step_input = self.map_topdown(step_input)
+        hidden_1 = self.recurrent_cell_1(step_input, hidden_1)
+        combined = self.map_feat(obj_feats)
+        combined = combined + self.map_hidd(hidden_1).unsqueeze(1)
+        combined = torch.tanh(combined)
+        scores = self.attend(combined)
+        scores = scores.masked_fill(object_masks == 0, float("-1e30"))
+        masks = F.softmax(scores, dim=1)
+        attended = (obj_feats * masks).sum(1)
+        lang_input = self.map_lang(torch.cat([attended, hidden_1], dim=-1))
+        hidden_2 = self.recurrent_cell_2(lang_input, hidden_2)
+        return hidden_1, hidden_2, masks
+
+    def _query_locals(self, data_dict, target_ids, object_masks, include_self=True):
+        return query_locals(data_dict["bbox_corner"], self.num_proposals, self.num_locals, self.query_mode,
+                            target_ids, object_masks, include_self)
+
+    def _add_relation_feat(self, data_dict, obj_feats, target_ids):  # :394-414
+        rel_feats = data_dict["edge_feature"]
+        batch_size = rel_feats.shape[0]
+        rel_feats = torch.gather(rel_feats, 1, target_ids.view(batch_size, 1, 1, 1).repeat(1, 1, self.num_locals, self.feat_size)).squeeze(1)
+        adjacent_mat = data_dict["adjacent_mat"]
+        rel_indices = torch.gather(adjacent_mat, 1, target_ids.view(batch_size, 1, 1).repeat(1, 1, self.num_proposals)).squeeze(1)
+        rel_masks = rel_indices.unsqueeze(-1).repeat(1, 1, self.feat_size) == 1
+        scattered = torch.zeros(obj_feats.shape, device=obj_feats.device).masked_scatter(rel_masks, rel_feats)
+        return obj_feats + scattered
+
+    def forward(self, data_dict, use_tf=True, is_eval=False, max_len=MAX_DES_LEN):
+        if not is_eval:
+            return self._forward_sample_batch(data_dict, max_len)
+        return self._forward_scene_batch(data_dict, use_tf, max_len)
+
+    def _forward_sample_batch(self, data_dict, max_len=MAX_DES_LEN, min_iou=MIN_IOU_THRESHOLD):  # :428-500
+        word_embs = data_dict["lang_feat"]
+        des_lens = data_dict["lang_len"]
+        obj_feats = data_dict["bbox_feature"]
+        object_masks = data_dict["bbox_mask"]
+        dev = obj_feats.device
+        num_words = des_lens.max()
+        batch_size = des_lens.shape[0]
+        if self.use_oracle:
+            target_ids = data_dict["bbox_idx"]
+            target_ious = torch.ones(batch_size, device=dev)
+        else:
+            target_ids, target_ious = select_target(data_dict)
+        target_feats = torch.gather(obj_feats, 1, target_ids.view(batch_size, 1, 1).repeat(1, 1, self.feat_size)).squeeze(1)
+        valid_masks = object_masks if self.num_locals == -1 else self._query_locals(data_dict, target_ids, object_masks)
+        if self.use_relation:
+            obj_feats = self._add_relation_feat(data_dict, obj_feats, target_ids)
+        outputs, masks = [], []
+        hidden_1 = torch.zeros(batch_size, self.hidden_size, device=dev)
+        hidden_2 = torch.zeros(batch_size, self.hidden_size, device=dev)
+        step_id = 0
+        step_input = word_embs[:, step_id]
+        while True:
+            hidden_1, hidden_2, step_mask = self._step(step_input, target_feats, obj_feats, hidden_1, hidden_2, valid_masks.unsqueeze(-1))
+            outputs.append(self.classifier(hidden_2).unsqueeze(1))
+            masks.append(step_mask)
+            step_id += 1
+            if step_id == num_words - 1:
+                break
+            step_input = word_embs[:, step_id]
+        outputs = torch.cat(outputs, dim=1)
+        masks = torch.cat(masks, dim=-1)
+        good_bbox_masks = target_ious > min_iou
+        num_good_bboxes = good_bbox_masks.sum()
+        mean_target_ious = target_ious[good_bbox_masks].mean() if num_good_bboxes > 0 else torch.zeros(1, device=dev)[0]
+        data_dict["lang_cap"] = outputs
+        data_dict["pred_ious"] = mean_target_ious
+        data_dict["topdown_attn"] = masks
+        data_dict["valid_masks"] = valid_masks
+        data_dict["good_bbox_masks"] = good_bbox_masks
+        return data_dict
+
+    def _forward_scene_batch(self, data_dict, use_tf=False, max_len=MAX_DES_LEN):  # :502-592
+        word_embs = data_dict["lang_feat"]
+        obj_feats = data_dict["bbox_feature"]
+        dev = obj_feats.device
+        batch_size = word_embs.shape[0]
+        object_masks = data_dict["bbox_mask"]
+        outputs, masks, valid_masks = [], [], []
+        for prop_id in range(self.num_proposals):
+            target_feats = obj_feats[:, prop_id]
+            target_ids = torch.zeros(batch_size).fill_(prop_id).long().to(dev)
+            prop_obj_feats = obj_feats.clone()
+            valid_prop_masks = object_masks if self.num_locals == -1 else self._query_locals(data_dict, target_ids, object_masks)
+            if self.use_relation:
+                prop_obj_feats = self._add_relation_feat(data_dict, prop_obj_feats, target_ids)
+            valid_masks.append(valid_prop_masks.unsqueeze(1))
+            prop_outputs, prop_masks = [], []
+            hidden_1 = torch.zeros(batch_size, self.hidden_size, device=dev)
+            hidden_2 = torch.zeros(batch_size, self.hidden_size, device=dev)
+            step_id = 0
+            step_input = word_embs[:, 0]
+            while True:
+                hidden_1, hidden_2, step_mask = self._step(step_input, target_feats, prop_obj_feats, hidden_1, hidden_2, valid_prop_masks.unsqueeze(-1))
+                step_output = self.classifier(hidden_2)
+                step_preds = []
+                for batch_id in range(batch_size):
+                    idx = step_output[batch_id].argmax()
+                    word = self.vocabulary["idx2word"][str(idx.item())]
+                    step_preds.append(torch.FloatTensor(self.embeddings[word]).unsqueeze(0).to(dev))
+                step_preds = torch.cat(step_preds, dim=0)
+                prop_outputs.append(step_output.unsqueeze(1))
+                prop_masks.append(step_mask)
+                step_id += 1
+                if step_id == max_len - 1:
+                    break
+                step_input = step_preds
+            outputs.append(torch.cat(prop_outputs, dim=1).unsqueeze(1))
+            masks.append(torch.cat(prop_masks, dim=-1).unsqueeze(1))
+        data_dict["lang_cap"] = torch.cat(outputs, dim=1)
+        data_dict["topdown_attn"] = torch.cat(masks, dim=1)
+        data_dict["valid_masks"] = torch.cat(valid_masks, dim=1)
+        return data_dict
+
+
+# --------------------------------------------------------------- models/capnet.py:14-123, models/capnet_pretrained.py
+class CapNet(nn.Module):
+    def __init__(self, num_class, vocabulary, embeddings, num_heading_bin, num_size_cluster, mean_size_arr,
+                 input_feature_dim=0, num_proposal=256, num_locals=-1, vote_factor=1, sampling="vote_fps",
+                 no_caption=False, use_topdown=False, query_mode="corner", graph_mode="graph_conv",
+                 num_graph_steps=0, use_relation=False, graph_aggr="add", use_orientation=False, num_bins=6,
+                 use_distance=False, use_new=False, emb_size=300, hidden_size=512):
+        super().__init__()
+        self.no_caption, self.num_graph_steps = no_caption, num_graph_steps
+        self.backbone_net = Pointnet2Backbone(input_feature_dim=input_feature_dim)
+        self.vgen = VotingModule(vote_factor, 256)
+        self.proposal = ProposalModule(num_class, num_heading_bin, num_size_cluster, mean_size_arr, num_proposal, sampling)
+        if num_graph_steps > 0:
+            self.graph = GraphModule(128, 128, num_graph_steps, num_proposal, 128, num_locals, query_mode, graph_mode,
+                                     return_edge=use_relation, graph_aggr=graph_aggr,
+                                     return_orientation=use_orientation, num_bins=num_bins, return_distance=use_distance)
+        if not no_caption:
+            assert use_topdown, "only the top-down decoder is restated in the oracle"
+            self.caption = TopDownSceneCaptionModule(vocabulary, embeddings, emb_size, 128, hidden_size, num_proposal,
+                                                     num_locals, query_mode, use_relation)
+
+    def forward(self, data_dict, use_tf=True, is_eval=False):
+        data_dict = self.backbone_net(data_dict)
+        xyz, features = data_dict["fp2_xyz"], data_dict["fp2_features"]
+        data_dict["seed_inds"], data_dict["seed_xyz"], data_dict["seed_features"] = data_dict["fp2_inds"], xyz, features
+        xyz, features = self.vgen(xyz, features)
+        features_norm = torch.norm(features, p=2, dim=1)
+        features = features.div(features_norm.unsqueeze(1))
+        data_dict["vote_xyz"], data_dict["vote_features"] = xyz, features
+        data_dict = self.proposal(xyz, features, data_dict)
+        if self.num_graph_steps > 0:
+            data_dict = self.graph(data_dict)
+        if not self.no_caption:
+            data_dict = self.caption(data_dict, use_tf, is_eval)
+        return data_dict
+
+
+class CapNetPretrained(nn.Module):
+    def __init__(self, mode, vocabulary, embeddings, use_topdown=True, num_locals=-1, query_mode="corner",
+                 graph_mode="edge_conv", num_graph_steps=0, use_relation=False, graph_aggr="add",
+                 use_orientation=False, num_bins=6, use_distance=False, emb_size=300, hidden_size=512):
+        super().__init__()
+        self.num_graph_steps = num_graph_steps
+        self.num_proposals = 128 if mode == "gt" else 256
+        if num_graph_steps > 0:
+            self.graph = GraphModule(128, 128, num_graph_steps, self.num_proposals, 128, num_locals, query_mode,
+                                     graph_mode, return_edge=use_relation, graph_aggr=graph_aggr,
+                                     return_orientation=use_orientation, num_bins=num_bins, return_distance=use_distance)
+        self.caption = TopDownSceneCaptionModule(vocabulary, embeddings, emb_size, 128, hidden_size, self.num_proposals,
+                                                 num_locals, query_mode, use_relation, use_oracle=(mode == "gt"))
+
+    def forward(self, data_dict, use_tf=True, is_eval=False):
+        if self.num_graph_steps > 0:
+            data_dict = self.graph(data_dict)
+        return self.caption(data_dict, use_tf, is_eval)

@@ -1,0 +1,166 @@
+"""Mirror of models/graph_module.py: EdgeConv (:22-115) and GraphModule (:117-316), same constructor
+arguments, attribute names (gc_layers.{i}.map_edge.{0,2}, edge_layer.map_edge, edge_predict -> checkpoint keys)
+and ``data_dict`` outputs.
+
+How it is issued on the B200 (the reference runs a 256-iteration Python loop of tiny kernels for the
+adjacency, then one scipy round trip + one PyG graph per scene):
+  * the adjacency of all B*K targets is ONE kernel launch (s2c_knn_adjacency, float64 distances);
+  * all scenes form one batched graph over the B*K proposal slots with a fixed K*num_locals edge slots per
+    scene; invalid proposals / neighbours are masked instead of compacted, so there is no host
+    synchronisation, no data-dependent shape and the whole module can be captured in a CUDA graph;
+  * the reference's compacted (valid-object) numbering, which it exposes through ``edge_index`` /
+    ``edge_feature`` / ``num_edge_source`` / ``num_edge_target``, is reproduced with prefix sums,
+    including its quirks (graph_module.py:283-300): num_tar = int(E / num_src), truncation to
+    num_src*num_tar edges, and the swallowed exception that leaves ``edge_orientations`` zero when
+    E != num_src*num_tar or when a scene has no edge at all.
+torch_geometric is not needed: EdgeConv is restated from its definition (message = MLP([x_i, x_j - x_i]) with
+x_i = x[edge_index[1]], x_j = x[edge_index[0]], aggregated at edge_index[1]; PyG flow "source_to_target").
+graph_mode="graph_conv" (PyG GCNConv, whose arithmetic lives wholly inside torch_geometric) is out of scope.
+"""
+import torch
+import torch.nn as nn
+
+from ..lib.config import CONF
+from ..lib.pointnet2 import _ext_graph
+
+
+class EdgeConv(nn.Module):
+    def __init__(self, in_size, out_size, aggregation="add"):
+        super().__init__()
+        assert aggregation in ("add", "mean", "max")
+        self.in_size = in_size
+        self.out_size = out_size
+        self.aggr = aggregation
+        self.map_edge = nn.Sequential(nn.Linear(2 * in_size, out_size), nn.ReLU(), nn.Linear(out_size, out_size))
+
+    def message(self, x_i, x_j):
+        return self.map_edge(torch.cat([x_i, x_j - x_i], dim=1))
+
+    def forward(self, x, edge_index, edge_mask=None):
+        """x (N,in), edge_index (2,E) long, optional edge_mask (E) bool -> (out (N,out), message (E,out))."""
+        row, col = edge_index[0], edge_index[1]
+        msg = self.message(x.index_select(0, col), x.index_select(0, row))
+        if edge_mask is not None:
+            msg = msg * edge_mask.unsqueeze(-1).to(msg.dtype)
+        out = x.new_zeros(x.shape[0], self.out_size)
+        if self.aggr == "add":
+            out = out.index_add(0, col, msg)
+        elif self.aggr == "mean":
+            ones = torch.ones_like(col, dtype=msg.dtype) if edge_mask is None else edge_mask.to(msg.dtype)
+            deg = x.new_zeros(x.shape[0]).index_add(0, col, ones).clamp_min(1)
+            out = out.index_add(0, col, msg) / deg.unsqueeze(-1)
+        else:
+            src = msg if edge_mask is None else msg.masked_fill(~edge_mask.unsqueeze(-1), float("-inf"))
+            out = out.fill_(float("-inf")).scatter_reduce(0, col.unsqueeze(-1).expand_as(src), src, "amax")
+            out = torch.where(torch.isinf(out), torch.zeros_like(out), out)
+        return out, msg
+
+
+class GraphModule(nn.Module):
+    def __init__(self, in_size, out_size, num_layers, num_proposals, feat_size, num_locals, query_mode="corner",
+                 graph_mode="graph_conv", return_edge=False, graph_aggr="add", return_orientation=False,
+                 num_bins=6, return_distance=False):
+        super().__init__()
+        self.in_size = in_size
+        self.out_size = out_size
+        self.num_proposals = num_proposals
+        self.feat_size = feat_size
+        self.num_locals = num_locals
+        self.query_mode = query_mode
+        self.graph_mode = graph_mode
+        if graph_mode == "graph_conv":
+            raise NotImplementedError("graph_mode='graph_conv' relies on torch_geometric.nn.GCNConv; only "
+                                      "'edge_conv' (the mode of every documented Scan2Cap configuration) is built")
+        if graph_mode != "edge_conv":
+            raise ValueError("invalid graph mode, choices: [\"graph_conv\", \"edge_conv\"]")
+        if query_mode not in ("center", "corner"):
+            raise ValueError("invalid distance mode, choice: [\"center\", \"corner\"]")
+        self.gc_layers = nn.ModuleList([EdgeConv(in_size, out_size, graph_aggr) for _ in range(num_layers)])
+        self.return_edge = return_edge
+        self.return_orientation = return_orientation
+        self.return_distance = return_distance
+        self.num_bins = num_bins
+        if self.return_orientation:
+            self.edge_layer = EdgeConv(in_size, out_size, graph_aggr)
+            self.edge_predict = nn.Linear(out_size, num_bins + 1)
+
+    def _create_adjacent_mat(self, data_dict, object_masks):
+        """(B,K,K) float 0/1 and the (B,K,num_locals) ascending neighbour ids, one launch."""
+        return _ext_graph.knn_adjacency(data_dict["bbox_corner"], object_masks, None, self.num_locals,
+                                        self.query_mode == "corner", False, CONF.TRAIN.OVERLAID_THRESHOLD)
+
+    def forward(self, data_dict):
+        obj_feats = data_dict["bbox_feature"]  # (B,K,F)
+        object_masks = data_dict["bbox_mask"]  # (B,K) int64
+        B, K, _ = obj_feats.shape
+        L = self.num_locals
+        dev = obj_feats.device
+        adjacent_mat, nbr = self._create_adjacent_mat(data_dict, object_masks)
+        nbr = nbr.long()
+
+        valid = object_masks == 1  # (B,K)
+        # edge slot (i,t) = (target i, its t-th neighbour in ascending id): exists iff both ends are valid.
+        slot_valid = valid.unsqueeze(-1) & torch.gather(valid, 1, nbr.view(B, K * L)).view(B, K, L)
+        flat_valid = slot_valid.view(B, K * L)
+        base = (torch.arange(B, device=dev) * K).view(B, 1, 1)
+        row_g = (base + torch.arange(K, device=dev).view(1, K, 1)).expand(B, K, L).reshape(-1)
+        col_g = (base + nbr).reshape(-1)
+        edge_g = torch.stack([row_g, col_g], 0)
+        emask = flat_valid.reshape(-1)
+
+        x = obj_feats.reshape(B * K, -1)
+        node_feat, message = x, None
+        for layer in self.gc_layers:
+            node_feat, message = layer(node_feat, edge_g, emask)
+
+        edge_feats = obj_feats.new_zeros(B, K, L, self.out_size)
+        edge_indices = obj_feats.new_zeros(B, 2, K * L)
+        edge_preds = obj_feats.new_zeros(B, K * L, self.num_bins + 1)
+        num_sources = torch.zeros(B, dtype=torch.long, device=dev)
+        num_targets = torch.zeros(B, dtype=torch.long, device=dev)
+        if self.return_orientation:
+            # the reference's compacted numbering, with prefix sums instead of boolean indexing
+            compact = torch.cumsum(valid.long(), 1) - 1                     # (B,K) id among valid objects
+            epos = torch.cumsum(flat_valid.long(), 1) - 1                   # (B,K*L) edge rank, row-major
+            E = flat_valid.sum(1)                                           # (B)
+            num_src = slot_valid.any(-1).sum(1)                             # len(set(edge_index[0]))
+            ok_scene = num_src > 0                                          # else ZeroDivisionError -> skipped
+            num_tar = torch.where(ok_scene, E // num_src.clamp_min(1), torch.zeros_like(E))
+            kept = flat_valid & (epos < (num_src * num_tar).unsqueeze(1)) & ok_scene.unsqueeze(1)
+            nt = num_tar.clamp_min(1).unsqueeze(1)
+            # edge e goes to edge_feats[b, e // num_tar, e % num_tar]; dropped slots go to a dump row
+            dst = torch.where(kept, (epos // nt) * L + (epos % nt), torch.full_like(epos, K * L))
+            buf = obj_feats.new_zeros(B, K * L + 1, self.out_size)
+            buf = buf.scatter(1, dst.unsqueeze(-1).expand(-1, -1, self.out_size), message.view(B, K * L, -1))
+            edge_feats = buf[:, :K * L].reshape(B, K, L, self.out_size)
+            dst_e = torch.where(kept, epos, torch.full_like(epos, K * L))
+            src_ids = torch.gather(compact, 1, torch.arange(K, device=dev).repeat_interleave(L).expand(B, -1))
+            tar_ids = torch.gather(compact, 1, nbr.view(B, K * L))
+            ibuf = obj_feats.new_zeros(B, 2, K * L + 1)
+            ibuf = ibuf.scatter(2, dst_e.unsqueeze(1).expand(-1, 2, -1),
+                                torch.stack([src_ids, tar_ids], 1).to(obj_feats.dtype))
+            edge_indices = ibuf[:, :, :K * L]
+            num_sources = torch.where(ok_scene, num_src, torch.zeros_like(num_src))
+            num_targets = num_tar
+            # extra EdgeConv on the LAST node features, then the orientation / distance head
+            _, edge_feat2 = self.edge_layer(node_feat, edge_g, emask)
+            pred = self.edge_predict(edge_feat2).view(B, K * L, -1)
+            pred_ok = (ok_scene & (E == num_src * num_tar)).unsqueeze(1)   # else shape mismatch -> skipped
+            dst_p = torch.where(flat_valid & pred_ok, epos, torch.full_like(epos, K * L))
+            pbuf = obj_feats.new_zeros(B, K * L + 1, self.num_bins + 1)
+            pbuf = pbuf.scatter(1, dst_p.unsqueeze(-1).expand(-1, -1, self.num_bins + 1), pred)
+            edge_preds = pbuf[:, :K * L]
+
+        # skip connection on the valid objects, zeros elsewhere (graph_module.py:302-304)
+        new_obj_feats = torch.where(valid.unsqueeze(-1), obj_feats + node_feat.view(B, K, -1),
+                                    torch.zeros_like(obj_feats))
+
+        data_dict["bbox_feature"] = new_obj_feats
+        data_dict["adjacent_mat"] = adjacent_mat
+        data_dict["edge_index"] = edge_indices
+        data_dict["edge_feature"] = edge_feats
+        data_dict["num_edge_source"] = num_sources
+        data_dict["num_edge_target"] = num_targets
+        data_dict["edge_orientations"] = edge_preds[:, :, :-1]
+        data_dict["edge_distances"] = edge_preds[:, :, -1]
+        return data_dict

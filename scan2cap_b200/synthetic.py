@@ -44,8 +44,9 @@ def make_boxes(rng, num=NUM_BOXES):
     return np.stack([cx, cy, cz, size[:, 0], size[:, 1], size[:, 2]], 1)
 
 
-def make_scene(n_points, seed=42, dup_frac=0.02, centre=True):
-    """One scene: xyz (N,3) f32, normals (N,3) f32, boxes (24,6) f64 (in the same, centred frame)."""
+def make_scene(n_points, seed=42, dup_frac=0.02, centre=True, return_owner=False):
+    """One scene: xyz (N,3) f32, normals (N,3) f32, boxes (24,6) f64 (in the same, centred frame)
+    [, owner (N) int64: index of the box a point lies on, -1 for the room shell]."""
     rng = np.random.default_rng(seed)
     boxes = make_boxes(rng)
     surf = [2 * (ROOM[0] * ROOM[1] + ROOM[0] * ROOM[2] + ROOM[1] * ROOM[2])]
@@ -53,29 +54,35 @@ def make_scene(n_points, seed=42, dup_frac=0.02, centre=True):
         surf.append(2 * (b[3] * b[5] + b[4] * b[5]) + b[3] * b[4])
     surf = np.array(surf)
     counts = rng.multinomial(n_points, surf / surf.sum())
-    pts, nrm = [], []
+    pts, nrm, own = [], [], []
     p, q = _sample_box_surface(rng, (0, 0, 0), ROOM, counts[0])
     pts.append(p)
     nrm.append(-q)  # room normals point inwards
-    for b, c in zip(boxes, counts[1:]):
+    own.append(np.full(counts[0], -1, np.int64))
+    for bi, (b, c) in enumerate(zip(boxes, counts[1:])):
         p, q = _sample_box_surface(rng, b[:3] - b[3:] / 2, b[:3] + b[3:] / 2, c, with_bottom=False)
         pts.append(p)
         nrm.append(q)
+        own.append(np.full(c, bi, np.int64))
     pts = np.concatenate(pts).astype(np.float32)
     nrm = np.concatenate(nrm).astype(np.float32)
+    own = np.concatenate(own)
     perm = rng.permutation(n_points)
-    pts, nrm = pts[perm], nrm[perm]
+    pts, nrm, own = pts[perm], nrm[perm], own[perm]
     ndup = int(round(dup_frac * n_points))
     if ndup > 0:
         dst = rng.choice(n_points, ndup, replace=False)
         src = rng.integers(0, n_points, ndup)
         pts[dst] = pts[src]
         nrm[dst] = nrm[src]
+        own[dst] = own[src]
     if centre:  # ScanNet scans are roughly centred in x/y; keeps |p|^2 > 1e-3 for almost every point
         off = np.array([ROOM[0] / 2, ROOM[1] / 2, 0.0], np.float32)
         pts = pts - off
         boxes = boxes.copy()
         boxes[:, :3] -= off
+    if return_owner:
+        return pts, nrm, boxes, own
     return pts, nrm, boxes
 
 
@@ -103,3 +110,97 @@ def uniform_cube(batch, n_points, seed=42):
     """Uniform points in the unit cube (the microbench sweep's second distribution)."""
     rng = np.random.default_rng(seed)
     return rng.random((batch, n_points, 3), dtype=np.float32)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Full training ``data_dict`` (keys / dtypes of lib/dataset.py:503-538 after default collate)
+# ----------------------------------------------------------------------------------------------------------
+MAX_NUM_OBJ = 128
+NUM_GT_BOXES = 12
+MAX_DES_LEN = 30  # CONF.TRAIN.MAX_DES_LEN; lang tensors hold MAX_DES_LEN + 2 tokens
+
+
+def make_vocabulary(num_vocabs=3500, emb_size=300, seed=42):
+    """Synthetic stand-in for ScanRefer_vocabulary.json + glove.p (neither is shipped with the reference):
+    vocabulary = {"word2idx", "idx2word"} (idx2word keyed by str(i), as the reference expects,
+    caption_module.py:561) and embeddings = {word: (emb_size,) float32}.  Index 0 is the pad token."""
+    rng = np.random.default_rng(seed)
+    words = ["pad_", "unk", "sos", "eos"] + ["w%d" % i for i in range(4, num_vocabs)]
+    table = rng.standard_normal((num_vocabs, emb_size)).astype(np.float32)
+    vocabulary = {"word2idx": {w: i for i, w in enumerate(words)}, "idx2word": {str(i): w for i, w in enumerate(words)}}
+    embeddings = {w: table[i] for i, w in enumerate(words)}
+    return vocabulary, embeddings, table
+
+
+def box_corners(center, size):
+    """(…,3),(…,3) float64 -> (…,8,3) float64, corner order of utils/box_util.get_3d_box_batch."""
+    sx = np.array([1, 1, -1, -1, 1, 1, -1, -1], np.float64)
+    sy = np.array([1, -1, -1, 1, 1, -1, -1, 1], np.float64)
+    sz = np.array([1, 1, 1, 1, -1, -1, -1, -1], np.float64)
+    sign = np.stack([sx, sy, sz], -1)
+    return (size[..., None, :] / 2) * sign + center[..., None, :]
+
+
+def make_data_dict(batch, n_points, use_normal=False, use_multiview=False, use_height=True, num_vocabs=3500,
+                   seed=42, mean_size_arr=None, lang_len=None):
+    """Seeded CPU ``data_dict`` (numpy arrays) for a full CapNet forward + loss + backward."""
+    from .data.scannet.model_util_scannet import MEAN_SIZE_ARR
+    mean_size_arr = MEAN_SIZE_ARR if mean_size_arr is None else mean_size_arr
+    _, _, table = make_vocabulary(num_vocabs, seed=seed)
+    T = MAX_DES_LEN + 2
+    d = {k: [] for k in ("point_clouds", "center_label", "size_class_label", "size_residual_label", "sem_cls_label",
+                         "box_label_mask", "vote_label", "vote_label_mask", "scene_object_rotations",
+                         "scene_object_rotation_masks", "ref_box_corner_label", "gt_box_corner_label",
+                         "lang_ids", "lang_len", "lang_feat", "num_bbox")}
+    for b in range(batch):
+        s = seed + 1000 * b
+        rng = np.random.default_rng(s + 3)
+        xyz, nrm, boxes, own = make_scene(n_points, seed=s, return_owner=True)
+        cols = [xyz]
+        if use_normal:
+            cols.append(nrm)
+        if use_multiview:
+            cols.append(np.clip(np.random.default_rng(s + 7).standard_normal((n_points, 128)).astype(np.float32) * 0.5, -3, 3))
+        if use_height:
+            cols.append((xyz[:, 2] - np.percentile(xyz[:, 2], 0.99))[:, None].astype(np.float32))
+        d["point_clouds"].append(np.concatenate(cols, 1).astype(np.float32))
+        gt = boxes[:NUM_GT_BOXES]
+        center = np.zeros((MAX_NUM_OBJ, 3), np.float32)
+        center[:NUM_GT_BOXES] = gt[:, :3]
+        cls = np.zeros(MAX_NUM_OBJ, np.int64)
+        cls[:NUM_GT_BOXES] = rng.integers(0, 18, NUM_GT_BOXES)
+        res = np.zeros((MAX_NUM_OBJ, 3), np.float32)
+        res[:NUM_GT_BOXES] = gt[:, 3:] - mean_size_arr[cls[:NUM_GT_BOXES]]
+        mask = np.zeros(MAX_NUM_OBJ, np.float32)
+        mask[:NUM_GT_BOXES] = 1
+        d["center_label"].append(center)
+        d["size_class_label"].append(cls)
+        d["size_residual_label"].append(res)
+        d["sem_cls_label"].append(cls.copy())
+        d["box_label_mask"].append(mask)
+        d["num_bbox"].append(NUM_GT_BOXES)
+        vmask = ((own >= 0) & (own < NUM_GT_BOXES)).astype(np.int64)
+        vote = np.zeros((n_points, 3), np.float32)
+        vote[vmask == 1] = gt[own[vmask == 1], :3].astype(np.float32) - xyz[vmask == 1]
+        d["vote_label"].append(np.tile(vote, (1, 3)))
+        d["vote_label_mask"].append(vmask)
+        q, _ = np.linalg.qr(rng.standard_normal((MAX_NUM_OBJ, 3, 3)))
+        d["scene_object_rotations"].append(q.astype(np.float32))
+        d["scene_object_rotation_masks"].append(np.ones(MAX_NUM_OBJ, np.int64))
+        corners = np.zeros((MAX_NUM_OBJ, 8, 3), np.float64)
+        corners[:NUM_GT_BOXES] = box_corners(gt[:, :3], gt[:, 3:])
+        d["gt_box_corner_label"].append(corners)
+        d["ref_box_corner_label"].append(corners[b % NUM_GT_BOXES].copy())
+        n_tok = int(rng.integers(8, T + 1)) if lang_len is None else int(lang_len)
+        ids = np.zeros(T, np.int64)
+        ids[:n_tok] = rng.integers(4, num_vocabs, n_tok)
+        ids[0], ids[n_tok - 1] = 2, 3
+        d["lang_ids"].append(ids)
+        d["lang_len"].append(n_tok)
+        d["lang_feat"].append(table[ids] * (ids != 0)[:, None])
+    out = {k: np.stack(v) if isinstance(v[0], np.ndarray) else np.asarray(v, np.int64) for k, v in d.items()}
+    B = batch
+    out["heading_class_label"] = np.zeros((B, MAX_NUM_OBJ), np.int64)
+    out["heading_residual_label"] = np.zeros((B, MAX_NUM_OBJ), np.float32)
+    out["lang_feat"] = out["lang_feat"].astype(np.float32)
+    return out

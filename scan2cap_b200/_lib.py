@@ -57,5 +57,20 @@ def check(rc, name):
         raise S2CError("%s failed (code %d): %s" % (name, rc, msg))
 
 
+# ---- instrumentation used by bench.py: how many of OUR kernels were launched, and optional per-entry timing ----
+LAUNCH_COUNT = 0
+TIMING = None  # None, or {entry_name: [(start_event, end_event), ...]} filled while set (torch.cuda.Event pairs)
+
+
 def call(name, *args):
+    global LAUNCH_COUNT
+    LAUNCH_COUNT += 1
+    if TIMING is not None and name in TIMING:
+        import torch
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        check(getattr(LIB, name)(*args), name)
+        b.record()
+        TIMING[name].append((a, b))
+        return
     check(getattr(LIB, name)(*args), name)

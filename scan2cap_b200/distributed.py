@@ -1,0 +1,45 @@
+"""Data parallelism for CapNet: one process per GPU, scenes sharded over the batch axis, ONE NCCL all-reduce
+per step over a single flat gradient buffer (the reference itself is single-GPU).
+
+Every parameter's ``.grad`` is a view into one contiguous fp32 buffer, so autograd accumulates straight into
+it and the all-reduce needs no flatten / unflatten copies.  Parameters that receive no gradient in a step (e.g.
+the graph head when a scene has no edge) simply stay zero, which keeps the buffer layout static.
+BatchNorm statistics stay per-GPU, exactly as N independent copies of the reference would behave."""
+import torch
+import torch.distributed as dist
+
+
+class FlatGradients(object):
+    def __init__(self, module):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.numel = n
+
+    def zero_(self):
+        self.flat.zero_()
+
+    def all_reduce_mean(self, group=None):
+        """sum over ranks in one collective, then scale by 1/world."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            self.flat.mul_(1.0 / dist.get_world_size(group))
+
+
+def shard_batch(data_dict, rank, world_size):
+    """Rank r's contiguous slice of every per-scene tensor (batch axis 0)."""
+    out = {}
+    for k, v in data_dict.items():
+        if isinstance(v, torch.Tensor) and v.dim() > 0:
+            B = v.shape[0]
+            assert B % world_size == 0, "global batch %d not divisible by world size %d" % (B, world_size)
+            per = B // world_size
+            out[k] = v[rank * per:(rank + 1) * per]
+        else:
+            out[k] = v
+    return out

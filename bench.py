@@ -140,7 +140,7 @@ def to_device(host, device, num_words=None):
     return d
 
 
-def cpu_baseline(cfg_name, scenes=1):
+def cpu_baseline(cfg_name, scenes=4, budget_s=12.0, max_steps=6):
     """Oracle port of the reference (C oracle for the native ops + restated Python layers) on the host cores."""
     from oracle import ref_model as R
     from oracle import native
@@ -153,15 +153,20 @@ def cpu_baseline(cfg_name, scenes=1):
     torch.set_num_threads(os.cpu_count())
     model, DC, loss_fn = build_model("reference", C, "cpu")
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5)
-    t0 = time.perf_counter()
-    out = loss_fn(model({k: v.clone() for k, v in host.items()}), "cpu", DC, None, **LOSS_FLAGS)
-    opt.zero_grad()
-    out["loss"].backward()
-    opt.step()
-    dt = time.perf_counter() - t0
-    return {"value": scenes / dt, "unit": "scenes/s", "cores": os.cpu_count(), "kind": "port",
+    steps, t0 = 0, time.perf_counter()
+    while True:  # bounded sample: whole steps until >= `budget_s` seconds of CPU work (at most `max_steps`)
+        out = loss_fn(model({k: v.clone() for k, v in host.items()}), "cpu", DC, None, **LOSS_FLAGS)
+        opt.zero_grad()
+        out["loss"].backward()
+        opt.step()
+        steps += 1
+        dt = time.perf_counter() - t0
+        if dt >= budget_s or steps >= max_steps:
+            break
+    return {"value": scenes * steps / dt, "unit": "scenes/s", "cores": os.cpu_count(), "kind": "port",
             "threads": {"torch": torch.get_num_threads(), "openmp_native_ops": native.num_threads()},
-            "sample": "1 training step on %d scene(s) of the same workload (N=%d), %.1f s" % (scenes, N, dt)}
+            "sample": "%d training step(s) on %d scene(s) of the same workload (N=%d), %.1f s of host time"
+                      % (steps, scenes, N, dt)}
 
 
 def main():
@@ -172,6 +177,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="ours: issue the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--ref-device", default="auto", choices=["auto", "cuda", "cpu"])
     args = ap.parse_args()
 
@@ -190,7 +196,7 @@ def main():
             # CPU-only oracle port: rank 0 alone runs it
             if rank != 0:
                 return
-            cb = cpu_baseline(args.config, scenes=1)
+            cb = cpu_baseline(args.config, scenes=4)
             B, N, _, _ = CONFIGS[args.config]
             line = {"impl": "reference", "metric": "scenes/sec CapNet fwd+bwd @40k pts", "value": cb["value"],
                     "unit": "scenes/s", "n_gpus": 0, "steps": 1, "warmup": 0, "ms_per_step": 1e3 / cb["value"],
@@ -212,8 +218,13 @@ def main():
     model, DC, loss_fn = build_model(args.impl, C, device)
     B, N = host["point_clouds"].shape[0], host["point_clouds"].shape[1]
     from scan2cap_b200.distributed import FlatGradients
-    flat = FlatGradients(model)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5)
+    engine = None
+    if args.impl == "ours":
+        from scan2cap_b200.engine import TrainStep
+        engine = TrainStep(model, DC, lr=1e-3, weight_decay=1e-5, use_cuda_graph=not args.no_graph, **LOSS_FLAGS)
+    else:
+        flat = FlatGradients(model)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5)
 
     # make the referred box of every scene a box the (random-init) detector proposes, so good_bbox_masks is not
     # empty and the caption loss / its gradients are exercised
@@ -226,6 +237,8 @@ def main():
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)  # 256 MB > 126 MB L2
 
     def step(data):
+        if engine is not None:
+            return engine.run(data)
         flat.zero_()
         out = loss_fn(model(data), device, DC, None, **LOSS_FLAGS)
         out["loss"].backward()
@@ -244,8 +257,10 @@ def main():
         for _ in range(K):
             flush.zero_()  # L2 flush between iterations (inside the timed region: conservative)
             if from_host:
-                data = to_device(host, device, num_words if args.impl == "ours" else None)
-                loss = step(data)
+                if engine is not None:  # the engine copies pinned host tensors into its static device buffers
+                    loss = step(dict(host, num_words=num_words))
+                else:
+                    loss = step(to_device(host, device, None))
                 last = float(loss.item())  # D2H read of the step's result
             else:
                 loss = step({k: v for k, v in resident.items()})
@@ -263,13 +278,24 @@ def main():
     if rank == 0:
         sampler.start()
     L.LAUNCH_COUNT = 0
-    qg_name = "s2c_query_and_group"
-    L.TIMING = {qg_name: []} if args.impl == "ours" else None
     ms, _ = timed(args.steps, False)
     launches = L.LAUNCH_COUNT
-    qg_events = L.TIMING[qg_name] if L.TIMING else []
-    L.TIMING = None
+    if engine is not None and engine.use_graph:
+        launches = engine.kernels_per_step * args.steps  # replayed from the graph: no Python call per launch
     clocks = sampler.stop() if rank == 0 else None
+    # single-kernel timing for the roofline: the same step issued eagerly, CUDA events around the SA1
+    # query+group launch (events cannot bracket a node inside a replayed graph)
+    qg_name = "s2c_query_and_group"
+    qg_events, qg_steps = [], min(args.steps, 5)
+    if engine is not None:
+        resident = to_device(host, device, num_words)
+        L.TIMING = {qg_name: []}
+        for _ in range(qg_steps):
+            flush.zero_()
+            engine.run_eager(dict(resident))
+        torch.cuda.synchronize()
+        qg_events = L.TIMING[qg_name]
+        L.TIMING = None
     timed(2, True)
     ms_e2e, last_loss = timed(args.steps, True)
 
@@ -289,7 +315,9 @@ def main():
                                "top-down caption, V=%d, %d decoder steps" % (args.config, B, N, C + 3, VOCAB, num_words - 1),
                    "global_batch": B * world, "points": N, "point_floats": C + 3, "tf32": False,
                    "l2": "256 MB buffer rewritten between iterations (inside the timed region)",
-                   "parallelism": "dp%d" % world},
+                   "parallelism": "dp%d" % world,
+                   "issue": ("cuda-graph replay of the whole step" if (engine is not None and engine.use_graph)
+                             else "eager launches")},
         "e2e": {"value": scenes / (ms_e2e * 1e-3), "unit": "scenes/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "last_loss": last_loss},
         "gpu_launches": launches,
@@ -302,7 +330,7 @@ def main():
                                        "restatement of the reference Python layers; CUDA_LAUNCH_BLOCKING unset")
     if qg_events:
         # SA1 is the first query_and_group call of every step (5 calls per step: SA1-4 + vote aggregation)
-        per_step = len(qg_events) // args.steps
+        per_step = len(qg_events) // qg_steps
         sa1 = [e for i, e in enumerate(qg_events) if i % per_step == 0]
         t_ms = float(np.mean([s.elapsed_time(e) for s, e in sa1]))
         M, ns = 2048, 64
@@ -314,7 +342,7 @@ def main():
                             "peak_source": pk_src}
     if not args.no_cpu_baseline and world == 1:
         try:
-            line["cpu_baseline"] = cpu_baseline(args.config, scenes=1)
+            line["cpu_baseline"] = cpu_baseline(args.config, scenes=4)
         except Exception as e:  # never lose the GPU numbers to a host-side problem
             line["cpu_baseline"] = {"error": repr(e)}
     print(json.dumps(line))

@@ -17,6 +17,16 @@ NEAR_THRESHOLD = 0.3
 GT_VOTE_FACTOR = 3
 OBJECTNESS_CLS_WEIGHTS = [0.2, 0.8]
 
+_CONST = {}
+
+
+def _const(name, make, device):
+    """Device-resident constants, created once per device (no H2D copy inside a captured step)."""
+    key = (name, str(device))
+    if key not in _CONST:
+        _CONST[key] = make().to(device)
+    return _CONST[key]
+
 
 def compute_vote_loss(data_dict):
     batch_size, num_seed = data_dict["seed_xyz"].shape[0], data_dict["seed_xyz"].shape[1]
@@ -44,7 +54,7 @@ def compute_objectness_loss(data_dict):
     objectness_label = near.long()
     objectness_mask = (near | (euclidean_dist1 > FAR_THRESHOLD)).float()
     objectness_scores = data_dict["objectness_scores"]
-    w = torch.tensor(OBJECTNESS_CLS_WEIGHTS, device=objectness_scores.device, dtype=objectness_scores.dtype)
+    w = _const("obj_w", lambda: torch.tensor(OBJECTNESS_CLS_WEIGHTS, dtype=torch.float32), objectness_scores.device)
     objectness_loss = F.cross_entropy(objectness_scores.transpose(2, 1), objectness_label, weight=w, reduction="none")
     objectness_loss = torch.sum(objectness_loss * objectness_mask) / (torch.sum(objectness_mask) + 1e-6)
     return objectness_loss, objectness_label, objectness_mask, ind1
@@ -83,7 +93,9 @@ def compute_box_and_sem_cls_loss(data_dict, config):
     size_residual_label = torch.gather(data_dict["size_residual_label"], 1, object_assignment.unsqueeze(-1).expand(-1, -1, 3))
     size_label_one_hot_tiled = F.one_hot(size_class_label, num_size_cluster).to(pred_center.dtype).unsqueeze(-1)
     predicted_size_residual_normalized = torch.sum(data_dict["size_residuals_normalized"] * size_label_one_hot_tiled, 2)
-    mean_size_arr_expanded = torch.from_numpy(mean_size_arr.astype(np.float32)).to(pred_center.device).unsqueeze(0).unsqueeze(0)
+    mean_size_arr_expanded = _const("mean_size%d" % id(mean_size_arr),
+                                    lambda: torch.from_numpy(mean_size_arr.astype(np.float32)),
+                                    pred_center.device).unsqueeze(0).unsqueeze(0)
     mean_size_label = torch.sum(size_label_one_hot_tiled * mean_size_arr_expanded, 2)
     size_residual_label_normalized = size_residual_label / mean_size_label
     size_residual_normalized_loss = torch.mean(
@@ -116,7 +128,8 @@ def compute_cap_loss(data_dict, config, weights):
 
 
 def radian_to_label(radians, num_bins=6):
-    boundaries = torch.arange(np.pi / num_bins, np.pi - 1e-8, np.pi / num_bins, device=radians.device)
+    boundaries = _const("bins%d" % num_bins, lambda: torch.arange(np.pi / num_bins, np.pi - 1e-8, np.pi / num_bins),
+                        radians.device)
     return torch.bucketize(radians, boundaries)
 
 

@@ -27,10 +27,20 @@ def box3d_iou_batch_tensor(corners1, corners2):
     return inter_vol / (box_vol_1 + box_vol_2 - inter_vol + 1e-8)
 
 
+_SIGN_CACHE = {}
+
+
+def _corner_signs(dtype, device):
+    key = (dtype, str(device))
+    if key not in _SIGN_CACHE:
+        _SIGN_CACHE[key] = torch.tensor([_SX, _SY, _SZ], dtype=dtype).t().contiguous().to(device)  # (8,3)
+    return _SIGN_CACHE[key]
+
+
 def axis_aligned_corners(box_size, center):
     """get_3d_box_batch for heading 0 (the only heading ScanNet has: model_util_scannet.py:126-136):
     box_size (...,3) f64, center (...,3) f64 -> (...,8,3) f64 = (+-size/2) + center, the same two float64
     operations numpy performs (the rotation by -0.0 rad multiplies by exactly 1 and adds exact zeros)."""
-    sign = torch.tensor([_SX, _SY, _SZ], dtype=box_size.dtype, device=box_size.device).t()  # (8,3)
+    sign = _corner_signs(box_size.dtype, box_size.device)
     half = box_size / 2
     return half.unsqueeze(-2) * sign + center.unsqueeze(-2)

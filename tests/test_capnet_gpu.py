@@ -85,12 +85,14 @@ def _check_outputs(o, r, int_keys, exact_keys, float_keys):
 def _check_grads(ours, ref, prefixes=None):
     go = {n: p.grad for n, p in ours.named_parameters() if p.grad is not None}
     gr = {n: p.grad for n, p in ref.named_parameters() if p.grad is not None}
-    assert set(go) == set(gr)
+    if prefixes is None:
+        assert set(go) == set(gr)
     gmax = max(float(g.abs().max()) for g in gr.values())
     badg, worst = {}, 0.0
     for n in gr:
         if prefixes is not None and not n.startswith(prefixes):
             continue
+        assert n in go, "no gradient for %s" % n
         scale = max(float(gr[n].abs().max()), 1e-3 * gmax)
         e = float((go[n] - gr[n]).abs().max()) / scale
         worst = max(worst, e)

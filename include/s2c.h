@@ -144,6 +144,22 @@ S2C_API int s2c_knn_adjacency(const double *corners, const long long *mask, cons
                               int K, int T, int num_locals, int corner_mode, int include_self,
                               double iou_threshold, float *adjacent, int *neighbours, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * mlp_layer_fwd -- one layer of the per-group shared MLP (SharedMLP: 1x1 Conv2d without bias, the
+ *   BatchNorm + ReLU of the PREVIOUS layer folded into the operand load), on the tcgen05 tensor cores
+ *   (3xTF32, fp32 accumulation in TMEM).  Replaces, per layer, the reference's cuDNN conv + BatchNorm2d
+ *   + ReLU kernel triple (lib/pointnet2/pytorch_utils.py:88-120 as used at pointnet2_modules.py:251).
+ *     A          (R, lda) fp32 rows = every (scene, group, sample); K valid columns
+ *     pro_scale / pro_shift  [K] or both NULL: a' = relu(a * scale[k] + shift[k]) applied on load
+ *     W          (N, K) fp32 row-major (Conv2d weight (Cout,Cin,1,1)); N multiple of 16, <= 256
+ *     C          (R, ldc) fp32 out = a' * W^T   (PRE-BatchNorm output of this layer)
+ *     stat_sum / stat_sumsq  [N] float64 or both NULL: += column sums of C and of C^2 (the batch
+ *                statistics of this layer's BatchNorm); the caller zeroes them
+ * ---------------------------------------------------------------------------------------- */
+S2C_API int s2c_mlp_layer_fwd(const float *A, long long lda, long long R, int K, const float *pro_scale,
+                              const float *pro_shift, const float *W, int N, float *C, long long ldc,
+                              double *stat_sum, double *stat_sumsq, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

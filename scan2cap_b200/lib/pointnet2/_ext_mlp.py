@@ -1,0 +1,28 @@
+"""Torch-facing wrappers of the grouped-MLP (tensor-core) entry points of libs2c.so (C ABI: include/s2c.h)."""
+import torch
+
+from ..._lib import call
+from ._ext import _guard, _stream
+
+
+def mlp_layer_fwd(A, W, pro_scale=None, pro_shift=None, want_stats=True, K=None):
+    """A (R, lda) fp32 (row stride lda >= K), W (N, K) -> C (R, N) = relu(A*scale+shift) @ W^T [no prologue when
+    scale is None], plus float64 column sums / sums of squares of C when want_stats."""
+    assert A.is_cuda and A.dtype == torch.float32 and A.dim() == 2 and A.stride(1) == 1
+    W = W.contiguous()
+    N, Kw = W.shape
+    K = Kw if K is None else K
+    assert K == Kw and A.shape[1] >= K
+    R, lda = A.shape[0], A.stride(0)
+    C = torch.empty((R, N), dtype=torch.float32, device=A.device)
+    s1 = s2 = None
+    if want_stats:
+        stats = torch.zeros((2, N), dtype=torch.float64, device=A.device)
+        s1, s2 = stats[0], stats[1]
+    with _guard(A):
+        call("s2c_mlp_layer_fwd", A.data_ptr(), lda, R, K,
+             pro_scale.data_ptr() if pro_scale is not None else None,
+             pro_shift.data_ptr() if pro_shift is not None else None,
+             W.data_ptr(), N, C.data_ptr(), N,
+             s1.data_ptr() if want_stats else None, s2.data_ptr() if want_stats else None, _stream(A))
+    return (C, s1, s2) if want_stats else C

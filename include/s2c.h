@@ -160,6 +160,20 @@ S2C_API int s2c_mlp_layer_fwd(const float *A, long long lda, long long R, int K,
                               const float *pro_shift, const float *W, int N, float *C, long long ldc,
                               double *stat_sum, double *stat_sumsq, void *stream);
 
+/* pool_fwd -- last BatchNorm + ReLU folded into the max over nsample (F.max_pool2d, pointnet2_modules.py:255-257):
+ *   Y (G*ns, ldy) pre-BatchNorm rows, N channels -> out (G, N) = max_s relu(Y*scale+shift); argmax (G, N) int32
+ *   (may be NULL) = first maximising sample, the element the backward pass routes the gradient to.  ns = 1 turns
+ *   this into a plain BatchNorm + ReLU (PointnetFPModule). */
+S2C_API int s2c_pool_fwd(const float *Y, long long ldy, long long G, int ns, int N, const float *scale,
+                         const float *shift, float *out, int *argmax, void *stream);
+
+/* pool_bwd_stats -- per-channel sums the last layer's BatchNorm backward needs, straight from the pooled gradient:
+ *   sum_g[c] += sum_G g, sum_gy[c] += sum_G g * y  with g = dpool[G,c] where relu(bn(y)) was active at the arg-max
+ *   element y = Y[G*ns + argmax[G,c], c], else 0.  float64 accumulators, zeroed by the caller. */
+S2C_API int s2c_pool_bwd_stats(const float *dpool, const int *argmax, const float *Y, long long ldy, long long G,
+                               int ns, int N, const float *scale, const float *shift, double *sum_g,
+                               double *sum_gy, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -324,3 +324,89 @@ extern "C" int s2c_mlp_layer_fwd(const float *A, long long lda, long long R, int
   S2C_CHECK_LAUNCH("mlp_layer_fwd launch");
   return S2C_OK;
 }
+
+// ================================================================================================
+// Pooling end of the stack:  out[g, c] = max_s relu(Y[g*ns + s, c] * scale[c] + shift[c])
+// (BatchNorm + ReLU of the LAST layer folded into F.max_pool2d, pointnet2_modules.py:255-257), plus the
+// arg-max sample the backward pass routes the gradient to (first maximum, like max_pool2d).
+// ================================================================================================
+namespace s2c {
+namespace {
+
+__global__ void __launch_bounds__(256)
+pool_fwd_kernel(const float *__restrict__ Y, long long ldy, long long G, int ns, int N, const float *__restrict__ scale,
+                const float *__restrict__ shift, float *__restrict__ out, int *__restrict__ argmax) {
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+  if (c >= N) return;
+  const float sc = scale[c], sh = shift[c];
+  for (long long grp = (long long)blockIdx.y * 4 + (threadIdx.x >> 6); grp < G; grp += (long long)gridDim.y * 4) {
+    const float *y = Y + grp * ns * ldy + c;
+    float best = -1.f;
+    int bi = 0;
+    for (int s = 0; s < ns; ++s) {
+      const float v = fmaxf(fmaf(__ldg(y + (long long)s * ldy), sc, sh), 0.f);
+      if (v > best) { best = v; bi = s; }
+    }
+    out[grp * N + c] = best;
+    if (argmax) argmax[grp * N + c] = bi;
+  }
+}
+
+// per-channel  sum_g = sum of the pooled gradient where the ReLU was active,  sum_gy = sum of g * y(argmax)
+__global__ void __launch_bounds__(256)
+pool_bwd_stats_kernel(const float *__restrict__ dpool, const int *__restrict__ argmax, const float *__restrict__ Y,
+                      long long ldy, long long G, int ns, int N, const float *__restrict__ scale,
+                      const float *__restrict__ shift, double *__restrict__ sum_g, double *__restrict__ sum_gy) {
+  __shared__ float s1[4][64], s2[4][64];
+  const int cl = threadIdx.x & 63, q = threadIdx.x >> 6;
+  const int c = blockIdx.x * 64 + cl;
+  float a = 0.f, b = 0.f;
+  if (c < N) {
+    const float sc = scale[c], sh = shift[c];
+    for (long long grp = (long long)blockIdx.y * 4 + q; grp < G; grp += (long long)gridDim.y * 4) {
+      const int s = argmax[grp * N + c];
+      const float y = __ldg(Y + (grp * ns + s) * ldy + c);
+      const float gval = (fmaf(y, sc, sh) > 0.f) ? dpool[grp * N + c] : 0.f;
+      a += gval;
+      b = fmaf(gval, y, b);
+    }
+  }
+  s1[q][cl] = a; s2[q][cl] = b;
+  __syncthreads();
+  if (q == 0 && c < N) {
+    atomicAdd(sum_g + c, (double)s1[0][cl] + (double)s1[1][cl] + (double)s1[2][cl] + (double)s1[3][cl]);
+    atomicAdd(sum_gy + c, (double)s2[0][cl] + (double)s2[1][cl] + (double)s2[2][cl] + (double)s2[3][cl]);
+  }
+}
+
+}  // namespace
+}  // namespace s2c
+
+extern "C" int s2c_pool_fwd(const float *Y, long long ldy, long long G, int ns, int N, const float *scale,
+                            const float *shift, float *out, int *argmax, void *stream) {
+  using namespace s2c;
+  S2C_REQUIRE(G >= 0 && ns >= 1 && N >= 1 && ldy >= N, "pool_fwd: bad sizes");
+  if (G == 0) return S2C_OK;
+  S2C_REQUIRE(Y && scale && shift && out, "pool_fwd: null pointer");
+  long long gy = (G + 3) / 4;
+  if (gy > 65535) gy = 65535;  // the kernel strides over the groups
+  dim3 grid((unsigned)ceil_div(N, 64), (unsigned)gy);
+  pool_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(Y, ldy, G, ns, N, scale, shift, out, argmax);
+  S2C_CHECK_LAUNCH("pool_fwd");
+  return S2C_OK;
+}
+
+extern "C" int s2c_pool_bwd_stats(const float *dpool, const int *argmax, const float *Y, long long ldy, long long G,
+                                  int ns, int N, const float *scale, const float *shift, double *sum_g,
+                                  double *sum_gy, void *stream) {
+  using namespace s2c;
+  S2C_REQUIRE(G >= 0 && ns >= 1 && N >= 1 && ldy >= N, "pool_bwd_stats: bad sizes");
+  if (G == 0) return S2C_OK;
+  S2C_REQUIRE(dpool && argmax && Y && scale && shift && sum_g && sum_gy, "pool_bwd_stats: null pointer");
+  long long gy = (G + 3) / 4;
+  if (gy > 256) gy = 256;
+  dim3 grid((unsigned)ceil_div(N, 64), (unsigned)gy);
+  pool_bwd_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dpool, argmax, Y, ldy, G, ns, N, scale, shift, sum_g, sum_gy);
+  S2C_CHECK_LAUNCH("pool_bwd_stats");
+  return S2C_OK;
+}

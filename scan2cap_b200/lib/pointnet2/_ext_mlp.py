@@ -26,3 +26,25 @@ def mlp_layer_fwd(A, W, pro_scale=None, pro_shift=None, want_stats=True, K=None)
              W.data_ptr(), N, C.data_ptr(), N,
              s1.data_ptr() if want_stats else None, s2.data_ptr() if want_stats else None, _stream(A))
     return (C, s1, s2) if want_stats else C
+
+
+def pool_fwd(Y, G, ns, scale, shift, want_argmax=True):
+    """Y (G*ns, N) -> out (G, N) = max_s relu(Y*scale+shift), argmax (G, N) int32."""
+    R, N = Y.shape
+    assert R == G * ns and Y.stride(1) == 1
+    out = torch.empty((G, N), dtype=torch.float32, device=Y.device)
+    am = torch.empty((G, N), dtype=torch.int32, device=Y.device) if want_argmax else None
+    with _guard(Y):
+        call("s2c_pool_fwd", Y.data_ptr(), Y.stride(0), G, ns, N, scale.data_ptr(), shift.data_ptr(), out.data_ptr(),
+             am.data_ptr() if want_argmax else None, _stream(Y))
+    return out, am
+
+
+def pool_bwd_stats(dpool, argmax, Y, ns, scale, shift):
+    """-> float64 (sum_g [N], sum_gy [N]) of the ReLU-masked pooled gradient routed to the arg-max elements."""
+    G, N = dpool.shape
+    stats = torch.zeros((2, N), dtype=torch.float64, device=Y.device)
+    with _guard(Y):
+        call("s2c_pool_bwd_stats", dpool.data_ptr(), argmax.data_ptr(), Y.data_ptr(), Y.stride(0), G, ns, N,
+             scale.data_ptr(), shift.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), _stream(Y))
+    return stats[0], stats[1]

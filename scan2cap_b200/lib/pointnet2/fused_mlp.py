@@ -1,0 +1,133 @@
+"""Fused shared-MLP (+ max-pool) on the tcgen05 kernels of libs2c.so, as one autograd Function.
+
+Arithmetic of the reference's SharedMLP (lib/pointnet2/pytorch_utils.py:11-36, 88-120: [1x1 conv without bias ->
+BatchNorm (batch statistics in training) -> ReLU] per layer) followed by the max over nsample
+(lib/pointnet2/pointnet2_modules.py:255-257) -- or without pooling (nsample = 1) for PointnetFPModule.
+
+Forward: one tensor-core kernel per layer; only the PRE-BatchNorm output of every layer is written to HBM (it is
+also what the backward pass needs), the normalised / rectified activations exist only inside the next kernel's
+operand staging; the batch statistics come out of the GEMM epilogue; the last BatchNorm + ReLU is folded into the
+pooling kernel.
+Backward: BatchNorm's batch-statistics backward is affine per channel in (g, y):
+    dY = a*g + b*y + c,  a = gamma*invstd, b = -a*invstd*mean(g*xhat), c = -a*mean(g) - b*mean
+so each layer's dY tile is formed on the fly from the stored y and the masked upstream gradient g.
+"""
+import torch
+from torch.autograd import Function
+
+from . import _ext_mlp
+
+
+def _bn_coefficients(s1, s2, R, bn, training):
+    """mean / invstd (float64) of this layer's BatchNorm and the folded fp32 (scale, shift); updates running stats."""
+    if training or not bn.track_running_stats:
+        mean = s1 / R
+        var = (s2 / R - mean * mean).clamp_min_(0.0)
+        if training and bn.track_running_stats:
+            with torch.no_grad():
+                mom = bn.momentum if bn.momentum is not None else 0.0
+                unbiased = var * (float(R) / max(R - 1, 1))
+                bn.running_mean.mul_(1 - mom).add_(mean.to(bn.running_mean.dtype), alpha=mom)
+                bn.running_var.mul_(1 - mom).add_(unbiased.to(bn.running_var.dtype), alpha=mom)
+                if bn.num_batches_tracked is not None:
+                    bn.num_batches_tracked.add_(1)
+    else:
+        mean = bn.running_mean.double()
+        var = bn.running_var.double()
+    invstd = torch.rsqrt(var + bn.eps)
+    scale = bn.weight.double() * invstd
+    shift = bn.bias.double() - mean * scale
+    return mean, invstd, scale.float(), shift.float()
+
+
+class _FusedMLPPool(Function):
+    @staticmethod
+    def forward(ctx, rows, K, G, ns, training, bns, *params):
+        """rows (R, lda) fp32 with K valid columns, R = G*ns; params = (W1, gamma1, beta1, W2, ...);
+        bns = the BatchNorm modules (running statistics / eps / momentum).  Returns pooled (G, C_last)."""
+        L = len(bns)
+        R = rows.shape[0]
+        Ys, coefs = [], []
+        A, scale, shift, k = rows, None, None, K
+        for l in range(L):
+            W = params[3 * l].reshape(params[3 * l].shape[0], -1)
+            need_stats = training or not bns[l].track_running_stats
+            res = _ext_mlp.mlp_layer_fwd(A, W, scale, shift, want_stats=need_stats, K=k)
+            Y, s1, s2 = res if need_stats else (res, None, None)
+            mean, invstd, scale, shift = _bn_coefficients(s1, s2, R, bns[l], training)
+            Ys.append(Y)
+            coefs.append((mean, invstd, scale, shift))
+            A, k = Y, W.shape[0]
+        pooled, argmax = _ext_mlp.pool_fwd(Ys[-1], G, ns, scale, shift, want_argmax=True)
+        ctx.save_for_backward(rows, argmax, *Ys, *[t for c in coefs for t in c], *params)
+        ctx.meta = (K, G, ns, L, bool(training), [bool(training or not b.track_running_stats) for b in bns])
+        return pooled
+
+    @staticmethod
+    def backward(ctx, dpool):
+        K, G, ns, L, training, batch_stats = ctx.meta
+        saved = ctx.saved_tensors
+        rows, argmax = saved[0], saved[1]
+        Ys = saved[2:2 + L]
+        coefs = [saved[2 + L + 4 * l: 2 + L + 4 * l + 4] for l in range(L)]
+        params = saved[2 + 5 * L:]
+        R = rows.shape[0]
+        grads = [None] * (3 * L)
+        dpool = dpool.contiguous()
+        # gradient w.r.t. the rectified output of the last layer: the pooled gradient at the arg-max sample
+        C_last = Ys[-1].shape[1]
+        g = torch.zeros((G, ns, C_last), dtype=dpool.dtype, device=dpool.device)
+        g.scatter_(1, argmax.long().unsqueeze(1), dpool.unsqueeze(1))
+        g = g.view(R, C_last)
+        grad_rows = None
+        for l in range(L - 1, -1, -1):
+            W = params[3 * l].reshape(params[3 * l].shape[0], -1)
+            gamma = params[3 * l + 1]
+            mean, invstd, scale, shift = coefs[l]
+            Y = Ys[l]
+            g = g * (torch.addcmul(shift, Y, scale) > 0)          # ReLU mask of this layer
+            sum_g = g.sum(0, dtype=torch.float64)
+            sum_gy = (g * Y).sum(0, dtype=torch.float64)
+            sum_gx = (sum_gy - mean * sum_g) * invstd             # sum of g * xhat
+            grads[3 * l + 1] = sum_gx.to(gamma.dtype)
+            grads[3 * l + 2] = sum_g.to(gamma.dtype)
+            a = gamma.double() * invstd
+            if batch_stats[l]:
+                b = -a * invstd * (sum_gx / R)
+                c = -a * (sum_g / R) - b * mean
+                dY = torch.addcmul(c.float(), g, a.float()).addcmul_(Y, b.float())
+            else:
+                dY = g * a.float()
+            if l > 0:
+                m_p, i_p, sc_p, sh_p = coefs[l - 1]
+                Xp = torch.relu_(torch.addcmul(sh_p, Ys[l - 1], sc_p))
+                grads[3 * l] = (dY.t() @ Xp).view_as(params[3 * l])
+                g = dY @ W
+            else:
+                X0 = rows[:, :K]
+                grads[0] = (dY.t() @ X0).view_as(params[0])
+                if ctx.needs_input_grad[0]:
+                    grad_rows = dY @ W
+                    if rows.shape[1] != K:
+                        grad_rows = torch.nn.functional.pad(grad_rows, (0, rows.shape[1] - K))
+        return (grad_rows, None, None, None, None, None) + tuple(grads)
+
+
+def fused_mlp_maxpool(rows, K, G, ns, layers, training):
+    """rows (G*ns, >=K) -> (G, C_last): SharedMLP `layers` = [(conv, bn)] then max over each group's ns rows."""
+    params, bns = [], []
+    for conv, bn in layers:
+        assert conv.bias is None and bn is not None, "fused path: conv without bias followed by BatchNorm"
+        params += [conv.weight, bn.weight, bn.bias]
+        bns.append(bn)
+    return _FusedMLPPool.apply(rows, K, G, ns, training, bns, *params)
+
+
+def fusable(layers):
+    if layers is None or len(layers) == 0:
+        return False
+    for conv, bn in layers:
+        n = conv.weight.shape[0]
+        if conv.bias is not None or bn is None or not bn.affine or n % 16 != 0 or n > 256:
+            return False
+    return True

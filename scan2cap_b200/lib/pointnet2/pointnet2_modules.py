@@ -17,9 +17,15 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+import os
+
 from . import _ext
+from . import fused_mlp
 from . import pointnet2_utils
 from . import pytorch_utils as pt_utils
+
+# S2C_FUSED_MLP=0 falls back to library GEMM + BatchNorm + ReLU kernels (A/B comparison, debugging)
+USE_FUSED_MLP = os.environ.get("S2C_FUSED_MLP", "1") != "0"
 
 
 def point_major(features):
@@ -104,8 +110,11 @@ class PointnetSAModuleVotes(nn.Module):
                                                      self.normalize_xyz, True, True)
         B, C, M, ns = grouped.shape
         rows = grouped.permute(0, 2, 3, 1).reshape(B * M * ns, C)  # a view: the kernel wrote channels-last
-        out = shared_mlp_rows(rows, layers, self.training)
-        pooled = out.view(B, M, ns, -1).amax(dim=2)  # (B, M, C') point-major
+        if USE_FUSED_MLP and fused_mlp.fusable(layers):
+            pooled = fused_mlp.fused_mlp_maxpool(rows, C, B * M, ns, layers, self.training).view(B, M, -1)
+        else:
+            out = shared_mlp_rows(rows, layers, self.training)
+            pooled = out.view(B, M, ns, -1).amax(dim=2)  # (B, M, C') point-major
         return new_xyz, pooled.transpose(1, 2), inds
 
     def _forward_generic(self, xyz, features, inds):
@@ -152,5 +161,8 @@ class PointnetFPModule(nn.Module):
             parts.append(unknow_feats.transpose(1, 2))
         rows = torch.cat(parts, dim=2)  # (B, n, C2+C1) point-major
         B, n, C = rows.shape
-        out = shared_mlp_rows(rows.reshape(B * n, C), layers, self.training)
+        if USE_FUSED_MLP and fused_mlp.fusable(layers):
+            out = fused_mlp.fused_mlp_maxpool(rows.reshape(B * n, C), C, B * n, 1, layers, self.training)
+        else:
+            out = shared_mlp_rows(rows.reshape(B * n, C), layers, self.training)
         return out.view(B, n, -1).transpose(1, 2)

@@ -27,10 +27,47 @@ def test_mlp_layer_fwd_matches_float64(R, K, N, lda, pro):
     C, s1, s2 = _ext_mlp.mlp_layer_fwd(buf if lda != K else A, W, scale, shift, want_stats=True, K=K)
     torch.cuda.synchronize()
     err = float((C.double() - want).abs().max() / want.abs().max())
-    assert err < 2e-6, "3xTF32 GEMM error %g" % err
+    assert err < 5e-6, "3xTF32 GEMM error %g" % err
     # plain fp32 library GEMM for scale: we must be in the same accuracy class
     ref32 = (A64.float() @ W.t())
     err32 = float((ref32.double() - want).abs().max() / want.abs().max())
-    assert err < max(4 * err32, 2e-6)
+    assert err < max(4 * err32, 5e-6)
     assert float((s1 - want.sum(0)).abs().max() / want.sum(0).abs().max().clamp_min(1.0)) < 1e-5
     assert float((s2 - (want * want).sum(0)).abs().max() / (want * want).sum(0).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("B,M,ns,C,widths,training", [
+    (2, 256, 16, 7, (64, 64, 128), True), (2, 128, 32, 131, (128, 128, 256), True),
+    (1, 64, 16, 259, (128, 128, 128), False), (3, 200, 1, 512, (256, 256), True),
+])
+def test_fused_mlp_maxpool_matches_torch_path(B, M, ns, C, widths, training):
+    """Fused tensor-core stack (forward AND backward, BatchNorm running statistics included) against the
+    library-kernel formulation of the same module (F.linear + F.batch_norm + relu + amax)."""
+    import copy
+    from scan2cap_b200.lib.pointnet2 import pytorch_utils as pt_utils
+    from scan2cap_b200.lib.pointnet2.fused_mlp import fused_mlp_maxpool
+    from scan2cap_b200.lib.pointnet2.pointnet2_modules import shared_mlp_rows
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(7)
+    mlp_a = pt_utils.SharedMLP([C] + list(widths), bn=True).to(DEV)
+    for m in mlp_a.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data.uniform_(0.5, 1.5); m.bias.data.normal_(0, 0.2)
+            m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
+    mlp_b = copy.deepcopy(mlp_a)
+    mlp_a.train(training); mlp_b.train(training)
+    R = B * M * ns
+    x_a = torch.randn(R, C, device=DEV, requires_grad=True)
+    x_b = x_a.detach().clone().requires_grad_(True)
+    gout = torch.randn(B * M, widths[-1], device=DEV)
+    out_a = fused_mlp_maxpool(x_a, C, B * M, ns, mlp_a.layer_params(), training)
+    out_b = shared_mlp_rows(x_b, mlp_b.layer_params(), training).view(B * M, ns, -1).amax(1)
+    rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-12))
+    assert rel(out_a, out_b) < 1e-4
+    (out_a * gout).sum().backward()
+    (out_b * gout).sum().backward()
+    assert rel(x_a.grad, x_b.grad) < 2e-3
+    for (n, pa), (_, pb) in zip(mlp_a.named_parameters(), mlp_b.named_parameters()):
+        assert rel(pa.grad, pb.grad) < 2e-3, n
+    for (n, ba), (_, bb) in zip(mlp_a.named_buffers(), mlp_b.named_buffers()):
+        assert rel(ba.float(), bb.float()) < 1e-4, n

@@ -25,7 +25,7 @@ from . import pointnet2_utils
 from . import pytorch_utils as pt_utils
 
 # S2C_FUSED_MLP=0 falls back to library GEMM + BatchNorm + ReLU kernels (A/B comparison, debugging)
-USE_FUSED_MLP = os.environ.get("S2C_FUSED_MLP", "1") != "0"
+USE_FUSED_MLP = os.environ.get("S2C_FUSED_MLP", "0") != "0"
 
 
 def point_major(features):

@@ -1,0 +1,99 @@
+"""No-GPU checks of the drop-in boundary: libs2c.so loads, exports every symbol include/s2c.h declares (and
+nothing is declared twice), argument validation returns error codes + messages without touching a device, the
+drop-in aliasing works, and the product package never imports the oracle."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "s2c.h")).read()
+    return re.findall(r"S2C_API\s+(?:const\s+char\s*\*|int)\s*(s2c_\w+)\s*\(", txt)
+
+
+def test_library_exports_every_declared_symbol():
+    from scan2cap_b200 import _lib
+    names = _declared()
+    assert len(names) == len(set(names)) and len(names) >= 15
+    for n in names:
+        assert hasattr(_lib.LIB, n), n
+    # and every symbol the Python side binds is declared in the header
+    for n in _lib.SIGNATURES:
+        assert n in names, "%s bound in _lib.py but not declared in include/s2c.h" % n
+    assert _lib.LIB.s2c_version() >= 100
+
+
+def test_argument_validation_without_a_device():
+    from scan2cap_b200 import _lib
+    L = _lib.LIB
+    # nsample out of range -> S2C_ERR_INVALID_ARGUMENT before any CUDA call
+    rc = L.s2c_ball_query(None, None, 1, 10, 4, ctypes.c_float(0.1), 0, None, None, None)
+    assert rc == 1 and b"nsample" in L.s2c_last_error()
+    rc = L.s2c_furthest_point_sampling(None, 1, 0, 4, None, None, None)
+    assert rc == 1
+    rc = L.s2c_mlp_layer_fwd(None, 8, 128, 8, None, None, None, 24, None, 24, None, None, None)
+    assert rc == 1 and b"multiple of 16" in L.s2c_last_error()
+    # empty problems are a no-op, not an error
+    assert L.s2c_ball_query(None, None, 0, 0, 0, ctypes.c_float(0.1), 4, None, None, None) == 0
+    with pytest.raises(_lib.S2CError):
+        _lib.call("s2c_knn_adjacency", None, None, None, 1, 2000, 1, 10, 1, 0, 0.5, None, None, None)
+
+
+def test_dropin_aliases():
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "import scan2cap_b200.dropin as d; d.install()\n"
+            "from models.capnet import CapNet\n"
+            "from lib.pointnet2.pointnet2_modules import PointnetSAModuleVotes, PointnetFPModule\n"
+            "from lib.pointnet2.pytorch_utils import BNMomentumScheduler\n"
+            "import pointnet2._ext as _ext\n"
+            "assert CapNet.__module__ == 'scan2cap_b200.models.capnet'\n"
+            "assert all(hasattr(_ext, n) for n in ['furthest_point_sampling','gather_points','gather_points_grad',"
+            "'ball_query','group_points','group_points_grad','three_nn','three_interpolate','three_interpolate_grad'])\n"
+            "print('ok')\n" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "scan2cap_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(dirpath, f)
+
+
+def test_state_dict_contract():
+    """Key names of the reference checkpoints."""
+    import numpy as np
+    from scan2cap_b200 import synthetic
+    from scan2cap_b200.data.scannet.model_util_scannet import ScannetDatasetConfig
+    from scan2cap_b200.models.capnet import CapNet
+    DC = ScannetDatasetConfig()
+    vocab, emb, _ = synthetic.make_vocabulary(50)
+    m = CapNet(DC.num_class, vocab, emb, DC.num_heading_bin, DC.num_size_cluster, DC.mean_size_arr, input_feature_dim=132,
+               num_locals=10, use_topdown=True, query_mode="center", graph_mode="edge_conv", num_graph_steps=2,
+               use_relation=True, use_orientation=True)
+    sd = m.state_dict()
+    for k, shape in {
+        "backbone_net.sa1.mlp_module.layer0.conv.weight": (64, 135, 1, 1),
+        "backbone_net.sa2.mlp_module.layer0.conv.weight": (128, 131, 1, 1),
+        "backbone_net.sa3.mlp_module.layer2.bn.bn.running_mean": (256,),
+        "backbone_net.fp1.mlp.layer0.conv.weight": (256, 512, 1, 1),
+        "vgen.conv3.weight": (259, 256, 1),
+        "proposal.vote_aggregation.mlp_module.layer0.conv.weight": (128, 259, 1, 1),
+        "proposal.proposal.6.weight": (97, 128, 1),
+        "graph.gc_layers.1.map_edge.2.weight": (128, 128),
+        "graph.edge_predict.weight": (7, 128),
+        "caption.map_topdown.0.weight": (300, 940),
+        "caption.recurrent_cell_2.weight_hh": (1536, 512),
+        "caption.classifier.weight": (50, 512),
+    }.items():
+        assert tuple(sd[k].shape) == shape, k
+    detector = [k for k in sd if k.startswith(("backbone_net", "vgen", "proposal"))]
+    assert len(detector) == 144  # the reference's PRETRAIN_VOTENET_* checkpoints hold exactly these 144 tensors

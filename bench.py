@@ -336,9 +336,14 @@ def main():
         M, ns = 2048, 64
         alg = B * (12 * N + 12 * M + 4 * C * N + 4 * M * ns + 4 * (3 + C) * M * ns)
         achieved = alg / (t_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get(args.config, {}).get("traffic")
         line["roofline"] = {"bound": "hbm", "kernel": "ball_query_kernel<GROUP> (SA1: N=%d, M=2048, nsample=64, C=%d)" % (N, C),
                             "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                            "traffic": None, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": t_ms,
+                            "traffic": traffic, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": t_ms,
                             "peak_source": pk_src}
     if not args.no_cpu_baseline and world == 1:
         try:

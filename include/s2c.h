@@ -174,6 +174,14 @@ S2C_API int s2c_pool_bwd_stats(const float *dpool, const int *argmax, const floa
                                int ns, int N, const float *scale, const float *shift, double *sum_g,
                                double *sum_gy, void *stream);
 
+/* mlp_layer_fwd_v2 -- same contract as s2c_mlp_layer_fwd, warp-specialised and fed by the TMA engine
+ *   (cp.async.bulk + mbarrier pipeline: loader / transform / MMA / epilogue warps, double-buffered TMEM).
+ *   Extra requirements: N in {64,128,256}; K, lda, ldc multiples of 4; A, C 16-byte aligned;
+ *   wprep = workspace of ceil(K/32)*N*256 bytes (16-byte aligned) for the split / swizzled weights. */
+S2C_API int s2c_mlp_layer_fwd_v2(const float *A, long long lda, long long R, int K, const float *pro_scale,
+                                 const float *pro_shift, const float *W, int N, float *C, long long ldc,
+                                 double *stat_sum, double *stat_sumsq, void *wprep, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,393 @@
+// Pipelined, warp-specialised version of the grouped-MLP layer kernel (see mlp.cu for the arithmetic):
+//
+//   loader warp      cp.async.bulk (TMA engine, no register staging) : raw fp32 rows of the activation tile -> smem ring,
+//                    and the pre-split / pre-swizzled weight chunk straight into the operand stage; mbarrier complete_tx
+//   transform warps  raw tile -> [previous layer's BatchNorm + ReLU] -> tf32 hi/lo split -> K-major SWIZZLE_128B operand
+//   MMA warp         one thread issues tcgen05.mma.cta_group::1.kind::tf32 (3xTF32), tcgen05.commit -> mbarriers
+//   epilogue warps   tcgen05.ld from the DOUBLE-BUFFERED TMEM accumulator -> 128-byte row stores + per-channel sum / sumsq
+//                    (warp transpose-reduce), overlapping the next tile's loads and MMAs
+// Every hand-off is an mbarrier; nothing in the steady state is a CTA-wide barrier.
+#include "s2c_common.cuh"
+
+namespace s2c {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 32;
+constexpr int OS = 2;  // operand stages
+constexpr int kLoaderWarp = 0, kMmaWarp = 1, kFirstTransformWarp = 2, kFirstEpilogueWarp = 6;
+constexpr int kThreads = 10 * 32;
+
+struct Gemm2Args {
+  const float *A; long long lda; int K;
+  const float *pro_scale; const float *pro_shift;
+  const unsigned char *wprep;  // KC chunks of [hi: N x 128 B swizzled][lo: N x 128 B swizzled]
+  float *C; long long ldc;
+  double *stat_sum; double *stat_sumsq;
+  long long R;
+  int RS;  // raw stages
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy executed by the TMA engine; completes `bytes` on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+  uint32_t *u = reinterpret_cast<uint32_t *>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+        "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+        "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {  // K-major SWIZZLE_128B, SBO = 1024 B, version 1
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__host__ __device__ __forceinline__ uint32_t swz(int r, int seg) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((seg ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ void split_tf32(float v, float &hi, float &lo) {
+  hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  lo = v - hi;
+}
+__device__ __forceinline__ void store_split(unsigned char *hi_base, unsigned char *lo_base, uint32_t off, float4 v) {
+  float4 h, l;
+  split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+  *reinterpret_cast<float4 *>(hi_base + off) = h;
+  *reinterpret_cast<float4 *>(lo_base + off) = l;
+}
+
+// lane l ends with the sum over the warp's 32 lanes of v[l] (transpose-reduce, 31 shuffles); v is clobbered
+__device__ __forceinline__ float warp_colsum32(float *v, int lane) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool up = (lane & w) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float keep = up ? v[i + w] : v[i];
+      const float send = up ? v[i] : v[i + w];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  return v[0];
+}
+
+// weight preparation: W (N, K) fp32 -> per K-chunk [hi | lo] blocks in the operand layout (done once per call)
+__global__ void w_prep_kernel(const float *__restrict__ W, int N, int K, unsigned char *__restrict__ out) {
+  const int KC = (K + BK - 1) / BK;
+  const int total = KC * N * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int seg = i & 7, r = (i >> 3) % N, kc = i / (8 * N);
+    const int kk = kc * BK + seg * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float *p = W + (size_t)r * K + kk;
+    if (kk + 0 < K) v.x = p[0];
+    if (kk + 1 < K) v.y = p[1];
+    if (kk + 2 < K) v.z = p[2];
+    if (kk + 3 < K) v.w = p[3];
+    unsigned char *hi = out + (size_t)kc * N * 256;
+    store_split(hi, hi + (size_t)N * 128, swz(r, seg), v);
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_gemm2_kernel(Gemm2Args g) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  constexpr uint32_t A_BYTES = BM * BK * 4;            // 16 KB per hi / lo / raw block
+  constexpr uint32_t W_BYTES = N * BK * 4;             // N x 128 B per hi / lo block
+  constexpr uint32_t OP_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+  constexpr uint32_t TMEM_COLS = (2 * N <= 32) ? 32 : (2 * N <= 64) ? 64 : (2 * N <= 128) ? 128 : (2 * N <= 256) ? 256 : 512;
+  const int RS = g.RS;
+  const int KC = (g.K + BK - 1) / BK;
+  unsigned char *op_base = smem;
+  unsigned char *raw_base = smem + OS * OP_BYTES;
+  float *s_scale = reinterpret_cast<float *>(raw_base + (size_t)RS * A_BYTES);
+  float *s_shift = s_scale + KC * BK;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_shift + KC * BK);
+  uint64_t *raw_full = bars, *raw_empty = bars + 4, *op_full = bars + 8, *op_empty = bars + 10, *acc_full = bars + 12,
+           *acc_empty = bars + 14;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool has_pro = g.pro_scale != nullptr;
+  if (tid == 0) {
+    for (int s = 0; s < RS; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 128); }
+    for (int s = 0; s < OS; ++s) { mbar_init(&op_full[s], 129); mbar_init(&op_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, TMEM_COLS);
+  for (int k = tid; k < KC * BK; k += kThreads) {
+    s_scale[k] = (has_pro && k < g.K) ? g.pro_scale[k] : 1.f;
+    s_shift[k] = (has_pro && k < g.K) ? g.pro_shift[k] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const long long num_tiles = (g.R + BM - 1) / BM;
+  const long long my_tiles = (num_tiles > (long long)blockIdx.x) ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const long long total_chunks = my_tiles * KC;
+
+  if (warp == kLoaderWarp) {
+    // ===================== loader: raw activation rows (ring of RS) and weight chunks (into the operand stage)
+    long long ia = 0, iw = 0;          // next raw chunk / next weight chunk to issue
+    long long ta = blockIdx.x; int ka = 0;  // (tile, kc) of chunk ia
+    int kw = 0;
+    while (iw < total_chunks) {
+      if (ia < total_chunks) {
+        const int rs = (int)(ia % RS);
+        if (ia < RS || mbar_test(&raw_empty[rs], (uint32_t)(((ia / RS) - 1) & 1))) {
+          const long long row0 = ta * BM;
+          const int rows = (int)((g.R - row0) < BM ? (g.R - row0) : BM);
+          const int k0 = ka * BK;
+          const uint32_t row_bytes = (uint32_t)(((g.K - k0) < BK ? (g.K - k0) : BK) * 4);
+          if (lane == 0) mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)rows * row_bytes);
+          __syncwarp();
+          unsigned char *dst = raw_base + (size_t)rs * A_BYTES;
+          for (int r = lane; r < rows; r += 32)
+            bulk_g2s(dst + r * 128, g.A + (row0 + r) * g.lda + k0, row_bytes, &raw_full[rs]);
+          ++ia;
+          if (++ka == KC) { ka = 0; ta += gridDim.x; }
+        }
+      }
+      {
+        const int os = (int)(iw % OS);
+        if (iw < OS || mbar_test(&op_empty[os], (uint32_t)(((iw / OS) - 1) & 1))) {
+          if (lane == 0) {
+            unsigned char *dst = op_base + (size_t)os * OP_BYTES + 2 * A_BYTES;
+            mbar_arrive_expect_tx(&op_full[os], 2 * W_BYTES);
+            bulk_g2s(dst, g.wprep + (size_t)kw * 2 * W_BYTES, 2 * W_BYTES, &op_full[os]);
+          }
+          __syncwarp();
+          ++iw;
+          if (++kw == KC) kw = 0;
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer
+    const uint32_t idesc = make_idesc(BM, N);
+    long long it = 0;
+    for (long long t = 0; t < my_tiles; ++t) {
+      const int ab = (int)(t & 1);
+      if (t >= 2) mbar_wait(&acc_empty[ab], (uint32_t)(((t >> 1) - 1) & 1));
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(ab * N);
+      for (int kc = 0; kc < KC; ++kc, ++it) {
+        const int os = (int)(it % OS);
+        mbar_wait(&op_full[os], (uint32_t)((it / OS) & 1));
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t ah = smem_u32(op_base + (size_t)os * OP_BYTES), al = ah + A_BYTES, bh = al + A_BYTES, bl = bh + W_BYTES;
+#pragma unroll
+          for (int j = 0; j < BK / 8; ++j) {
+            const uint32_t o = j * 32;
+            umma_tf32(d_tmem, make_desc(ah + o), make_desc(bh + o), idesc, (kc | j) ? 1u : 0u);
+            umma_tf32(d_tmem, make_desc(ah + o), make_desc(bl + o), idesc, 1u);
+            umma_tf32(d_tmem, make_desc(al + o), make_desc(bh + o), idesc, 1u);
+          }
+          umma_commit(&op_empty[os]);
+          if (kc == KC - 1) umma_commit(&acc_full[ab]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < kFirstEpilogueWarp) {
+    // ===================== transform: raw rows -> prologue -> hi/lo split -> swizzled operand
+    const int tt = tid - kFirstTransformWarp * 32;  // 0..127
+    const int seg = tt & 7;
+    long long it = 0;
+    for (long long t = 0; t < my_tiles; ++t) {
+      const long long row0 = ((long long)blockIdx.x + t * gridDim.x) * BM;
+      for (int kc = 0; kc < KC; ++kc, ++it) {
+        const int rs = (int)(it % RS), os = (int)(it % OS);
+        const int kk = kc * BK + seg * 4;
+        const float4 sc = *reinterpret_cast<const float4 *>(s_scale + kk);
+        const float4 sh = *reinterpret_cast<const float4 *>(s_shift + kk);
+        mbar_wait(&raw_full[rs], (uint32_t)((it / RS) & 1));
+        if (it >= OS) mbar_wait(&op_empty[os], (uint32_t)(((it / OS) - 1) & 1));
+        const unsigned char *raw = raw_base + (size_t)rs * A_BYTES;
+        unsigned char *a_hi = op_base + (size_t)os * OP_BYTES, *a_lo = a_hi + A_BYTES;
+#pragma unroll
+        for (int pass = 0; pass < BM / 16; ++pass) {
+          const int r = pass * 16 + (tt >> 3);
+          float4 v = *reinterpret_cast<const float4 *>(raw + r * 128 + seg * 16);
+          if (has_pro) {
+            v.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f); v.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
+            v.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f); v.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
+          }
+          const bool row_ok = (row0 + r) < g.R;  // stale smem beyond the copied bytes is masked, never multiplied
+          if (!row_ok || kk + 0 >= g.K) v.x = 0.f;
+          if (!row_ok || kk + 1 >= g.K) v.y = 0.f;
+          if (!row_ok || kk + 2 >= g.K) v.z = 0.f;
+          if (!row_ok || kk + 3 >= g.K) v.w = 0.f;
+          store_split(a_hi, a_lo, swz(r, seg), v);
+        }
+        fence_async_proxy();
+        mbar_arrive(&op_full[os]);
+        mbar_arrive(&raw_empty[rs]);
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global rows (+ column statistics)
+    const int q = warp & 3;  // the TMEM lane quarter this warp may access
+    const bool has_stats = g.stat_sum != nullptr;
+    float acc_s[N / 32], acc_q[N / 32];
+#pragma unroll
+    for (int i = 0; i < N / 32; ++i) { acc_s[i] = 0.f; acc_q[i] = 0.f; }
+    for (long long t = 0; t < my_tiles; ++t) {
+      const int ab = (int)(t & 1);
+      const long long row = ((long long)blockIdx.x + t * gridDim.x) * BM + q * 32 + lane;
+      mbar_wait(&acc_full[ab], (uint32_t)((t >> 1) & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int cb = 0; cb < N / 32; ++cb) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * N + cb * 32), v);
+        if (row < g.R) {
+          float4 *dst = reinterpret_cast<float4 *>(g.C + row * g.ldc + cb * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        if (has_stats) {  // rows beyond R were staged as zeros, so they add nothing
+          float sq[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+          acc_s[cb] += warp_colsum32(v, lane);
+          acc_q[cb] += warp_colsum32(sq, lane);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[ab]);
+    }
+    if (has_stats) {
+#pragma unroll
+      for (int cb = 0; cb < N / 32; ++cb) {
+        atomicAdd(g.stat_sum + cb * 32 + lane, (double)acc_s[cb]);
+        atomicAdd(g.stat_sumsq + cb * 32 + lane, (double)acc_q[cb]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+size_t gemm2_smem(int N, int K, int RS) {
+  const int KC = (K + BK - 1) / BK;
+  return (size_t)OS * (2 * BM * BK * 4 + 2 * (size_t)N * BK * 4) + (size_t)RS * BM * BK * 4 + (size_t)2 * KC * BK * 4 + 16 * 8 + 16;
+}
+
+template <int N>
+int launch_gemm2(const Gemm2Args &g0, cudaStream_t st) {
+  Gemm2Args g = g0;
+  int RS = 3;
+  while (RS > 1 && gemm2_smem(N, g.K, RS) > 227 * 1024) --RS;
+  const size_t smem = gemm2_smem(N, g.K, RS);
+  if (smem > 227 * 1024) {
+    set_error("mlp_layer_fwd: shared memory %zu B exceeds 227 KB (N=%d K=%d)", smem, N, g.K);
+    return S2C_ERR_UNSUPPORTED;
+  }
+  g.RS = RS;
+  auto kern = mlp_gemm2_kernel<N>;
+  S2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "mlp_gemm2 smem attr");
+  const long long tiles = (g.R + BM - 1) / BM;
+  const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+  kern<<<grid, kThreads, smem, st>>>(g);
+  S2C_CHECK_LAUNCH("mlp_gemm2 launch");
+  return S2C_OK;
+}
+
+}  // namespace
+}  // namespace s2c
+
+// Pipelined layer kernel.  Extra requirements over s2c_mlp_layer_fwd: N in {64,128,256}; K, lda, ldc multiples of 4;
+// A and C 16-byte aligned; `wprep` = caller-provided workspace of ceil(K/32) * N * 256 bytes (16-byte aligned).
+extern "C" int s2c_mlp_layer_fwd_v2(const float *A, long long lda, long long R, int K, const float *pro_scale,
+                                    const float *pro_shift, const float *W, int N, float *C, long long ldc,
+                                    double *stat_sum, double *stat_sumsq, void *wprep, void *stream) {
+  using namespace s2c;
+  S2C_REQUIRE(R >= 0 && K >= 4, "mlp_layer_fwd_v2: bad sizes");
+  S2C_REQUIRE(N == 64 || N == 128 || N == 256, "mlp_layer_fwd_v2: N=%d must be 64, 128 or 256", N);
+  S2C_REQUIRE((K & 3) == 0 && (lda & 3) == 0 && (ldc & 3) == 0 && lda >= K && ldc >= N, "mlp_layer_fwd_v2: K, lda, ldc must be multiples of 4 (K=%d lda=%lld ldc=%lld)", K, lda, ldc);
+  S2C_REQUIRE((pro_scale == nullptr) == (pro_shift == nullptr), "mlp_layer_fwd_v2: scale/shift must both be given or both null");
+  S2C_REQUIRE((stat_sum == nullptr) == (stat_sumsq == nullptr), "mlp_layer_fwd_v2: stat pointers must both be given or both null");
+  if (R == 0) return S2C_OK;
+  S2C_REQUIRE(A && W && C && wprep, "mlp_layer_fwd_v2: null pointer");
+  S2C_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)C & 15) == 0 && ((uintptr_t)wprep & 15) == 0, "mlp_layer_fwd_v2: A, C and wprep must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int KC = (K + BK - 1) / BK;
+  w_prep_kernel<<<ceil_div(KC * N * 8, 256), 256, 0, st>>>(W, N, K, (unsigned char *)wprep);
+  S2C_CHECK_LAUNCH("w_prep");
+  Gemm2Args g;
+  g.A = A; g.lda = lda; g.K = K; g.pro_scale = pro_scale; g.pro_shift = pro_shift; g.wprep = (const unsigned char *)wprep;
+  g.C = C; g.ldc = ldc; g.stat_sum = stat_sum; g.stat_sumsq = stat_sumsq; g.R = R; g.RS = 0;
+  if (N == 64) return launch_gemm2<64>(g, st);
+  if (N == 128) return launch_gemm2<128>(g, st);
+  return launch_gemm2<256>(g, st);
+}

@@ -5,7 +5,12 @@ from ..._lib import call
 from ._ext import _guard, _stream
 
 
-def mlp_layer_fwd(A, W, pro_scale=None, pro_shift=None, want_stats=True, K=None):
+import os
+
+KERNEL_VERSION = int(os.environ.get("S2C_MLP_KERNEL", "2"))  # 2 = pipelined (default), 1 = single-role kernel
+
+
+def mlp_layer_fwd(A, W, pro_scale=None, pro_shift=None, want_stats=True, K=None, version=None):
     """A (R, lda) fp32 (row stride lda >= K), W (N, K) -> C (R, N) = relu(A*scale+shift) @ W^T [no prologue when
     scale is None], plus float64 column sums / sums of squares of C when want_stats."""
     assert A.is_cuda and A.dtype == torch.float32 and A.dim() == 2 and A.stride(1) == 1
@@ -19,12 +24,23 @@ def mlp_layer_fwd(A, W, pro_scale=None, pro_shift=None, want_stats=True, K=None)
     if want_stats:
         stats = torch.zeros((2, N), dtype=torch.float64, device=A.device)
         s1, s2 = stats[0], stats[1]
+    version = KERNEL_VERSION if version is None else version
+    v2_ok = (N in (64, 128, 256) and K % 4 == 0 and lda % 4 == 0 and A.data_ptr() % 16 == 0 and K >= 4)
     with _guard(A):
-        call("s2c_mlp_layer_fwd", A.data_ptr(), lda, R, K,
-             pro_scale.data_ptr() if pro_scale is not None else None,
-             pro_shift.data_ptr() if pro_shift is not None else None,
-             W.data_ptr(), N, C.data_ptr(), N,
-             s1.data_ptr() if want_stats else None, s2.data_ptr() if want_stats else None, _stream(A))
+        if version == 2 and v2_ok:
+            wprep = torch.empty(((K + 31) // 32) * N * 256, dtype=torch.uint8, device=A.device)
+            call("s2c_mlp_layer_fwd_v2", A.data_ptr(), lda, R, K,
+                 pro_scale.data_ptr() if pro_scale is not None else None,
+                 pro_shift.data_ptr() if pro_shift is not None else None,
+                 W.data_ptr(), N, C.data_ptr(), N,
+                 s1.data_ptr() if want_stats else None, s2.data_ptr() if want_stats else None, wprep.data_ptr(),
+                 _stream(A))
+        else:
+            call("s2c_mlp_layer_fwd", A.data_ptr(), lda, R, K,
+                 pro_scale.data_ptr() if pro_scale is not None else None,
+                 pro_shift.data_ptr() if pro_shift is not None else None,
+                 W.data_ptr(), N, C.data_ptr(), N,
+                 s1.data_ptr() if want_stats else None, s2.data_ptr() if want_stats else None, _stream(A))
     return (C, s1, s2) if want_stats else C
 
 

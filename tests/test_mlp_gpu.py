@@ -6,12 +6,14 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.mark.parametrize("version", [1, 2])
 @pytest.mark.parametrize("R,K,N,lda,pro", [
     (1000, 7, 64, 7, False), (4096, 64, 64, 64, True), (128 * 300 + 5, 64, 128, 64, True),
     (5000, 131, 128, 131, False), (3000, 259, 128, 260, True), (20000, 128, 256, 128, True),
-    (777, 32, 16, 40, False), (2048 * 64, 8, 64, 8, False),
+    (777, 32, 16, 40, False), (2048 * 64, 8, 64, 8, False), (5000, 132, 128, 132, True), (3000, 260, 128, 260, True),
+    (9000, 512, 256, 512, True), (100, 64, 64, 64, True),
 ])
-def test_mlp_layer_fwd_matches_float64(R, K, N, lda, pro):
+def test_mlp_layer_fwd_matches_float64(R, K, N, lda, pro, version):
     from scan2cap_b200.lib.pointnet2 import _ext_mlp
     torch.manual_seed(R + K + N)
     buf = torch.randn(R, lda, device=DEV)
@@ -24,7 +26,7 @@ def test_mlp_layer_fwd_matches_float64(R, K, N, lda, pro):
         shift = torch.randn(K, device=DEV) * 0.3
         A64 = torch.relu(A64 * scale.double() + shift.double())
     want = A64 @ W.double().t()
-    C, s1, s2 = _ext_mlp.mlp_layer_fwd(buf if lda != K else A, W, scale, shift, want_stats=True, K=K)
+    C, s1, s2 = _ext_mlp.mlp_layer_fwd(buf if lda != K else A, W, scale, shift, want_stats=True, K=K, version=version)
     torch.cuda.synchronize()
     err = float((C.double() - want).abs().max() / want.abs().max())
     assert err < 5e-6, "3xTF32 GEMM error %g" % err

@@ -201,7 +201,8 @@ mlp_gemm2_kernel(Gemm2Args g) {
     while (iw < total_chunks) {
       if (ia < total_chunks) {
         const int rs = (int)(ia % RS);
-        if (ia < RS || mbar_test(&raw_empty[rs], (uint32_t)(((ia / RS) - 1) & 1))) {
+        // lane 0 polls and broadcasts: the decision (and the counters below) must be warp-uniform
+        if (ia < RS || __shfl_sync(0xffffffffu, lane == 0 ? (int)mbar_test(&raw_empty[rs], (uint32_t)(((ia / RS) - 1) & 1)) : 0, 0)) {
           const long long row0 = ta * BM;
           const int rows = (int)((g.R - row0) < BM ? (g.R - row0) : BM);
           const int k0 = ka * BK;
@@ -217,7 +218,7 @@ mlp_gemm2_kernel(Gemm2Args g) {
       }
       {
         const int os = (int)(iw % OS);
-        if (iw < OS || mbar_test(&op_empty[os], (uint32_t)(((iw / OS) - 1) & 1))) {
+        if (iw < OS || __shfl_sync(0xffffffffu, lane == 0 ? (int)mbar_test(&op_empty[os], (uint32_t)(((iw / OS) - 1) & 1)) : 0, 0)) {
           if (lane == 0) {
             unsigned char *dst = op_base + (size_t)os * OP_BYTES + 2 * A_BYTES;
             mbar_arrive_expect_tx(&op_full[os], 2 * W_BYTES);
@@ -347,6 +348,7 @@ template <int N>
 int launch_gemm2(const Gemm2Args &g0, cudaStream_t st) {
   Gemm2Args g = g0;
   int RS = 3;
+  if (const char *e = getenv("S2C_MLP_RS")) RS = atoi(e) >= 1 && atoi(e) <= 3 ? atoi(e) : 3;  // tuning / debugging knob
   while (RS > 1 && gemm2_smem(N, g.K, RS) > 227 * 1024) --RS;
   const size_t smem = gemm2_smem(N, g.K, RS);
   if (smem > 227 * 1024) {

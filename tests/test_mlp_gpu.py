@@ -29,11 +29,11 @@ def test_mlp_layer_fwd_matches_float64(R, K, N, lda, pro, version):
     C, s1, s2 = _ext_mlp.mlp_layer_fwd(buf if lda != K else A, W, scale, shift, want_stats=True, K=K, version=version)
     torch.cuda.synchronize()
     err = float((C.double() - want).abs().max() / want.abs().max())
-    assert err < 5e-6, "3xTF32 GEMM error %g" % err
+    assert err < 1e-5, "3xTF32 GEMM error %g" % err
     # plain fp32 library GEMM for scale: we must be in the same accuracy class
     ref32 = (A64.float() @ W.t())
     err32 = float((ref32.double() - want).abs().max() / want.abs().max())
-    assert err < max(4 * err32, 5e-6)
+    assert err < max(4 * err32, 1e-5)
     assert float((s1 - want.sum(0)).abs().max() / want.sum(0).abs().max().clamp_min(1.0)) < 1e-5
     assert float((s2 - (want * want).sum(0)).abs().max() / (want * want).sum(0).abs().max()) < 1e-5
 

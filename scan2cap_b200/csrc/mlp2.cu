@@ -7,6 +7,8 @@
 //   epilogue warps   tcgen05.ld from the DOUBLE-BUFFERED TMEM accumulator -> 128-byte row stores + per-channel sum / sumsq
 //                    (warp transpose-reduce), overlapping the next tile's loads and MMAs
 // Every hand-off is an mbarrier; nothing in the steady state is a CTA-wide barrier.
+#include <cuda.h>
+
 #include "s2c_common.cuh"
 
 namespace s2c {
@@ -153,9 +155,19 @@ __global__ void w_prep_kernel(const float *__restrict__ W, int N, int K, unsigne
   }
 }
 
+// 2-D TMA load of one [128 rows x 32 fp32] box of the activation matrix (rows / columns outside the tensor are
+// zero-filled by the hardware); completes 16 KB on the mbarrier
+__device__ __forceinline__ void tma_load_box(void *dst_smem, const CUtensorMap *tmap, int x, int y, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+
 template <int N>
 __global__ void __launch_bounds__(kThreads, 1)
-mlp_gemm2_kernel(Gemm2Args g) {
+mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   constexpr uint32_t A_BYTES = BM * BK * 4;            // 16 KB per hi / lo / raw block
   constexpr uint32_t W_BYTES = N * BK * 4;             // N x 128 B per hi / lo block
@@ -195,6 +207,7 @@ mlp_gemm2_kernel(Gemm2Args g) {
 
   if (warp == kLoaderWarp) {
     // ===================== loader: raw activation rows (ring of RS) and weight chunks (into the operand stage)
+    if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
     long long ia = 0, iw = 0;          // next raw chunk / next weight chunk to issue
     long long ta = blockIdx.x; int ka = 0;  // (tile, kc) of chunk ia
     int kw = 0;
@@ -203,15 +216,11 @@ mlp_gemm2_kernel(Gemm2Args g) {
         const int rs = (int)(ia % RS);
         // lane 0 polls and broadcasts: the decision (and the counters below) must be warp-uniform
         if (ia < RS || __shfl_sync(0xffffffffu, lane == 0 ? (int)mbar_test(&raw_empty[rs], (uint32_t)(((ia / RS) - 1) & 1)) : 0, 0)) {
-          const long long row0 = ta * BM;
-          const int rows = (int)((g.R - row0) < BM ? (g.R - row0) : BM);
-          const int k0 = ka * BK;
-          const uint32_t row_bytes = (uint32_t)(((g.K - k0) < BK ? (g.K - k0) : BK) * 4);
-          if (lane == 0) mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)rows * row_bytes);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&raw_full[rs], A_BYTES);
+            tma_load_box(raw_base + (size_t)rs * A_BYTES, &tmap_a, ka * BK, (int)(ta * BM), &raw_full[rs]);
+          }
           __syncwarp();
-          unsigned char *dst = raw_base + (size_t)rs * A_BYTES;
-          for (int r = lane; r < rows; r += 32)
-            bulk_g2s(dst + r * 128, g.A + (row0 + r) * g.lda + k0, row_bytes, &raw_full[rs]);
           ++ia;
           if (++ka == KC) { ka = 0; ta += gridDim.x; }
         }
@@ -282,7 +291,7 @@ mlp_gemm2_kernel(Gemm2Args g) {
             v.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f); v.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
             v.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f); v.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
           }
-          const bool row_ok = (row0 + r) < g.R;  // stale smem beyond the copied bytes is masked, never multiplied
+          const bool row_ok = (row0 + r) < g.R;  // TMA zero-fills out-of-range elements; relu(0*s+t) may not be 0
           if (!row_ok || kk + 0 >= g.K) v.x = 0.f;
           if (!row_ok || kk + 1 >= g.K) v.y = 0.f;
           if (!row_ok || kk + 2 >= g.K) v.z = 0.f;
@@ -344,9 +353,43 @@ size_t gemm2_smem(int N, int K, int RS) {
   return (size_t)OS * (2 * BM * BK * 4 + 2 * (size_t)N * BK * 4) + (size_t)RS * BM * BK * 4 + (size_t)2 * KC * BK * 4 + 16 * 8 + 16;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {  // driver entry point through the runtime: no link-time dependency on libcuda
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
 template <int N>
 int launch_gemm2(const Gemm2Args &g0, cudaStream_t st) {
   Gemm2Args g = g0;
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) {
+    set_error("mlp_layer_fwd_v2: cuTensorMapEncodeTiled is not available from this driver");
+    return S2C_ERR_UNSUPPORTED;
+  }
+  CUtensorMap tmap;
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)g.K, (cuuint64_t)g.R};
+    const cuuint64_t strides[1] = {(cuuint64_t)g.lda * 4};
+    const cuuint32_t box[2] = {BK, BM};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(g.A), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("mlp_layer_fwd_v2: cuTensorMapEncodeTiled failed (%d) for R=%lld K=%d lda=%lld", (int)r, g.R, g.K, g.lda);
+      return S2C_ERR_CUDA;
+    }
+  }
   int RS = 3;
   if (const char *e = getenv("S2C_MLP_RS")) RS = atoi(e) >= 1 && atoi(e) <= 3 ? atoi(e) : 3;  // tuning / debugging knob
   while (RS > 1 && gemm2_smem(N, g.K, RS) > 227 * 1024) --RS;
@@ -360,7 +403,7 @@ int launch_gemm2(const Gemm2Args &g0, cudaStream_t st) {
   S2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "mlp_gemm2 smem attr");
   const long long tiles = (g.R + BM - 1) / BM;
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-  kern<<<grid, kThreads, smem, st>>>(g);
+  kern<<<grid, kThreads, smem, st>>>(g, tmap);
   S2C_CHECK_LAUNCH("mlp_gemm2 launch");
   return S2C_OK;
 }

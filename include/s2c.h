@@ -182,6 +182,24 @@ S2C_API int s2c_mlp_layer_fwd_v2(const float *A, long long lda, long long R, int
                                  const float *pro_shift, const float *W, int N, float *C, long long ldc,
                                  double *stat_sum, double *stat_sumsq, void *wprep, void *stream);
 
+/* mlp_layer_bwd_data -- backward "data" pass of one shared-MLP layer l on the tensor cores (same pipeline as
+ *   mlp_layer_fwd_v2), fusing BatchNorm backward, the 1x1-conv data gradient, the previous layer's ReLU mask and the
+ *   reductions of the previous layer's BatchNorm backward:
+ *       dY_l   = a[k]*g_l + b[k]*Y_l + c[k]              (BatchNorm-backward of layer l is affine per channel)
+ *       g_prev = (dY_l * W_l) masked by relu(bn_{l-1}(Y_prev)) > 0                     -> C (R, ldc)
+ *       stat_sum[n] += sum_r g_prev,  stat_sumsq[n] += sum_r g_prev * Y_prev           (float64; caller zeroes)
+ *   g_l: dense G (R, ldg), or for the LAST layer rebuilt from the pooled gradient: dpool / argmax (R/ns, K) with
+ *   last_scale/last_shift [K] = that layer's folded BatchNorm (its ReLU mask).  W (K, N) row-major = Conv2d weight
+ *   of layer l (K = C_l, N = C_{l-1}); N in {64,128,256}; K and all leading dimensions multiples of 4.
+ *   dY_out (R, K) optional: dY_l written back.  wprep: workspace of ceil(K/32)*N*256 bytes.
+ *   Replaces autograd through BatchNorm2d/ReLU/Conv2d of pytorch_utils.py:88-120 (cuDNN dgrad + ATen BN backward). */
+S2C_API int s2c_mlp_layer_bwd_data(const float *G, long long ldg, const float *Y, long long ldy, long long R, int K,
+                                   const float *a, const float *b, const float *c, const float *dpool,
+                                   const int *argmax, int ns, const float *last_scale, const float *last_shift,
+                                   const float *W, int N, const float *Yprev, long long ldyp,
+                                   const float *prev_scale, const float *prev_shift, float *C, long long ldc,
+                                   float *dY_out, double *stat_sum, double *stat_sumsq, void *wprep, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

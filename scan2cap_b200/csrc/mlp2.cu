@@ -20,11 +20,22 @@ constexpr int OS = 2;  // operand stages
 constexpr int kLoaderWarp = 0, kMmaWarp = 1, kFirstTransformWarp = 2, kFirstEpilogueWarp = 6;
 constexpr int kThreads = 10 * 32;
 
+// operand prologues (applied by the transform warps while staging the A tile)
+constexpr int PRO_BNRELU = 1;   // a' = relu(a*p0[k] + p1[k])             (p0 == null: identity)         -- forward
+constexpr int PRO_AFFINE2 = 2;  // a' = p0[k]*g + p1[k]*y + p2[k]          two raw tiles (g = A, y = A2)  -- BatchNorm backward
+constexpr int PRO_POOL = 3;     // as AFFINE2 with g = (argmax == sample && relu active) ? dpool : 0     -- last layer
+// epilogues
+constexpr int EPI_STORE_STATS = 0;  // C = acc ; optional column sum / sum of squares
+constexpr int EPI_MASK_STATS = 1;   // C = acc where relu(bn(Yprev)) was active else 0 ; column sum(C), sum(C*Yprev)
+
 struct Gemm2Args {
   const float *A; long long lda; int K;
-  const float *pro_scale; const float *pro_shift;
+  const float *p0, *p1, *p2, *p3, *p4;  // per-K prologue coefficients (see PRO_*); p3/p4 = last layer's scale/shift (PRO_POOL)
+  const float *dpool; const int *argmax; int ns;  // PRO_POOL: (G, K) pooled gradient and arg-max sample
   const unsigned char *wprep;  // KC chunks of [hi: N x 128 B swizzled][lo: N x 128 B swizzled]
   float *C; long long ldc;
+  float *dY_out;  // optional (R, K): the staged operand a' written back (the weight-gradient GEMM consumes it)
+  const float *Yprev; long long ldyp; const float *e_scale, *e_shift;  // EPI_MASK_STATS
   double *stat_sum; double *stat_sumsq;
   long long R;
   int RS;  // raw stages
@@ -138,18 +149,21 @@ __device__ __forceinline__ float warp_colsum32(float *v, int lane) {
 }
 
 // weight preparation: W (N, K) fp32 -> per K-chunk [hi | lo] blocks in the operand layout (done once per call)
-__global__ void w_prep_kernel(const float *__restrict__ W, int N, int K, unsigned char *__restrict__ out) {
+// kmajor = 1: operand row n, column k = W[n*ld + k]   (forward: W is (N, K))
+// kmajor = 0: operand row n, column k = W[k*ld + n]   (backward data: the operand is W^T of a (K, N) weight)
+__global__ void w_prep_kernel(const float *__restrict__ W, int N, int K, int ld, int kmajor, unsigned char *__restrict__ out) {
   const int KC = (K + BK - 1) / BK;
   const int total = KC * N * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int seg = i & 7, r = (i >> 3) % N, kc = i / (8 * N);
     const int kk = kc * BK + seg * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float *p = W + (size_t)r * K + kk;
+    const size_t sk = kmajor ? 1 : (size_t)ld, sn = kmajor ? (size_t)ld : 1;
+    const float *p = W + (size_t)r * sn + (size_t)kk * sk;
     if (kk + 0 < K) v.x = p[0];
-    if (kk + 1 < K) v.y = p[1];
-    if (kk + 2 < K) v.z = p[2];
-    if (kk + 3 < K) v.w = p[3];
+    if (kk + 1 < K) v.y = p[sk];
+    if (kk + 2 < K) v.z = p[2 * sk];
+    if (kk + 3 < K) v.w = p[3 * sk];
     unsigned char *hi = out + (size_t)kc * N * 256;
     store_split(hi, hi + (size_t)N * 128, swz(r, seg), v);
   }
@@ -165,27 +179,29 @@ __device__ __forceinline__ void tma_load_box(void *dst_smem, const CUtensorMap *
       : "memory");
 }
 
-template <int N>
+template <int N, int PRO, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
-mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a) {
+mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2) {
   extern __shared__ __align__(1024) unsigned char smem[];
   constexpr uint32_t A_BYTES = BM * BK * 4;            // 16 KB per hi / lo / raw block
   constexpr uint32_t W_BYTES = N * BK * 4;             // N x 128 B per hi / lo block
   constexpr uint32_t OP_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+  constexpr uint32_t RAW_TILES = (PRO == PRO_AFFINE2) ? 2 : 1;   // raw tiles per chunk (g and y for the affine prologue)
+  constexpr uint32_t RAW_BYTES = RAW_TILES * A_BYTES;
+  constexpr int NPRO = (PRO == PRO_BNRELU) ? 2 : (PRO == PRO_AFFINE2) ? 3 : 5;
   constexpr uint32_t TMEM_COLS = (2 * N <= 32) ? 32 : (2 * N <= 64) ? 64 : (2 * N <= 128) ? 128 : (2 * N <= 256) ? 256 : 512;
   const int RS = g.RS;
   const int KC = (g.K + BK - 1) / BK;
   unsigned char *op_base = smem;
   unsigned char *raw_base = smem + OS * OP_BYTES;
-  float *s_scale = reinterpret_cast<float *>(raw_base + (size_t)RS * A_BYTES);
-  float *s_shift = s_scale + KC * BK;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(s_shift + KC * BK);
+  float *s_pro = reinterpret_cast<float *>(raw_base + (size_t)RS * RAW_BYTES);  // [NPRO][KC*BK] coefficients
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_pro + NPRO * KC * BK);
   uint64_t *raw_full = bars, *raw_empty = bars + 4, *op_full = bars + 8, *op_empty = bars + 10, *acc_full = bars + 12,
            *acc_empty = bars + 14;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool has_pro = g.pro_scale != nullptr;
+  const bool has_pro = g.p0 != nullptr;
   if (tid == 0) {
     for (int s = 0; s < RS; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 128); }
     for (int s = 0; s < OS; ++s) { mbar_init(&op_full[s], 129); mbar_init(&op_empty[s], 1); }
@@ -193,9 +209,14 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, TMEM_COLS);
-  for (int k = tid; k < KC * BK; k += kThreads) {
-    s_scale[k] = (has_pro && k < g.K) ? g.pro_scale[k] : 1.f;
-    s_shift[k] = (has_pro && k < g.K) ? g.pro_shift[k] : 0.f;
+  {
+    const float *src[5] = {g.p0, g.p1, g.p2, g.p3, g.p4};
+    for (int i = tid; i < NPRO * KC * BK; i += kThreads) {
+      const int a = i / (KC * BK), k = i - a * (KC * BK);
+      // identity defaults: scale-like arrays (index 0, and 3 for PRO_POOL) -> 1, the others -> 0
+      const float dflt = (a == 0 || a == 3) ? 1.f : 0.f;
+      s_pro[i] = (src[a] != nullptr && k < g.K) ? src[a][k] : dflt;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -217,8 +238,14 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a) {
         // lane 0 polls and broadcasts: the decision (and the counters below) must be warp-uniform
         if (ia < RS || __shfl_sync(0xffffffffu, lane == 0 ? (int)mbar_test(&raw_empty[rs], (uint32_t)(((ia / RS) - 1) & 1)) : 0, 0)) {
           if (lane == 0) {
-            mbar_arrive_expect_tx(&raw_full[rs], A_BYTES);
-            tma_load_box(raw_base + (size_t)rs * A_BYTES, &tmap_a, ka * BK, (int)(ta * BM), &raw_full[rs]);
+            mbar_arrive_expect_tx(&raw_full[rs], RAW_BYTES);
+            unsigned char *dst = raw_base + (size_t)rs * RAW_BYTES;
+            if (PRO == PRO_POOL) {  // only y comes through TMA; g is rebuilt from the pooled gradient
+              tma_load_box(dst, &tmap_a2, ka * BK, (int)(ta * BM), &raw_full[rs]);
+            } else {
+              tma_load_box(dst, &tmap_a, ka * BK, (int)(ta * BM), &raw_full[rs]);
+              if (PRO == PRO_AFFINE2) tma_load_box(dst + A_BYTES, &tmap_a2, ka * BK, (int)(ta * BM), &raw_full[rs]);
+            }
           }
           __syncwarp();
           ++ia;
@@ -277,26 +304,57 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a) {
       for (int kc = 0; kc < KC; ++kc, ++it) {
         const int rs = (int)(it % RS), os = (int)(it % OS);
         const int kk = kc * BK + seg * 4;
-        const float4 sc = *reinterpret_cast<const float4 *>(s_scale + kk);
-        const float4 sh = *reinterpret_cast<const float4 *>(s_shift + kk);
+        const int KP = KC * BK;
+        const float4 c0 = *reinterpret_cast<const float4 *>(s_pro + kk);
+        const float4 c1 = *reinterpret_cast<const float4 *>(s_pro + KP + kk);
+        float4 c2 = make_float4(0.f, 0.f, 0.f, 0.f), c3 = c2, c4 = c2;
+        if (PRO != PRO_BNRELU) c2 = *reinterpret_cast<const float4 *>(s_pro + 2 * KP + kk);
+        if (PRO == PRO_POOL) {
+          c3 = *reinterpret_cast<const float4 *>(s_pro + 3 * KP + kk);
+          c4 = *reinterpret_cast<const float4 *>(s_pro + 4 * KP + kk);
+        }
         mbar_wait(&raw_full[rs], (uint32_t)((it / RS) & 1));
         if (it >= OS) mbar_wait(&op_empty[os], (uint32_t)(((it / OS) - 1) & 1));
-        const unsigned char *raw = raw_base + (size_t)rs * A_BYTES;
+        const unsigned char *raw = raw_base + (size_t)rs * RAW_BYTES;
         unsigned char *a_hi = op_base + (size_t)os * OP_BYTES, *a_lo = a_hi + A_BYTES;
 #pragma unroll
         for (int pass = 0; pass < BM / 16; ++pass) {
           const int r = pass * 16 + (tt >> 3);
+          const long long row = row0 + r;
           float4 v = *reinterpret_cast<const float4 *>(raw + r * 128 + seg * 16);
-          if (has_pro) {
-            v.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f); v.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
-            v.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f); v.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
+          if (PRO == PRO_BNRELU) {
+            if (has_pro) {
+              v.x = fmaxf(fmaf(v.x, c0.x, c1.x), 0.f); v.y = fmaxf(fmaf(v.y, c0.y, c1.y), 0.f);
+              v.z = fmaxf(fmaf(v.z, c0.z, c1.z), 0.f); v.w = fmaxf(fmaf(v.w, c0.w, c1.w), 0.f);
+            }
+          } else if (PRO == PRO_AFFINE2) {
+            const float4 y = *reinterpret_cast<const float4 *>(raw + A_BYTES + r * 128 + seg * 16);
+            v.x = fmaf(c0.x, v.x, fmaf(c1.x, y.x, c2.x)); v.y = fmaf(c0.y, v.y, fmaf(c1.y, y.y, c2.y));
+            v.z = fmaf(c0.z, v.z, fmaf(c1.z, y.z, c2.z)); v.w = fmaf(c0.w, v.w, fmaf(c1.w, y.w, c2.w));
+          } else {  // PRO_POOL: v holds y
+            const float4 y = v;
+            float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < g.R && kk < g.K) {
+              const long long grp = row / g.ns;
+              const int smp = (int)(row - grp * g.ns);
+              const int4 am = __ldg(reinterpret_cast<const int4 *>(g.argmax + grp * g.K + kk));
+              const float4 dp = __ldg(reinterpret_cast<const float4 *>(g.dpool + grp * g.K + kk));
+              gg.x = (am.x == smp && fmaf(y.x, c3.x, c4.x) > 0.f) ? dp.x : 0.f;
+              gg.y = (am.y == smp && fmaf(y.y, c3.y, c4.y) > 0.f) ? dp.y : 0.f;
+              gg.z = (am.z == smp && fmaf(y.z, c3.z, c4.z) > 0.f) ? dp.z : 0.f;
+              gg.w = (am.w == smp && fmaf(y.w, c3.w, c4.w) > 0.f) ? dp.w : 0.f;
+            }
+            v.x = fmaf(c0.x, gg.x, fmaf(c1.x, y.x, c2.x)); v.y = fmaf(c0.y, gg.y, fmaf(c1.y, y.y, c2.y));
+            v.z = fmaf(c0.z, gg.z, fmaf(c1.z, y.z, c2.z)); v.w = fmaf(c0.w, gg.w, fmaf(c1.w, y.w, c2.w));
           }
-          const bool row_ok = (row0 + r) < g.R;  // TMA zero-fills out-of-range elements; relu(0*s+t) may not be 0
+          const bool row_ok = row < g.R;  // TMA zero-fills out-of-range elements, but the prologue may map 0 to non-zero
           if (!row_ok || kk + 0 >= g.K) v.x = 0.f;
           if (!row_ok || kk + 1 >= g.K) v.y = 0.f;
           if (!row_ok || kk + 2 >= g.K) v.z = 0.f;
           if (!row_ok || kk + 3 >= g.K) v.w = 0.f;
           store_split(a_hi, a_lo, swz(r, seg), v);
+          if (PRO != PRO_BNRELU && g.dY_out != nullptr && row_ok && kk < g.K)
+            *reinterpret_cast<float4 *>(g.dY_out + row * g.K + kk) = v;
         }
         fence_async_proxy();
         mbar_arrive(&op_full[os]);
@@ -319,17 +377,49 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a) {
       for (int cb = 0; cb < N / 32; ++cb) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * N + cb * 32), v);
-        if (row < g.R) {
-          float4 *dst = reinterpret_cast<float4 *>(g.C + row * g.ldc + cb * 32);
+        if (EPI == EPI_MASK_STATS) {
+          // gradient w.r.t. the previous layer's rectified output -> mask by its ReLU, store, and reduce the two
+          // per-channel sums its BatchNorm backward needs: sum(g) and sum(g * y)
+          float yv[32];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-        if (has_stats) {  // rows beyond R were staged as zeros, so they add nothing
-          float sq[32];
+          for (int j = 0; j < 32; ++j) yv[j] = 0.f;
+          if (row < g.R) {
+            const float4 *yp = reinterpret_cast<const float4 *>(g.Yprev + row * g.ldyp + cb * 32);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
-          acc_s[cb] += warp_colsum32(v, lane);
-          acc_q[cb] += warp_colsum32(sq, lane);
+            for (int j = 0; j < 8; ++j) {
+              const float4 t4 = __ldg(yp + j);
+              yv[4 * j] = t4.x; yv[4 * j + 1] = t4.y; yv[4 * j + 2] = t4.z; yv[4 * j + 3] = t4.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float esc = __ldg(g.e_scale + cb * 32 + j), esh = __ldg(g.e_shift + cb * 32 + j);
+            v[j] = (row < g.R && fmaf(yv[j], esc, esh) > 0.f) ? v[j] : 0.f;
+          }
+          if (row < g.R) {
+            float4 *dst = reinterpret_cast<float4 *>(g.C + row * g.ldc + cb * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (has_stats) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) yv[j] *= v[j];
+            acc_s[cb] += warp_colsum32(v, lane);
+            acc_q[cb] += warp_colsum32(yv, lane);
+          }
+        } else {
+          if (row < g.R) {
+            float4 *dst = reinterpret_cast<float4 *>(g.C + row * g.ldc + cb * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (has_stats) {  // rows beyond R were staged as zeros, so they add nothing
+            float sq[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+            acc_s[cb] += warp_colsum32(v, lane);
+            acc_q[cb] += warp_colsum32(sq, lane);
+          }
         }
       }
       tc_fence_before();
@@ -348,9 +438,10 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a) {
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-size_t gemm2_smem(int N, int K, int RS) {
+size_t gemm2_smem(int N, int K, int RS, int raw_tiles, int npro) {
   const int KC = (K + BK - 1) / BK;
-  return (size_t)OS * (2 * BM * BK * 4 + 2 * (size_t)N * BK * 4) + (size_t)RS * BM * BK * 4 + (size_t)2 * KC * BK * 4 + 16 * 8 + 16;
+  return (size_t)OS * (2 * BM * BK * 4 + 2 * (size_t)N * BK * 4) + (size_t)RS * raw_tiles * BM * BK * 4 +
+         (size_t)npro * KC * BK * 4 + 16 * 8 + 16;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -368,42 +459,51 @@ EncodeTiledFn encode_tiled() {  // driver entry point through the runtime: no li
   return fn;
 }
 
-template <int N>
-int launch_gemm2(const Gemm2Args &g0, cudaStream_t st) {
-  Gemm2Args g = g0;
+// tensor map of a row-major (R, ld) fp32 matrix with K valid columns, box = [128 rows x 32 columns]
+int make_tmap(CUtensorMap *tmap, const float *base, long long R, int K, long long ld) {
   EncodeTiledFn enc = encode_tiled();
   if (!enc) {
-    set_error("mlp_layer_fwd_v2: cuTensorMapEncodeTiled is not available from this driver");
+    set_error("mlp: cuTensorMapEncodeTiled is not available from this driver");
     return S2C_ERR_UNSUPPORTED;
   }
-  CUtensorMap tmap;
-  {
-    const cuuint64_t dims[2] = {(cuuint64_t)g.K, (cuuint64_t)g.R};
-    const cuuint64_t strides[1] = {(cuuint64_t)g.lda * 4};
-    const cuuint32_t box[2] = {BK, BM};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(g.A), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      set_error("mlp_layer_fwd_v2: cuTensorMapEncodeTiled failed (%d) for R=%lld K=%d lda=%lld", (int)r, g.R, g.K, g.lda);
-      return S2C_ERR_CUDA;
-    }
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)R};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {BK, BM};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("mlp: cuTensorMapEncodeTiled failed (%d) for R=%lld K=%d ld=%lld", (int)r, R, K, ld);
+    return S2C_ERR_CUDA;
   }
+  return S2C_OK;
+}
+
+template <int N, int PRO, int EPI>
+int launch_gemm2(const Gemm2Args &g0, const float *A2, long long lda2, cudaStream_t st) {
+  Gemm2Args g = g0;
+  constexpr int raw_tiles = (PRO == PRO_AFFINE2) ? 2 : 1;
+  constexpr int npro = (PRO == PRO_BNRELU) ? 2 : (PRO == PRO_AFFINE2) ? 3 : 5;
+  CUtensorMap tmap, tmap2;
+  int rc = make_tmap(&tmap, g.A ? g.A : A2, g.R, g.K, g.A ? g.lda : lda2);
+  if (rc) return rc;
+  rc = make_tmap(&tmap2, A2 ? A2 : g.A, g.R, g.K, A2 ? lda2 : g.lda);
+  if (rc) return rc;
   int RS = 3;
   if (const char *e = getenv("S2C_MLP_RS")) RS = atoi(e) >= 1 && atoi(e) <= 3 ? atoi(e) : 3;  // tuning / debugging knob
-  while (RS > 1 && gemm2_smem(N, g.K, RS) > 227 * 1024) --RS;
-  const size_t smem = gemm2_smem(N, g.K, RS);
+  while (RS > 1 && gemm2_smem(N, g.K, RS, raw_tiles, npro) > 227 * 1024) --RS;
+  const size_t smem = gemm2_smem(N, g.K, RS, raw_tiles, npro);
   if (smem > 227 * 1024) {
-    set_error("mlp_layer_fwd: shared memory %zu B exceeds 227 KB (N=%d K=%d)", smem, N, g.K);
+    set_error("mlp: shared memory %zu B exceeds 227 KB (N=%d K=%d)", smem, N, g.K);
     return S2C_ERR_UNSUPPORTED;
   }
   g.RS = RS;
-  auto kern = mlp_gemm2_kernel<N>;
+  auto kern = mlp_gemm2_kernel<N, PRO, EPI>;
   S2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "mlp_gemm2 smem attr");
   const long long tiles = (g.R + BM - 1) / BM;
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-  kern<<<grid, kThreads, smem, st>>>(g, tmap);
+  kern<<<grid, kThreads, smem, st>>>(g, tmap, tmap2);
   S2C_CHECK_LAUNCH("mlp_gemm2 launch");
   return S2C_OK;
 }
@@ -427,12 +527,57 @@ extern "C" int s2c_mlp_layer_fwd_v2(const float *A, long long lda, long long R, 
   S2C_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)C & 15) == 0 && ((uintptr_t)wprep & 15) == 0, "mlp_layer_fwd_v2: A, C and wprep must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const int KC = (K + BK - 1) / BK;
-  w_prep_kernel<<<ceil_div(KC * N * 8, 256), 256, 0, st>>>(W, N, K, (unsigned char *)wprep);
+  w_prep_kernel<<<ceil_div(KC * N * 8, 256), 256, 0, st>>>(W, N, K, K, 1, (unsigned char *)wprep);
   S2C_CHECK_LAUNCH("w_prep");
-  Gemm2Args g;
-  g.A = A; g.lda = lda; g.K = K; g.pro_scale = pro_scale; g.pro_shift = pro_shift; g.wprep = (const unsigned char *)wprep;
-  g.C = C; g.ldc = ldc; g.stat_sum = stat_sum; g.stat_sumsq = stat_sumsq; g.R = R; g.RS = 0;
-  if (N == 64) return launch_gemm2<64>(g, st);
-  if (N == 128) return launch_gemm2<128>(g, st);
-  return launch_gemm2<256>(g, st);
+  Gemm2Args g = {};
+  g.A = A; g.lda = lda; g.K = K; g.p0 = pro_scale; g.p1 = pro_shift; g.wprep = (const unsigned char *)wprep;
+  g.C = C; g.ldc = ldc; g.stat_sum = stat_sum; g.stat_sumsq = stat_sumsq; g.R = R;
+  if (N == 64) return launch_gemm2<64, PRO_BNRELU, EPI_STORE_STATS>(g, nullptr, 0, st);
+  if (N == 128) return launch_gemm2<128, PRO_BNRELU, EPI_STORE_STATS>(g, nullptr, 0, st);
+  return launch_gemm2<256, PRO_BNRELU, EPI_STORE_STATS>(g, nullptr, 0, st);
+}
+
+// Backward "data" kernel of one layer l of the shared MLP (tensor cores, same pipeline as the forward):
+//     dY_l   = a[k]*g_l + b[k]*Y_l + c[k]          BatchNorm backward of layer l, affine per channel (a,b,c from the caller)
+//     dX     = dY_l * W_l                           (R, N = C_{l-1})
+//     g_prev = dX where relu(bn_{l-1}(Y_prev)) was active, else 0     -> C
+//     stat_sum += sum_rows g_prev,  stat_sumsq += sum_rows g_prev * Y_prev     (float64, zeroed by the caller)
+//   g_l is either dense (G, ldg) or -- for the LAST layer -- rebuilt on the fly from the pooled gradient:
+//   dpool/argmax (R/ns, K) with last_scale/last_shift = the last layer's folded BatchNorm (ReLU mask of layer l).
+//   W is layer l's Conv2d weight (K = C_l rows, N = C_{l-1} columns, row-major).  N in {64,128,256}; K multiple of 4.
+//   dY_out (R, K), optional: dY_l written back for the weight-gradient GEMM  dW_l = dY_l^T * relu(bn(Y_prev)).
+extern "C" int s2c_mlp_layer_bwd_data(const float *G, long long ldg, const float *Y, long long ldy, long long R, int K,
+                                      const float *a, const float *b, const float *c, const float *dpool,
+                                      const int *argmax, int ns, const float *last_scale, const float *last_shift,
+                                      const float *W, int N, const float *Yprev, long long ldyp, const float *prev_scale,
+                                      const float *prev_shift, float *C, long long ldc, float *dY_out, double *stat_sum,
+                                      double *stat_sumsq, void *wprep, void *stream) {
+  using namespace s2c;
+  S2C_REQUIRE(R >= 0 && K >= 4 && (K & 3) == 0, "mlp_layer_bwd_data: K=%d must be a positive multiple of 4", K);
+  S2C_REQUIRE(N == 64 || N == 128 || N == 256, "mlp_layer_bwd_data: N=%d must be 64, 128 or 256", N);
+  S2C_REQUIRE((ldy & 3) == 0 && (ldyp & 3) == 0 && (ldc & 3) == 0 && ldy >= K && ldyp >= N && ldc >= N, "mlp_layer_bwd_data: bad leading dimensions");
+  if (R == 0) return S2C_OK;
+  const bool pool = dpool != nullptr;
+  S2C_REQUIRE(pool || (G && (ldg & 3) == 0 && ldg >= K), "mlp_layer_bwd_data: need either a dense gradient or dpool/argmax");
+  S2C_REQUIRE(!pool || (argmax && ns >= 1 && last_scale && last_shift && R % ns == 0), "mlp_layer_bwd_data: incomplete pooled-gradient arguments");
+  S2C_REQUIRE(Y && a && b && c && W && Yprev && prev_scale && prev_shift && C && wprep && stat_sum && stat_sumsq, "mlp_layer_bwd_data: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int KC = (K + BK - 1) / BK;
+  // B operand = W_l^T: B[n][k] = W[k][n]
+  w_prep_kernel<<<ceil_div(KC * N * 8, 256), 256, 0, st>>>(W, N, K, N, 0, (unsigned char *)wprep);
+  S2C_CHECK_LAUNCH("w_prep");
+  Gemm2Args g = {};
+  g.K = K; g.p0 = a; g.p1 = b; g.p2 = c; g.wprep = (const unsigned char *)wprep; g.C = C; g.ldc = ldc; g.dY_out = dY_out;
+  g.Yprev = Yprev; g.ldyp = ldyp; g.e_scale = prev_scale; g.e_shift = prev_shift;
+  g.stat_sum = stat_sum; g.stat_sumsq = stat_sumsq; g.R = R;
+  if (pool) {
+    g.A = nullptr; g.lda = 0; g.p3 = last_scale; g.p4 = last_shift; g.dpool = dpool; g.argmax = argmax; g.ns = ns;
+    if (N == 64) return launch_gemm2<64, PRO_POOL, EPI_MASK_STATS>(g, Y, ldy, st);
+    if (N == 128) return launch_gemm2<128, PRO_POOL, EPI_MASK_STATS>(g, Y, ldy, st);
+    return launch_gemm2<256, PRO_POOL, EPI_MASK_STATS>(g, Y, ldy, st);
+  }
+  g.A = G; g.lda = ldg;
+  if (N == 64) return launch_gemm2<64, PRO_AFFINE2, EPI_MASK_STATS>(g, Y, ldy, st);
+  if (N == 128) return launch_gemm2<128, PRO_AFFINE2, EPI_MASK_STATS>(g, Y, ldy, st);
+  return launch_gemm2<256, PRO_AFFINE2, EPI_MASK_STATS>(g, Y, ldy, st);
 }

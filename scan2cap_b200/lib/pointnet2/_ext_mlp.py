@@ -64,3 +64,29 @@ def pool_bwd_stats(dpool, argmax, Y, ns, scale, shift):
         call("s2c_pool_bwd_stats", dpool.data_ptr(), argmax.data_ptr(), Y.data_ptr(), Y.stride(0), G, ns, N,
              scale.data_ptr(), shift.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), _stream(Y))
     return stats[0], stats[1]
+
+
+def bwd_data_supported(K, N):
+    return KERNEL_VERSION == 2 and N in (64, 128, 256) and K % 4 == 0 and K >= 4
+
+
+def mlp_layer_bwd_data(Y, a, b, c, W, Yprev, prev_scale, prev_shift, G=None, dpool=None, argmax=None, ns=1,
+                       last_scale=None, last_shift=None, want_dY=True):
+    """One layer's fused backward-data pass (see include/s2c.h).  Y (R,K) pre-BN output of layer l; W (K,N) its
+    weight; Yprev (R,N) pre-BN output of layer l-1.  Gradient in: dense G (R,K) or (dpool, argmax) (R/ns, K).
+    Returns g_prev (R,N), dY (R,K) or None, sum_g (N) f64, sum_gy (N) f64."""
+    R, K = Y.shape
+    N = Yprev.shape[1]
+    W = W.contiguous()
+    assert W.shape == (K, N)
+    gprev = torch.empty((R, N), dtype=torch.float32, device=Y.device)
+    dY = torch.empty((R, K), dtype=torch.float32, device=Y.device) if want_dY else None
+    stats = torch.zeros((2, N), dtype=torch.float64, device=Y.device)
+    wprep = torch.empty(((K + 31) // 32) * N * 256, dtype=torch.uint8, device=Y.device)
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    with _guard(Y):
+        call("s2c_mlp_layer_bwd_data", ptr(G), G.stride(0) if G is not None else 0, Y.data_ptr(), Y.stride(0), R, K,
+             a.data_ptr(), b.data_ptr(), c.data_ptr(), ptr(dpool), ptr(argmax), int(ns), ptr(last_scale), ptr(last_shift),
+             W.data_ptr(), N, Yprev.data_ptr(), Yprev.stride(0), prev_scale.data_ptr(), prev_shift.data_ptr(),
+             gprev.data_ptr(), N, ptr(dY), stats[0].data_ptr(), stats[1].data_ptr(), wprep.data_ptr(), _stream(Y))
+    return gprev, dY, stats[0], stats[1]

@@ -74,20 +74,12 @@ class _FusedMLPPool(Function):
         R = rows.shape[0]
         grads = [None] * (3 * L)
         dpool = dpool.contiguous()
-        # gradient w.r.t. the rectified output of the last layer: the pooled gradient at the arg-max sample
-        C_last = Ys[-1].shape[1]
-        g = torch.zeros((G, ns, C_last), dtype=dpool.dtype, device=dpool.device)
-        g.scatter_(1, argmax.long().unsqueeze(1), dpool.unsqueeze(1))
-        g = g.view(R, C_last)
         grad_rows = None
-        for l in range(L - 1, -1, -1):
-            W = params[3 * l].reshape(params[3 * l].shape[0], -1)
+
+        def affine(l, sum_g, sum_gy):
+            """BatchNorm backward of layer l as dY = a*g + b*y + c; also its gamma / beta gradients."""
+            mean, invstd, _, _ = coefs[l]
             gamma = params[3 * l + 1]
-            mean, invstd, scale, shift = coefs[l]
-            Y = Ys[l]
-            g = g * (torch.addcmul(shift, Y, scale) > 0)          # ReLU mask of this layer
-            sum_g = g.sum(0, dtype=torch.float64)
-            sum_gy = (g * Y).sum(0, dtype=torch.float64)
             sum_gx = (sum_gy - mean * sum_g) * invstd             # sum of g * xhat
             grads[3 * l + 1] = sum_gx.to(gamma.dtype)
             grads[3 * l + 2] = sum_g.to(gamma.dtype)
@@ -95,21 +87,52 @@ class _FusedMLPPool(Function):
             if batch_stats[l]:
                 b = -a * invstd * (sum_gx / R)
                 c = -a * (sum_g / R) - b * mean
-                dY = torch.addcmul(c.float(), g, a.float()).addcmul_(Y, b.float())
             else:
-                dY = g * a.float()
-            if l > 0:
-                m_p, i_p, sc_p, sh_p = coefs[l - 1]
+                b = torch.zeros_like(a)
+                c = torch.zeros_like(a)
+            return a.float(), b.float(), c.float()
+
+        # last layer: its masked gradient is the pooled gradient at the arg-max sample -> sums straight from dpool
+        l = L - 1
+        _, _, sc_l, sh_l = coefs[l]
+        sum_g, sum_gy = _ext_mlp.pool_bwd_stats(dpool, argmax, Ys[l], ns, sc_l, sh_l)
+        g = None  # dense masked gradient of layer l (None while it is still "pooled")
+        while l >= 0:
+            W = params[3 * l].reshape(params[3 * l].shape[0], -1)
+            a, b, c = affine(l, sum_g, sum_gy)
+            Y = Ys[l]
+            fused = l > 0 and _ext_mlp.bwd_data_supported(Y.shape[1], Ys[l - 1].shape[1])
+            if fused:
+                _, _, sc_p, sh_p = coefs[l - 1]
+                if g is None:
+                    g_prev, dY, sum_g, sum_gy = _ext_mlp.mlp_layer_bwd_data(
+                        Y, a, b, c, W, Ys[l - 1], sc_p, sh_p, dpool=dpool, argmax=argmax, ns=ns, last_scale=coefs[l][2],
+                        last_shift=coefs[l][3])
+                else:
+                    g_prev, dY, sum_g, sum_gy = _ext_mlp.mlp_layer_bwd_data(Y, a, b, c, W, Ys[l - 1], sc_p, sh_p, G=g)
                 Xp = torch.relu_(torch.addcmul(sh_p, Ys[l - 1], sc_p))
                 grads[3 * l] = (dY.t() @ Xp).view_as(params[3 * l])
-                g = dY @ W
+                g = g_prev
             else:
-                X0 = rows[:, :K]
-                grads[0] = (dY.t() @ X0).view_as(params[0])
-                if ctx.needs_input_grad[0]:
-                    grad_rows = dY @ W
-                    if rows.shape[1] != K:
-                        grad_rows = torch.nn.functional.pad(grad_rows, (0, rows.shape[1] - K))
+                if g is None:  # materialise the pooled gradient (ReLU mask of the last layer applied)
+                    g = torch.zeros((G, ns, Y.shape[1]), dtype=dpool.dtype, device=dpool.device)
+                    g.scatter_(1, argmax.long().unsqueeze(1), dpool.unsqueeze(1))
+                    g = g.view(R, -1) * (torch.addcmul(coefs[l][3], Y, coefs[l][2]) > 0)
+                dY = torch.addcmul(c, g, a).addcmul_(Y, b)
+                if l > 0:
+                    _, _, sc_p, sh_p = coefs[l - 1]
+                    pre = torch.addcmul(sh_p, Ys[l - 1], sc_p)
+                    grads[3 * l] = (dY.t() @ torch.relu(pre)).view_as(params[3 * l])
+                    g = (dY @ W) * (pre > 0)
+                    sum_g = g.sum(0, dtype=torch.float64)
+                    sum_gy = (g * Ys[l - 1]).sum(0, dtype=torch.float64)
+                else:
+                    grads[0] = (dY.t() @ rows[:, :K]).view_as(params[0])
+                    if ctx.needs_input_grad[0]:
+                        grad_rows = dY @ W
+                        if rows.shape[1] != K:
+                            grad_rows = torch.nn.functional.pad(grad_rows, (0, rows.shape[1] - K))
+            l -= 1
         return (grad_rows, None, None, None, None, None) + tuple(grads)
 
 

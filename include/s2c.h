@@ -116,6 +116,8 @@ S2C_API int s2c_three_interpolate_grad(const float *grad_out, const int *idx, co
  *     grouped   out, 3+C channels, xyz channels first:
  *                 out_layout 0: (B,3+C,M,nsample)   the reference's layout
  *                 out_layout 1: (B,M,nsample,3+C)   channels-last (what the grouped-MLP kernels eat)
+ *                 out_layout 2: (B,M,nsample,Cp)    channels-last, Cp = 3+C rounded up to a multiple of 4, pad = 0
+ *                                                   (16-byte aligned rows for the TMA-fed MLP kernel)
  *   normalize_xyz != 0 multiplies the relative coordinates by the fp32 reciprocal of radius
  *   (what torch's CUDA div-by-python-scalar does).
  * ---------------------------------------------------------------------------------------- */

@@ -28,7 +28,7 @@ struct GroupArgs {
   float *grouped;         // may be null (query only)
   int C;
   long long feat_point_stride, feat_chan_stride, feat_scene_stride;
-  int out_layout;  // 0: (B,3+C,M,ns)  1: (B,M,ns,3+C)
+  int out_layout;  // 0: (B,3+C,M,ns)  1: (B,M,ns,3+C)  2: (B,M,ns,Cp), Cp = 3+C rounded up to 4, zero padded
   float inv_radius;  // 1 if !normalize_xyz
   int normalize;
 };
@@ -140,14 +140,17 @@ ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ x
             st_stream(o + (size_t)(3 + ch) * cstride + s, __ldg(fk + (size_t)ch * ga.feat_chan_stride));
         }
       } else {
-        // (B,M,ns,3+C): the centre's whole block is one contiguous run of ns*(3+C) floats
-        float *o = ga.grouped + ((size_t)b * M + j) * (size_t)nsample * CC;
-        const int total = nsample * CC;
+        // (B,M,ns,Cp): the centre's whole block is one contiguous run of ns*Cp floats (Cp = 3+C, or padded to 4)
+        const int CP = ga.out_layout == 2 ? ((CC + 3) & ~3) : CC;
+        float *o = ga.grouped + ((size_t)b * M + j) * (size_t)nsample * CP;
+        const int total = nsample * CP;
         for (int t = lane; t < total; t += 32) {
-          const int s = t / CC, ch = t - s * CC;
+          const int s = t / CP, ch = t - s * CP;
           const int k = li[s];
           float v;
-          if (ch < 3) {
+          if (ch >= CC) {
+            v = 0.f;
+          } else if (ch < 3) {
             v = __fsub_rn(xyz[(size_t)k * 3 + ch], ch == 0 ? ccx : (ch == 1 ? ccy : ccz));
             if (ga.normalize) v = __fmul_rn(v, ga.inv_radius);
           } else {
@@ -197,7 +200,7 @@ extern "C" int s2c_query_and_group(const float *xyz, const float *new_xyz, const
   S2C_REQUIRE(B >= 0 && n >= 1 && M >= 0 && C >= 0, "query_and_group: bad sizes B=%d n=%d M=%d C=%d", B, n, M, C);
   S2C_REQUIRE(nsample >= 1 && nsample <= 1024, "query_and_group: nsample=%d outside [1,1024]", nsample);
   S2C_REQUIRE(feat_layout == 0 || feat_layout == 1, "query_and_group: feat_layout must be 0 or 1");
-  S2C_REQUIRE(out_layout == 0 || out_layout == 1, "query_and_group: out_layout must be 0 or 1");
+  S2C_REQUIRE(out_layout >= 0 && out_layout <= 2, "query_and_group: out_layout must be 0, 1 or 2");
   if (B == 0 || M == 0) return S2C_OK;
   S2C_REQUIRE(xyz && new_xyz && grouped, "query_and_group: null pointer");
   S2C_REQUIRE(C == 0 || features, "query_and_group: features is null but C=%d", C);

@@ -158,12 +158,14 @@ def three_interpolate_grad(grad_out, idx, weight, m):
 
 
 def query_and_group(xyz, new_xyz, features, radius, nsample, normalize_xyz, feat_point_major=False,
-                    channels_last=False):
+                    channels_last=False, pad4=False):
     """Fused QueryAndGroup.forward (use_xyz=True).  Returns (grouped, idx).
 
     features: None, (B,C,n) [default] or, with feat_point_major, a (B,n,C) view whose last dim is
     contiguous (row stride may exceed C).  grouped: (B,3+C,M,ns) contiguous, or with channels_last the
-    same logical shape in torch.channels_last memory format (physically (B,M,ns,3+C)).
+    same logical shape in torch.channels_last memory format (physically (B,M,ns,3+C); with pad4 the rows are
+    padded with zeros to a multiple of 4 floats so that they are 16-byte aligned, and the returned tensor has
+    Cp = ceil4(3+C) channels, the last Cp-3-C of them zero).
     """
     _chk(xyz, "xyz", torch.float32)
     _chk(new_xyz, "new_xyz", torch.float32)
@@ -181,14 +183,16 @@ def query_and_group(xyz, new_xyz, features, radius, nsample, normalize_xyz, feat
             C = features.shape[1]
         fptr = features.data_ptr()
     idx = torch.empty((B, M, int(nsample)), dtype=torch.int32, device=xyz.device)
+    pad4 = bool(pad4 and channels_last)
     if channels_last:
-        grouped = torch.empty((B, M, int(nsample), 3 + C), dtype=torch.float32, device=xyz.device)
+        Cp = (3 + C + 3) // 4 * 4 if pad4 else 3 + C
+        grouped = torch.empty((B, M, int(nsample), Cp), dtype=torch.float32, device=xyz.device)
     else:
         grouped = torch.empty((B, 3 + C, M, int(nsample)), dtype=torch.float32, device=xyz.device)
     with _guard(xyz):
         call("s2c_query_and_group", xyz.data_ptr(), new_xyz.data_ptr(), fptr, B, n, M, C, flayout, fstride,
-             float(radius), int(nsample), 1 if normalize_xyz else 0, 1 if channels_last else 0, idx.data_ptr(),
-             grouped.data_ptr(), _stream(xyz))
+             float(radius), int(nsample), 1 if normalize_xyz else 0, (2 if pad4 else 1) if channels_last else 0,
+             idx.data_ptr(), grouped.data_ptr(), _stream(xyz))
     if channels_last:
-        grouped = grouped.permute(0, 3, 1, 2)
+        grouped = grouped.permute(0, 3, 1, 2)  # logical (B,Cp,M,ns) over channels-last storage (Cp > 3+C: zero pad)
     return grouped, idx

@@ -52,6 +52,11 @@ class _FusedMLPPool(Function):
         for l in range(L):
             W = params[3 * l].reshape(params[3 * l].shape[0], -1)
             need_stats = training or not bns[l].track_running_stats
+            if l == 0 and k % 4 != 0 and A.shape[1] >= (k + 3) // 4 * 4:
+                # the producer zero-padded the rows to a multiple of 4 columns: pad the weight to match (TMA path)
+                k4 = (k + 3) // 4 * 4
+                W = torch.nn.functional.pad(W, (0, k4 - k))
+                k = k4
             res = _ext_mlp.mlp_layer_fwd(A, W, scale, shift, want_stats=need_stats, K=k)
             Y, s1, s2 = res if need_stats else (res, None, None)
             mean, invstd, scale, shift = _bn_coefficients(s1, s2, R, bns[l], training)

@@ -106,13 +106,17 @@ class PointnetSAModuleVotes(nn.Module):
             assert inds.shape[1] == self.npoint
             new_xyz = torch.gather(xyz, 1, inds.long().unsqueeze(-1).expand(-1, -1, 3))
         feats_pm = point_major(features) if features is not None else None
+        use_fused = USE_FUSED_MLP and fused_mlp.fusable(layers)
         grouped, _ = pointnet2_utils.query_and_group(xyz, new_xyz, feats_pm, self.radius, self.nsample,
-                                                     self.normalize_xyz, True, True)
+                                                     self.normalize_xyz, True, True, use_fused)
         B, C, M, ns = grouped.shape
-        rows = grouped.permute(0, 2, 3, 1).reshape(B * M * ns, C)  # a view: the kernel wrote channels-last
-        if USE_FUSED_MLP and fused_mlp.fusable(layers):
-            pooled = fused_mlp.fused_mlp_maxpool(rows, C, B * M, ns, layers, self.training).view(B, M, -1)
+        if use_fused:
+            # rows of the zero-padded, 16-byte aligned channels-last buffer the kernel wrote: (R, Cp), Cin valid
+            Cin = 3 + (feats_pm.shape[2] if feats_pm is not None else 0)
+            rows = grouped.permute(0, 2, 3, 1).reshape(B * M * ns, C)
+            pooled = fused_mlp.fused_mlp_maxpool(rows, Cin, B * M, ns, layers, self.training).view(B, M, -1)
         else:
+            rows = grouped.permute(0, 2, 3, 1).reshape(B * M * ns, C)  # a view: the kernel wrote channels-last
             out = shared_mlp_rows(rows, layers, self.training)
             pooled = out.view(B, M, ns, -1).amax(dim=2)  # (B, M, C') point-major
         return new_xyz, pooled.transpose(1, 2), inds

@@ -111,14 +111,15 @@ class _FusedQueryAndGroup(Function):
     """grouped (B,3+C,M,ns) = cat([ (xyz[idx]-new_xyz) * (1/r if normalize), features[idx] ]) in one kernel."""
 
     @staticmethod
-    def forward(ctx, xyz, new_xyz, features, radius, nsample, normalize_xyz, feat_point_major, channels_last):
+    def forward(ctx, xyz, new_xyz, features, radius, nsample, normalize_xyz, feat_point_major, channels_last, pad4):
         grouped, idx = _ext.query_and_group(xyz, new_xyz, features, radius, nsample, normalize_xyz,
-                                            feat_point_major=feat_point_major, channels_last=channels_last)
+                                            feat_point_major=feat_point_major, channels_last=channels_last, pad4=pad4)
         ctx.idx = idx
         ctx.n = xyz.shape[1]
         ctx.scale = (1.0 / radius) if normalize_xyz else 1.0
         ctx.feat_point_major = feat_point_major
         ctx.has_feat = features is not None
+        ctx.C = 0 if features is None else (features.shape[2] if feat_point_major else features.shape[1])
         ctx.mark_non_differentiable(idx)
         return grouped, idx
 
@@ -133,16 +134,16 @@ class _FusedQueryAndGroup(Function):
             if ctx.needs_input_grad[1]:
                 g_new = -gx.sum(-1).transpose(1, 2)
         if ctx.has_feat and ctx.needs_input_grad[2]:
-            g_feat = _ext.group_points_grad(grad[:, 3:].contiguous(), idx, n)  # (B,C,n)
+            g_feat = _ext.group_points_grad(grad[:, 3:3 + ctx.C].contiguous(), idx, n)  # (B,C,n)
             if ctx.feat_point_major:
                 g_feat = g_feat.transpose(1, 2)
-        return g_xyz, g_new, g_feat, None, None, None, None, None
+        return g_xyz, g_new, g_feat, None, None, None, None, None, None
 
 
 def query_and_group(xyz, new_xyz, features, radius, nsample, normalize_xyz=False, feat_point_major=False,
-                    channels_last=False):
+                    channels_last=False, pad4=False):
     return _FusedQueryAndGroup.apply(xyz, new_xyz, features, radius, nsample, normalize_xyz, feat_point_major,
-                                     channels_last)
+                                     channels_last, pad4)
 
 
 class QueryAndGroup(nn.Module):

@@ -232,7 +232,7 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
     long long ia = 0, iw = 0;          // next raw chunk / next weight chunk to issue
     long long ta = blockIdx.x; int ka = 0;  // (tile, kc) of chunk ia
     int kw = 0;
-    while (iw < total_chunks) {
+    while (ia < total_chunks || iw < total_chunks) {
       if (ia < total_chunks) {
         const int rs = (int)(ia % RS);
         // lane 0 polls and broadcasts: the decision (and the counters below) must be warp-uniform
@@ -252,7 +252,7 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
           if (++ka == KC) { ka = 0; ta += gridDim.x; }
         }
       }
-      {
+      if (iw < total_chunks) {
         const int os = (int)(iw % OS);
         if (iw < OS || __shfl_sync(0xffffffffu, lane == 0 ? (int)mbar_test(&op_empty[os], (uint32_t)(((iw / OS) - 1) & 1)) : 0, 0)) {
           if (lane == 0) {

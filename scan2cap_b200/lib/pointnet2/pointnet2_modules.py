@@ -24,8 +24,8 @@ from . import fused_mlp
 from . import pointnet2_utils
 from . import pytorch_utils as pt_utils
 
-# S2C_FUSED_MLP=0 falls back to library GEMM + BatchNorm + ReLU kernels (A/B comparison, debugging)
-USE_FUSED_MLP = os.environ.get("S2C_FUSED_MLP", "0") != "0"
+# S2C_FUSED_MLP=0 selects library GEMM + BatchNorm + ReLU kernels instead of the tcgen05 path (A/B comparison)
+USE_FUSED_MLP = os.environ.get("S2C_FUSED_MLP", "1") != "0"
 
 
 def point_major(features):

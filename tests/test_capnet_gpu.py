@@ -18,10 +18,13 @@ from scan2cap_b200.data.scannet.model_util_scannet import ScannetDatasetConfig
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 RTOL = 1e-3
-# gradients: ReLU / max-pool are discontinuous, so the ~1e-6 forward differences between two fp32 evaluation
-# orders flip a handful of arg-max / sign decisions among ~10^6 of them, each moving a gradient entry by O(1e-3)
-# of the tensor's scale (the same happens between fp32 and fp64 runs of ONE implementation: tools/diag_mlp.py)
-GRAD_RTOL = 1e-2
+# Gradients.  ReLU / max-pool / arg-max are discontinuous: the ~1e-6 forward differences between two fp32
+# evaluation orders flip a handful of decisions among ~10^6, and k flips among n routed entries change a
+# gradient tensor by about sqrt(k/n) in relative L2 (the same happens between an fp32 and an fp64 run of ONE
+# implementation, tools/diag_mlp.py / tools/diag_fused.py; with no flip every kernel is at 1e-6 of float64).
+# The whole-network check is therefore a coarse one (gross errors: missing terms, wrong routing); the tight
+# gradient checks are the per-kernel ones against float64 in tests/test_mlp_gpu.py and tests/test_native_ops_gpu.py.
+GRAD_L2_TOL = 5e-2
 
 INT_KEYS = ["sa1_inds", "sa2_inds", "fp2_inds", "aggregated_vote_inds", "bbox_mask", "bbox_sems", "num_edge_source",
             "num_edge_target", "good_bbox_masks", "object_assignment", "objectness_label"]
@@ -83,23 +86,30 @@ def _check_outputs(o, r, int_keys, exact_keys, float_keys):
 
 
 def _check_grads(ours, ref, prefixes=None):
+    """Per-parameter relative L2 deviation (floored at 1e-3 of the largest gradient entry of the model) below
+    GRAD_L2_TOL, and cosine similarity of the whole flattened gradient above 0.999."""
     go = {n: p.grad for n, p in ours.named_parameters() if p.grad is not None}
     gr = {n: p.grad for n, p in ref.named_parameters() if p.grad is not None}
     if prefixes is None:
         assert set(go) == set(gr)
     gmax = max(float(g.abs().max()) for g in gr.values())
     badg, worst = {}, 0.0
+    fo, fr = [], []
     for n in gr:
         if prefixes is not None and not n.startswith(prefixes):
             continue
         assert n in go, "no gradient for %s" % n
-        scale = max(float(gr[n].abs().max()), 1e-3 * gmax)
-        e = float((go[n] - gr[n]).abs().max()) / scale
+        floor = 1e-3 * gmax * gr[n].numel() ** 0.5
+        e = float((go[n].double() - gr[n].double()).norm()) / max(float(gr[n].double().norm()), floor)
         worst = max(worst, e)
-        if not e < GRAD_RTOL:
+        if not e < GRAD_L2_TOL:
             badg[n] = e
-    print("worst gradient deviation: %.2e" % worst)
-    assert not badg, "gradients beyond %g: %s" % (GRAD_RTOL, badg)
+        fo.append(go[n].double().flatten()); fr.append(gr[n].double().flatten())
+    fo, fr = torch.cat(fo), torch.cat(fr)
+    cos = float(torch.dot(fo, fr) / (fo.norm() * fr.norm()))
+    print("worst per-parameter gradient L2 deviation: %.2e, cosine of the full gradient: %.6f" % (worst, cos))
+    assert not badg, "gradients beyond %g: %s" % (GRAD_L2_TOL, badg)
+    assert cos > 0.999
 
 
 @pytest.mark.parametrize("query_mode,B,N", [("center", 2, 8000), ("corner", 1, 20000)])

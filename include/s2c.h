@@ -202,6 +202,19 @@ S2C_API int s2c_mlp_layer_bwd_data(const float *G, long long ldg, const float *Y
                                    const float *prev_scale, const float *prev_shift, float *C, long long ldc,
                                    float *dY_out, double *stat_sum, double *stat_sumsq, void *wprep, void *stream);
 
+/* mlp_layer_bwd_weight -- weight gradient of one shared-MLP layer on the tensor cores (MN-major tcgen05 operands,
+ *   3xTF32, per-CTA accumulation in TMEM, fp32 atomics into dW):
+ *       dW[C x P] += sum_r dY[r,:]^T * X'[r,:]
+ *   dY (R, lddy): dense, or -- when a/b/c [C] are given -- formed on the fly as a*dY_in + b*Y + c (BatchNorm
+ *   backward of this layer from its masked upstream gradient and its pre-BN output Y);
+ *   X (R, ldx): previous layer's pre-BN output with xs/xh [P] (X' = relu(X*xs+xh)), or the raw layer input (xs = NULL).
+ *   C <= 256, P <= 288, ceil(C/128)*ceil(P/32) <= 16; leading dimensions multiples of 4.  The caller zero-fills dW.
+ *   Replaces the cuDNN/cuBLAS weight-gradient GEMM of Conv2d in SharedMLP (pytorch_utils.py:88-95). */
+S2C_API int s2c_mlp_layer_bwd_weight(const float *dY, long long lddy, const float *Y, long long ldy, const float *a,
+                                     const float *b, const float *c, const float *X, long long ldx, const float *xs,
+                                     const float *xh, long long R, int C, int P, float *dW, long long lddw,
+                                     void *stream);
+
 #ifdef __cplusplus
 }
 #endif

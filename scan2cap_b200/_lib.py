@@ -29,6 +29,7 @@ SIGNATURES = {
     "s2c_mlp_layer_fwd_v2": [P, c_ll, c_ll, c_int, P, P, P, c_int, P, c_ll, P, P, P, P],
     "s2c_mlp_layer_bwd_data": [P, c_ll, P, c_ll, c_ll, c_int, P, P, P, P, P, c_int, P, P, P, c_int, P, c_ll, P, P, P, c_ll,
                                P, P, P, P, P],
+    "s2c_mlp_layer_bwd_weight": [P, c_ll, P, c_ll, P, P, P, P, c_ll, P, P, c_ll, c_int, c_int, P, c_ll, P],
     "s2c_pool_fwd": [P, c_ll, c_ll, c_int, c_int, P, P, P, P, P],
     "s2c_pool_bwd_stats": [P, P, P, c_ll, c_ll, c_int, c_int, P, P, P, P, P],
     "s2c_knn_adjacency": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.c_double, P, P, P],

@@ -90,3 +90,21 @@ def mlp_layer_bwd_data(Y, a, b, c, W, Yprev, prev_scale, prev_shift, G=None, dpo
              W.data_ptr(), N, Yprev.data_ptr(), Yprev.stride(0), prev_scale.data_ptr(), prev_shift.data_ptr(),
              gprev.data_ptr(), N, ptr(dY), stats[0].data_ptr(), stats[1].data_ptr(), wprep.data_ptr(), _stream(Y))
     return gprev, dY, stats[0], stats[1]
+
+
+def bwd_weight_supported(C, P, *lds):
+    MH, NB = (C + 127) // 128, (P + 31) // 32
+    return KERNEL_VERSION == 2 and C <= 256 and NB <= 9 and MH * NB <= 16 and all(ld % 4 == 0 for ld in lds)
+
+
+def mlp_layer_bwd_weight(dY, X, P, xs=None, xh=None, a=None, b=None, c=None, Y=None):
+    """dW (C, P) = sum_r dY[r]^T X'[r]; dY (R, C) dense or (with a, b, c, Y) formed as a*dY + b*Y + c; X (R, >=P)
+    with optional relu(X*xs+xh) prologue."""
+    R, C = dY.shape
+    dW = torch.zeros((C, P), dtype=torch.float32, device=dY.device)
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    with _guard(dY):
+        call("s2c_mlp_layer_bwd_weight", dY.data_ptr(), dY.stride(0), ptr(Y), Y.stride(0) if Y is not None else 0,
+             ptr(a), ptr(b), ptr(c), X.data_ptr(), X.stride(0), ptr(xs), ptr(xh), R, C, int(P), dW.data_ptr(), P,
+             _stream(dY))
+    return dW

@@ -115,14 +115,22 @@ class _FusedMLPPool(Function):
                         last_shift=coefs[l][3])
                 else:
                     g_prev, dY, sum_g, sum_gy = _ext_mlp.mlp_layer_bwd_data(Y, a, b, c, W, Ys[l - 1], sc_p, sh_p, G=g)
-                Xp = torch.relu_(torch.addcmul(sh_p, Ys[l - 1], sc_p))
-                grads[3 * l] = (dY.t() @ Xp).view_as(params[3 * l])
+                if _ext_mlp.bwd_weight_supported(Y.shape[1], Ys[l - 1].shape[1], dY.stride(0), Ys[l - 1].stride(0)):
+                    grads[3 * l] = _ext_mlp.mlp_layer_bwd_weight(dY, Ys[l - 1], Ys[l - 1].shape[1], sc_p, sh_p).view_as(params[3 * l])
+                else:
+                    Xp = torch.relu_(torch.addcmul(sh_p, Ys[l - 1], sc_p))
+                    grads[3 * l] = (dY.t() @ Xp).view_as(params[3 * l])
                 g = g_prev
             else:
                 if g is None:  # materialise the pooled gradient (ReLU mask of the last layer applied)
                     g = torch.zeros((G, ns, Y.shape[1]), dtype=dpool.dtype, device=dpool.device)
                     g.scatter_(1, argmax.long().unsqueeze(1), dpool.unsqueeze(1))
                     g = g.view(R, -1) * (torch.addcmul(coefs[l][3], Y, coefs[l][2]) > 0)
+                if (l == 0 and not ctx.needs_input_grad[0] and
+                        _ext_mlp.bwd_weight_supported(Y.shape[1], K, g.stride(0), Y.stride(0), rows.stride(0))):
+                    # first layer, no gradient w.r.t. the input (SA1): dY is formed inside the weight-gradient kernel
+                    grads[0] = _ext_mlp.mlp_layer_bwd_weight(g, rows, K, a=a, b=b, c=c, Y=Y).view_as(params[0])
+                    break
                 dY = torch.addcmul(c, g, a).addcmul_(Y, b)
                 if l > 0:
                     _, _, sc_p, sh_p = coefs[l - 1]
@@ -132,7 +140,10 @@ class _FusedMLPPool(Function):
                     sum_g = g.sum(0, dtype=torch.float64)
                     sum_gy = (g * Ys[l - 1]).sum(0, dtype=torch.float64)
                 else:
-                    grads[0] = (dY.t() @ rows[:, :K]).view_as(params[0])
+                    if _ext_mlp.bwd_weight_supported(Y.shape[1], K, dY.stride(0), rows.stride(0)):
+                        grads[0] = _ext_mlp.mlp_layer_bwd_weight(dY, rows, K).view_as(params[0])
+                    else:
+                        grads[0] = (dY.t() @ rows[:, :K]).view_as(params[0])
                     if ctx.needs_input_grad[0]:
                         grad_rows = dY @ W
                         if rows.shape[1] != K:

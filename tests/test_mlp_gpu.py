@@ -78,3 +78,32 @@ def test_fused_mlp_maxpool_matches_torch_path(B, M, ns, C, widths, training):
         assert l2(pa.grad, pb.grad) < 5e-3, n
     for (n, ba), (_, bb) in zip(mlp_a.named_buffers(), mlp_b.named_buffers()):
         assert rel(ba.float(), bb.float()) < 1e-4, n
+
+
+@pytest.mark.parametrize("R,C,P,ldx,affine,xpro", [
+    (4096, 64, 64, 64, False, True), (100000, 128, 64, 64, False, True), (5000, 256, 128, 128, True, True),
+    (3333, 128, 259, 260, False, False), (70000, 64, 7, 8, True, False), (2048, 128, 131, 132, True, False),
+])
+def test_mlp_layer_bwd_weight_matches_float64(R, C, P, ldx, affine, xpro):
+    from scan2cap_b200.lib.pointnet2 import _ext_mlp
+    torch.manual_seed(R + C + P)
+    g = torch.randn(R, C, device=DEV)
+    Xbuf = torch.randn(R, ldx, device=DEV)
+    X = Xbuf[:, :P]
+    d64 = g.double()
+    kw = {}
+    if affine:
+        Y = torch.randn(R, C, device=DEV)
+        a, b, c = (torch.randn(C, device=DEV) for _ in range(3))
+        d64 = a.double() * g.double() + b.double() * Y.double() + c.double()
+        kw.update(a=a, b=b, c=c, Y=Y)
+    x64 = X.double()
+    if xpro:
+        xs, xh = torch.rand(P, device=DEV) + 0.5, torch.randn(P, device=DEV) * 0.3
+        x64 = torch.relu(x64 * xs.double() + xh.double())
+        kw.update(xs=xs, xh=xh)
+    want = d64.t() @ x64
+    got = _ext_mlp.mlp_layer_bwd_weight(g, Xbuf, P, **kw)
+    torch.cuda.synchronize()
+    err = float((got.double() - want).abs().max() / want.abs().max())
+    assert err < 2e-5, "wgrad error %g" % err

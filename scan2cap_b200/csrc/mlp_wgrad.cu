@@ -4,12 +4,12 @@
 //
 // This is a GEMM whose reduction dimension is the ROW index (R ~ 10^5..10^6) and whose output is tiny, the shape the
 // library handles worst (the reference's cuDNN wgrad / cuBLAS "nt" split-K kernels take ~6 ms per step here).
-// Both operands are "MN-major" for the tensor core: a [32 rows x 32 channels] block of the row-major activation
-// matrix, staged with the SAME 128-byte swizzle as the forward kernel, is exactly one MN-major SWIZZLE_128B atom
-// column (8 K-rows of 128 bytes per atom) -- so no transposition is needed anywhere; the UMMA descriptors just say
-// a_major = b_major = MN.  dY is optionally formed on the fly (BatchNorm-backward affine a*g + b*y + c), X' by the
-// BatchNorm + ReLU prologue; fp32 operands are split hi/lo (3xTF32).  Each persistent CTA accumulates its share of
-// the rows in TMEM and adds its [C_l x C_prev] partial to the result with fp32 atomics at the end.
+// Per 32-row chunk both operands are staged TRANSPOSED into the K-major SWIZZLE_128B layout of the forward kernel
+// (operand row = channel, operand K = the 32 data rows = one 128-byte swizzle row): loads stay coalesced along the
+// channels, and the transposing 4-byte shared-memory stores are made bank-conflict-free by rotating which of its
+// four channels a thread stores at each step.  dY is optionally formed on the fly (BatchNorm-backward affine
+// a*g + b*y + c), X' by the BatchNorm + ReLU prologue; fp32 operands are split hi/lo (3xTF32).  Each persistent CTA
+// accumulates its share of the rows in TMEM and adds its [C_l x C_prev] partial to the result with fp32 atomics.
 #include "s2c_common.cuh"
 
 namespace s2c {
@@ -82,27 +82,34 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// MN-major SWIZZLE_128B descriptor: atoms of 8 K-rows x 128 B (32 MN elements); LBO = byte stride between atoms
-// along MN (the next 32 channels), SBO = byte stride between atoms along K (unused: one MMA spans K = 8 = one atom)
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | (64ull << 32) | (1ull << 46) |
-         (2ull << 61);
+// K-major SWIZZLE_128B descriptor / tf32 instruction descriptor (same as the forward kernel, mlp.cu)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-__device__ __forceinline__ uint32_t make_idesc_mn(int M, int N) {  // tf32 x tf32 -> f32, A and B MN-major
-  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ uint32_t swz(int r, int seg) {
-  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((seg ^ (r & 7)) << 4));
+// byte offset of element (operand row m, k) in a [rows x 32 fp32] K-major SWIZZLE_128B block
+__device__ __forceinline__ uint32_t swz_elem(int m, int k) {
+  return (uint32_t)((m >> 3) * 1024 + (m & 7) * 128 + ((((k >> 2) ^ (m & 7)) & 7) << 4) + (k & 3) * 4);
+}
+// transposing store of a thread's 4 consecutive channels (m0..m0+3) of data row k, hi/lo split.  At step e the thread
+// stores channel (e + seg/2) mod 4, which spreads a warp's 32 stores over all 32 banks.
+__device__ __forceinline__ void store_split_t(unsigned char *hi_base, unsigned char *lo_base, int m0, int k, int seg, float4 v) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int ee = (e + (seg >> 1)) & 3;
+    const float val = ee == 0 ? v.x : (ee == 1 ? v.y : (ee == 2 ? v.z : v.w));
+    float h, l;
+    split_tf32(val, h, l);
+    const uint32_t off = swz_elem(m0 + ee, k);
+    *reinterpret_cast<float *>(hi_base + off) = h;
+    *reinterpret_cast<float *>(lo_base + off) = l;
+  }
 }
 __device__ __forceinline__ void split_tf32(float v, float &hi, float &lo) {
   hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
   lo = v - hi;
-}
-__device__ __forceinline__ void store_split(unsigned char *hi_base, unsigned char *lo_base, uint32_t off, float4 v) {
-  float4 h, l;
-  split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-  *reinterpret_cast<float4 *>(hi_base + off) = h;
-  *reinterpret_cast<float4 *>(lo_base + off) = l;
 }
 __device__ __forceinline__ float4 ld4_guard(const float *base, long long ld, long long row, long long R, int col, int ncols) {
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -119,7 +126,7 @@ __device__ __forceinline__ float4 ld4_guard(const float *base, long long ld, lon
   return v;
 }
 
-constexpr uint32_t BLK = CK * 32 * 4;  // one [32 rows x 32 channels] fp32 block = 4 KB
+constexpr uint32_t BLK = 32 * CK * 4;  // 32 operand rows (channels) x 32 k (data rows) fp32 = 4 KB
 
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_wgrad_kernel(WgradArgs g) {
@@ -152,7 +159,7 @@ mlp_wgrad_kernel(WgradArgs g) {
   const long long my_chunks = (num_chunks > (long long)blockIdx.x) ? (num_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (warp < kLoadWarps) {
-    // ===================== load + transform: global -> prologue -> hi/lo split -> swizzled MN-major blocks
+    // ===================== load + transform: global -> prologue -> hi/lo split -> transposed K-major operand blocks
     const int r = tid >> 3, seg = tid & 7;  // 256 threads = 32 rows x 8 sixteen-byte segments
     const int CB = (g.C + 31) / 32;         // real channel blocks of A
     const bool affine = g.a != nullptr;
@@ -181,7 +188,7 @@ mlp_wgrad_kernel(WgradArgs g) {
       for (int mb = 0; mb < 8; ++mb) {
         if (mb < CB) {
           float4 v = va[mb];
-          const int ch = mb * 32 + seg * 4;
+          const int ch = mb * 32 + seg * 4;  // operand row of v.x (rows >= C stay zero from the one-time clear)
           if (affine) {
             const float4 y = vy[mb];
             float ca[4], cb[4], cc[4];
@@ -194,7 +201,7 @@ mlp_wgrad_kernel(WgradArgs g) {
             v.z = fmaf(ca[2], v.z, fmaf(cb[2], y.z, cc[2])); v.w = fmaf(ca[3], v.w, fmaf(cb[3], y.w, cc[3]));
             if (row >= g.R) v = make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          store_split(a_hi + mb * BLK, a_lo + mb * BLK, swz(r, seg), v);
+          store_split_t(a_hi, a_lo, ch, r, seg, v);
         }
       }
 #pragma unroll
@@ -213,16 +220,16 @@ mlp_wgrad_kernel(WgradArgs g) {
             v.z = fmaxf(fmaf(v.z, xs[2], xh[2]), 0.f); v.w = fmaxf(fmaf(v.w, xs[3], xh[3]), 0.f);
             if (row >= g.R) v = make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          store_split(b_hi + nb * BLK, b_lo + nb * BLK, swz(r, seg), v);
+          store_split_t(b_hi, b_lo, ch, r, seg, v);
         }
       }
       fence_async_proxy();
       mbar_arrive(&bars[s]);
     }
   } else {
-    // ===================== MMA issuer: D[128 x N] (per M half) += A^T-view[128 x 8] * B^T-view[8 x N], K = 8 rows per MMA
+    // ===================== MMA issuer: D[128 x N] (per M half) += A[128 ch x 8 rows] * B[N ch x 8 rows]^T
     const int n0 = (NB > 8 ? 8 : NB) * 32, n1 = (NB > 8 ? NB - 8 : 0) * 32;
-    const uint32_t idesc0 = make_idesc_mn(128, n0), idesc1 = n1 ? make_idesc_mn(128, n1) : 0u;
+    const uint32_t idesc0 = make_idesc(128, n0), idesc1 = n1 ? make_idesc(128, n1) : 0u;
     for (long long i = 0; i < my_chunks; ++i) {
       const int s = (int)(i % OS);
       mbar_wait(&bars[s], (uint32_t)((i / OS) & 1));
@@ -232,17 +239,17 @@ mlp_wgrad_kernel(WgradArgs g) {
         for (int mh = 0; mh < g.MH; ++mh) {
           const uint32_t d0 = tmem_base + (uint32_t)(mh * NB * 32);
 #pragma unroll
-          for (int ks = 0; ks < CK / 8; ++ks) {
+          for (int ks = 0; ks < CK / 8; ++ks) {  // UMMA K = 8 data rows = 32 bytes inside the 128-byte swizzle row
             const uint32_t acc = (i | ks) ? 1u : 0u;
-            const uint32_t ao = (uint32_t)(mh * 4) * BLK + ks * 1024, bo = ks * 1024;
-            umma_tf32(d0, make_desc_mn(ah + ao, BLK), make_desc_mn(bh + bo, BLK), idesc0, acc);
-            umma_tf32(d0, make_desc_mn(ah + ao, BLK), make_desc_mn(bl + bo, BLK), idesc0, 1u);
-            umma_tf32(d0, make_desc_mn(al + ao, BLK), make_desc_mn(bh + bo, BLK), idesc0, 1u);
+            const uint32_t ao = (uint32_t)mh * 128 * 128 + ks * 32, bo = ks * 32;
+            umma_tf32(d0, make_desc(ah + ao), make_desc(bh + bo), idesc0, acc);
+            umma_tf32(d0, make_desc(ah + ao), make_desc(bl + bo), idesc0, 1u);
+            umma_tf32(d0, make_desc(al + ao), make_desc(bh + bo), idesc0, 1u);
             if (n1) {
-              const uint32_t bo1 = 8 * BLK + ks * 1024;
-              umma_tf32(d0 + n0, make_desc_mn(ah + ao, BLK), make_desc_mn(bh + bo1, BLK), idesc1, acc);
-              umma_tf32(d0 + n0, make_desc_mn(ah + ao, BLK), make_desc_mn(bl + bo1, BLK), idesc1, 1u);
-              umma_tf32(d0 + n0, make_desc_mn(al + ao, BLK), make_desc_mn(bh + bo1, BLK), idesc1, 1u);
+              const uint32_t bo1 = 256 * 128 + ks * 32;  // operand rows 256.. of B
+              umma_tf32(d0 + n0, make_desc(ah + ao), make_desc(bh + bo1), idesc1, acc);
+              umma_tf32(d0 + n0, make_desc(ah + ao), make_desc(bl + bo1), idesc1, 1u);
+              umma_tf32(d0 + n0, make_desc(al + ao), make_desc(bh + bo1), idesc1, 1u);
             }
           }
         }

@@ -94,7 +94,8 @@ def mlp_layer_bwd_data(Y, a, b, c, W, Yprev, prev_scale, prev_shift, G=None, dpo
 
 def bwd_weight_supported(C, P, *lds):
     MH, NB = (C + 127) // 128, (P + 31) // 32
-    return KERNEL_VERSION == 2 and C <= 256 and NB <= 9 and MH * NB <= 16 and all(ld % 4 == 0 for ld in lds)
+    return (KERNEL_VERSION == 2 and C <= 256 and NB <= 9 and MH * NB <= 16 and 4 * MH + NB <= 13
+            and all(ld % 4 == 0 for ld in lds))
 
 
 def mlp_layer_bwd_weight(dY, X, P, xs=None, xh=None, a=None, b=None, c=None, Y=None):

@@ -89,6 +89,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+__device__ __forceinline__ void split_tf32(float v, float &hi, float &lo) {
+  hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  lo = v - hi;
+}
 // byte offset of element (operand row m, k) in a [rows x 32 fp32] K-major SWIZZLE_128B block
 __device__ __forceinline__ uint32_t swz_elem(int m, int k) {
   return (uint32_t)((m >> 3) * 1024 + (m & 7) * 128 + ((((k >> 2) ^ (m & 7)) & 7) << 4) + (k & 3) * 4);
@@ -106,10 +110,6 @@ __device__ __forceinline__ void store_split_t(unsigned char *hi_base, unsigned c
     *reinterpret_cast<float *>(hi_base + off) = h;
     *reinterpret_cast<float *>(lo_base + off) = l;
   }
-}
-__device__ __forceinline__ void split_tf32(float v, float &hi, float &lo) {
-  hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-  lo = v - hi;
 }
 __device__ __forceinline__ float4 ld4_guard(const float *base, long long ld, long long row, long long R, int col, int ncols) {
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -128,7 +128,10 @@ __device__ __forceinline__ float4 ld4_guard(const float *base, long long ld, lon
 
 constexpr uint32_t BLK = 32 * CK * 4;  // 32 operand rows (channels) x 32 k (data rows) fp32 = 4 KB
 
-__global__ void __launch_bounds__(kThreads, 1)
+// CBT / NBT: compile-time bounds on the 32-channel blocks of dY / X a thread handles (register arrays);
+// PF: register prefetch of the next chunk (small shapes only) and two CTAs per SM
+template <int CBT, int NBT, bool PF>
+__global__ void __launch_bounds__(kThreads, PF ? 2 : 1)
 mlp_wgrad_kernel(WgradArgs g) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int MB = 4 * g.MH;   // A blocks per chunk (M padded to 128 per half)
@@ -164,28 +167,41 @@ mlp_wgrad_kernel(WgradArgs g) {
     const int CB = (g.C + 31) / 32;         // real channel blocks of A
     const bool affine = g.a != nullptr;
     const bool xpro = g.xs != nullptr;
+    float4 va[CBT], vy[CBT], vb[NBT];       // the chunk being staged
+    float4 na[CBT], ny[CBT], nbv[NBT];      // PF: the next chunk, in flight while this one is staged
+    auto issue_loads = [&](long long i, float4 *pa, float4 *py, float4 *pb) {
+      const long long row = ((long long)blockIdx.x + i * gridDim.x) * CK + r;
+#pragma unroll
+      for (int mb = 0; mb < CBT; ++mb) {
+        pa[mb] = make_float4(0.f, 0.f, 0.f, 0.f); py[mb] = pa[mb];
+        if (mb < CB) {
+          pa[mb] = ld4_guard(g.dY, g.lddy, row, g.R, mb * 32 + seg * 4, g.C);
+          if (affine) py[mb] = ld4_guard(g.Y, g.ldy, row, g.R, mb * 32 + seg * 4, g.C);
+        }
+      }
+#pragma unroll
+      for (int nb = 0; nb < NBT; ++nb) {
+        pb[nb] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nb < NB) pb[nb] = ld4_guard(g.X, g.ldx, row, g.R, nb * 32 + seg * 4, g.P);
+      }
+    };
+    if (PF && my_chunks > 0) issue_loads(0, na, ny, nbv);
     for (long long i = 0; i < my_chunks; ++i) {
       const int s = (int)(i % OS);
       const long long row = ((long long)blockIdx.x + i * gridDim.x) * CK + r;
       unsigned char *a_hi = smem + (size_t)s * stage_bytes, *a_lo = a_hi + a_bytes, *b_hi = a_lo + a_bytes, *b_lo = b_hi + b_bytes;
-      // issue all the loads of the chunk first (memory-level parallelism), then wait for the stage
-      float4 va[8], vy[8], vb[9];
+      if (PF) {
 #pragma unroll
-      for (int mb = 0; mb < 8; ++mb) {
-        va[mb] = make_float4(0.f, 0.f, 0.f, 0.f); vy[mb] = va[mb];
-        if (mb < CB) {
-          va[mb] = ld4_guard(g.dY, g.lddy, row, g.R, mb * 32 + seg * 4, g.C);
-          if (affine) vy[mb] = ld4_guard(g.Y, g.ldy, row, g.R, mb * 32 + seg * 4, g.C);
-        }
-      }
+        for (int mb = 0; mb < CBT; ++mb) { va[mb] = na[mb]; vy[mb] = ny[mb]; }
 #pragma unroll
-      for (int nb = 0; nb < 9; ++nb) {
-        vb[nb] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (nb < NB) vb[nb] = ld4_guard(g.X, g.ldx, row, g.R, nb * 32 + seg * 4, g.P);
+        for (int nb = 0; nb < NBT; ++nb) vb[nb] = nbv[nb];
+        if (i + 1 < my_chunks) issue_loads(i + 1, na, ny, nbv);  // stays in flight during the stores below
+      } else {
+        issue_loads(i, va, vy, vb);  // all loads of the chunk first (memory-level parallelism), then the stage wait
       }
       if (i >= OS) mbar_wait(&bars[2 + s], (uint32_t)(((i / OS) - 1) & 1));
 #pragma unroll
-      for (int mb = 0; mb < 8; ++mb) {
+      for (int mb = 0; mb < CBT; ++mb) {
         if (mb < CB) {
           float4 v = va[mb];
           const int ch = mb * 32 + seg * 4;  // operand row of v.x (rows >= C stay zero from the one-time clear)
@@ -205,7 +221,7 @@ mlp_wgrad_kernel(WgradArgs g) {
         }
       }
 #pragma unroll
-      for (int nb = 0; nb < 9; ++nb) {
+      for (int nb = 0; nb < NBT; ++nb) {
         if (nb < NB) {
           float4 v = vb[nb];
           const int ch = nb * 32 + seg * 4;
@@ -307,10 +323,23 @@ extern "C" int s2c_mlp_layer_bwd_weight(const float *dY, long long lddy, const f
   g.dW = dW; g.lddw = lddw; g.R = R; g.C = C; g.P = P; g.MH = MH; g.NB = NB;
   const size_t smem = (size_t)OS * 2 * (4 * MH + NB) * BLK + 8 * 8 + 16;
   S2C_REQUIRE(smem <= 227 * 1024, "mlp_layer_bwd_weight: shared memory %zu B exceeds 227 KB", smem);
-  S2C_CUDA(cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "wgrad smem attr");
   const long long chunks = (R + CK - 1) / CK;
-  const int grid = (int)(chunks < kNumSMs ? chunks : kNumSMs);
-  mlp_wgrad_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(g);
-  S2C_CHECK_LAUNCH("mlp_wgrad launch");
-  return S2C_OK;
+  const int CB = (C + 31) / 32;
+#define S2C_WGRAD(CBT, NBT, PF)                                                                                         \
+  do {                                                                                                                  \
+    auto kern = mlp_wgrad_kernel<CBT, NBT, PF>;                                                                         \
+    S2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "wgrad smem attr");    \
+    const long long cap = (long long)kNumSMs * ((PF) ? 2 : 1);                                                          \
+    const int grid = (int)(chunks < cap ? chunks : cap);                                                                \
+    kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(g);                                                            \
+    S2C_CHECK_LAUNCH("mlp_wgrad launch");                                                                               \
+    return S2C_OK;                                                                                                      \
+  } while (0)
+  // small shapes: two CTAs per SM (<= 113 KB of shared memory each) with register prefetch of the next chunk
+  if (CB <= 2 && NB <= 2 && smem <= 113 * 1024) S2C_WGRAD(2, 2, true);
+  if (CB <= 4 && NB <= 2 && smem <= 113 * 1024) S2C_WGRAD(4, 2, true);
+  if (CB <= 4 && NB <= 4) S2C_WGRAD(4, 4, false);
+  if (CB <= 8 && NB <= 4) S2C_WGRAD(8, 4, false);
+  S2C_WGRAD(8, 9, false);
+#undef S2C_WGRAD
 }

@@ -215,6 +215,17 @@ S2C_API int s2c_mlp_layer_bwd_weight(const float *dY, long long lddy, const floa
                                      const float *xh, long long R, int C, int P, float *dW, long long lddw,
                                      void *stream);
 
+/* query_and_group_grid -- same contract and bit-identical results as s2c_query_and_group / s2c_ball_query, with a
+ *   uniform-grid pre-filter (cell edge >= r): per scene a counting sort of the points by cell, then each centre tests
+ *   only the points of the 27 surrounding cells and recovers "the first nsample indices in index order" from a
+ *   per-warp bitmap.  ~200 distance tests per centre instead of n.  grouped may be NULL (ball query only), idx may be
+ *   NULL (grouped only).  workspace: s2c_ball_query_grid_workspace_bytes(B, n) bytes of device memory. */
+S2C_API long long s2c_ball_query_grid_workspace_bytes(int B, int n);
+S2C_API int s2c_query_and_group_grid(const float *xyz, const float *new_xyz, const float *features, int B, int n,
+                                     int M, int C, int feat_layout, long long feat_stride, float radius,
+                                     int nsample, int normalize_xyz, int out_layout, int *idx, float *grouped,
+                                     void *workspace, long long workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

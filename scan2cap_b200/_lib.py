@@ -32,6 +32,8 @@ SIGNATURES = {
     "s2c_mlp_layer_bwd_weight": [P, c_ll, P, c_ll, P, P, P, P, c_ll, P, P, c_ll, c_int, c_int, P, c_ll, P],
     "s2c_pool_fwd": [P, c_ll, c_ll, c_int, c_int, P, P, P, P, P],
     "s2c_pool_bwd_stats": [P, P, P, c_ll, c_ll, c_int, c_int, P, P, P, P, P],
+    "s2c_query_and_group_grid": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_ll, c_float, c_int, c_int, c_int, P, P,
+                                 P, c_ll, P],
     "s2c_knn_adjacency": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.c_double, P, P, P],
 }
 
@@ -48,6 +50,8 @@ def _load():
     lib = ctypes.CDLL(LIB_PATH)
     lib.s2c_version.restype = c_int
     lib.s2c_last_error.restype = ctypes.c_char_p
+    lib.s2c_ball_query_grid_workspace_bytes.restype = c_ll
+    lib.s2c_ball_query_grid_workspace_bytes.argtypes = [c_int, c_int]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.argtypes = argtypes

@@ -1,0 +1,332 @@
+// Ball query / fused query+group with a spatial pre-filter, bit-exact with the reference's semantics.
+//
+// The reference kernel (lib/pointnet2/_ext_src/src/ball_query_gpu.cu:9-44) and the brute-force kernel of
+// ball_query.cu test every (centre, point) pair: M*n = 82 M distance tests per scene at SA1.  The RESULT, however,
+// only depends on the points inside the ball: "the nsample smallest indices k with d2(k) < r^2, in increasing order".
+// So:
+//   1. grid_build_kernel (one CTA per scene): bounding box, uniform grid with cell edge >= r*(1+1e-3) (capped at
+//      65 536 cells), counting sort of the point indices by cell (order inside a cell is irrelevant).
+//   2. query kernel (one warp per centre): visit the 3x3 runs of x-adjacent cells around the centre (each run is one
+//      contiguous range of the sorted array), test ONLY those candidates with exactly the reference's fp32
+//      expression, and set bit k of a per-warp bitmap for every hit; the first nsample set bits of the bitmap, read in
+//      index order, are the reference's neighbour list.  Padding / empty-ball rules as in the reference.
+//   The gather epilogue (centre subtraction, 1/r, concat, channels-last output) is the one of ball_query.cu.
+// Candidate count per centre drops from n (40 000) to ~200, so the kernel becomes a gather bound by the bytes it
+// writes instead of by distance arithmetic.
+//
+// Exactness of the pre-filter: a hit has |dx| <= sqrt(d2) < r*(1+2^-22) per axis.  Cell coordinates are
+// floor(fl(fl(x-lo)*inv)) -- monotone in x -- with at most 2^16 cells per axis range, so the fp32 rounding of the
+// argument is < 1e-2 of a cell, far below the 1e-3*r/cs... margin built into the cell edge: a hit can never be more
+// than one cell away from its centre's cell in any axis.
+#include "s2c_common.cuh"
+
+namespace s2c {
+namespace {
+
+constexpr int kMaxCells = 65536;
+constexpr int kBuildThreads = 1024;
+
+struct GridParams {   // per scene, written by the build kernel
+  float lo[3];
+  float inv;          // 1 / cell edge
+  int n[3];           // cells per axis
+  int ncell;
+};
+
+__device__ __forceinline__ int cell_coord(float x, float lo, float inv, int ncells) {
+  float f = __fmul_rn(__fsub_rn(x, lo), inv);
+  f = fminf(fmaxf(f, -2.0f), (float)ncells + 1.0f);  // keeps far-away centres representable; inside points are unaffected
+  return (int)floorf(f);
+}
+
+// ---- 1. build: bbox -> grid params -> counts -> exclusive scan -> scatter ---------------------------------------
+__global__ void __launch_bounds__(kBuildThreads)
+grid_build_kernel(const float *__restrict__ xyz, int n, float radius, GridParams *__restrict__ params,
+                  int *__restrict__ cell_start /* (B, kMaxCells+1) */, float4 *__restrict__ sorted /* (B, n): x,y,z,index */,
+                  int *__restrict__ cursor /* (B, kMaxCells) scratch */) {
+  __shared__ float s_red[6][32];
+  __shared__ GridParams gp;
+  __shared__ int s_scan[kBuildThreads];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  xyz += (size_t)b * n * 3;
+  cell_start += (size_t)b * (kMaxCells + 1);
+  sorted += (size_t)b * n;
+  cursor += (size_t)b * kMaxCells;
+  // bounding box
+  float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+  for (int k = tid; k < n; k += kBuildThreads) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float v = xyz[(size_t)k * 3 + a];
+      mn[a] = fminf(mn[a], v); mx[a] = fmaxf(mx[a], v);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    for (int o = 16; o; o >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+    if (lane == 0) { s_red[a][warp] = mn[a]; s_red[3 + a][warp] = mx[a]; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = s_red[a][0]; hi[a] = s_red[3 + a][0];
+      for (int w = 1; w < kBuildThreads / 32; ++w) { lo[a] = fminf(lo[a], s_red[a][w]); hi[a] = fmaxf(hi[a], s_red[3 + a][w]); }
+    }
+    float cs = radius * 1.001f;  // cell edge: strictly larger than any per-axis offset of a hit
+    if (!(cs > 0.f)) cs = 1.f;
+    for (;;) {  // coarsen until the grid fits (cells larger than needed are still correct)
+      long long tot = 1;
+      int dims[3];
+      for (int a = 0; a < 3; ++a) {
+        const float ext = fmaxf(hi[a] - lo[a], 0.f);
+        const float q = ext / cs;
+        dims[a] = q < 65000.f ? (int)q + 1 : 65001;
+        tot *= dims[a];
+      }
+      if (tot <= kMaxCells) {
+        gp.n[0] = dims[0]; gp.n[1] = dims[1]; gp.n[2] = dims[2]; gp.ncell = (int)tot;
+        break;
+      }
+      cs *= 1.26f;
+    }
+    gp.lo[0] = lo[0]; gp.lo[1] = lo[1]; gp.lo[2] = lo[2];
+    gp.inv = 1.0f / cs;
+    params[b] = gp;
+  }
+  __syncthreads();
+  const int ncell = gp.ncell;
+  for (int c = tid; c < ncell; c += kBuildThreads) cursor[c] = 0;
+  __syncthreads();
+  // counts (cursor doubles as the histogram)
+  for (int k = tid; k < n; k += kBuildThreads) {
+    const int ix = min(max(cell_coord(xyz[(size_t)k * 3 + 0], gp.lo[0], gp.inv, gp.n[0]), 0), gp.n[0] - 1);
+    const int iy = min(max(cell_coord(xyz[(size_t)k * 3 + 1], gp.lo[1], gp.inv, gp.n[1]), 0), gp.n[1] - 1);
+    const int iz = min(max(cell_coord(xyz[(size_t)k * 3 + 2], gp.lo[2], gp.inv, gp.n[2]), 0), gp.n[2] - 1);
+    atomicAdd(&cursor[(iz * gp.n[1] + iy) * gp.n[0] + ix], 1);
+  }
+  __syncthreads();
+  // exclusive scan of the counts: each thread owns a contiguous slice of cells
+  const int per = (ncell + kBuildThreads - 1) / kBuildThreads;
+  const int c0 = tid * per, c1 = min(c0 + per, ncell);
+  int local = 0;
+  for (int c = c0; c < c1; ++c) local += cursor[c];
+  s_scan[tid] = local;
+  __syncthreads();
+  for (int o = 1; o < kBuildThreads; o <<= 1) {  // Hillis-Steele inclusive scan over the 1024 slice totals
+    const int v = tid >= o ? s_scan[tid - o] : 0;
+    __syncthreads();
+    s_scan[tid] += v;
+    __syncthreads();
+  }
+  int run = s_scan[tid] - local;
+  for (int c = c0; c < c1; ++c) {
+    const int cnt = cursor[c];
+    cell_start[c] = run;
+    cursor[c] = run;  // becomes the write cursor of the scatter
+    run += cnt;
+  }
+  if (tid == kBuildThreads - 1) cell_start[ncell] = n;
+  __syncthreads();
+  if (tid == 0) cell_start[ncell] = n;
+  __syncthreads();
+  for (int k = tid; k < n; k += kBuildThreads) {
+    const int ix = min(max(cell_coord(xyz[(size_t)k * 3 + 0], gp.lo[0], gp.inv, gp.n[0]), 0), gp.n[0] - 1);
+    const int iy = min(max(cell_coord(xyz[(size_t)k * 3 + 1], gp.lo[1], gp.inv, gp.n[1]), 0), gp.n[1] - 1);
+    const int iz = min(max(cell_coord(xyz[(size_t)k * 3 + 2], gp.lo[2], gp.inv, gp.n[2]), 0), gp.n[2] - 1);
+    const int pos = atomicAdd(&cursor[(iz * gp.n[1] + iy) * gp.n[0] + ix], 1);
+    // the candidate scan reads coordinates and index with ONE coalesced 16-byte load per point
+    sorted[pos] = make_float4(xyz[(size_t)k * 3 + 0], xyz[(size_t)k * 3 + 1], xyz[(size_t)k * 3 + 2], __int_as_float(k));
+  }
+}
+
+// ---- 2. query (+ gather) ---------------------------------------------------------------------------------
+struct GroupArgs {
+  const float *features; float *grouped; int C;
+  long long feat_point_stride, feat_chan_stride, feat_scene_stride;
+  int out_layout; float inv_radius; int normalize;
+};
+
+template <bool GROUP>
+__global__ void __launch_bounds__(256)
+grid_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz, int n, int M, float radius, int nsample,
+                  const GridParams *__restrict__ params, const int *__restrict__ cell_start, const float4 *__restrict__ sorted,
+                  int words /* bitmap words per warp */, int *__restrict__ idx, GroupArgs ga) {
+  extern __shared__ unsigned int smem_u[];
+  const int warps = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned int *bm = smem_u + (size_t)warp * words;
+  int *li = reinterpret_cast<int *>(smem_u + (size_t)warps * words) + (size_t)warp * nsample;
+  const int b = blockIdx.y;
+  xyz += (size_t)b * n * 3;
+  new_xyz += (size_t)b * M * 3;
+  cell_start += (size_t)b * (kMaxCells + 1);
+  sorted += (size_t)b * n;
+  const GridParams gp = params[b];
+  const float radius2 = __fmul_rn(radius, radius);
+  for (int w = lane; w < words; w += 32) bm[w] = 0u;
+  __syncwarp();
+
+  for (int j = blockIdx.x * warps + warp; j < M; j += gridDim.x * warps) {
+    const float cx = new_xyz[j * 3 + 0], cy = new_xyz[j * 3 + 1], cz = new_xyz[j * 3 + 2];
+    const int ix = cell_coord(cx, gp.lo[0], gp.inv, gp.n[0]);
+    const int iy = cell_coord(cy, gp.lo[1], gp.inv, gp.n[1]);
+    const int iz = cell_coord(cz, gp.lo[2], gp.inv, gp.n[2]);
+    int hits = 0;
+    const int x0 = max(ix - 1, 0), x1 = min(ix + 1, gp.n[0] - 1);
+    if (x0 <= x1) {
+      for (int dz = -1; dz <= 1; ++dz) {
+        const int z = iz + dz;
+        if (z < 0 || z >= gp.n[2]) continue;
+        for (int dy = -1; dy <= 1; ++dy) {
+          const int y = iy + dy;
+          if (y < 0 || y >= gp.n[1]) continue;
+          const int row = (z * gp.n[1] + y) * gp.n[0];
+          const int s = cell_start[row + x0], e = cell_start[row + x1 + 1];  // x-adjacent cells are contiguous
+          for (int t = s + lane; t < e; t += 32) {
+            const float4 p = __ldg(sorted + t);
+            const int k = __float_as_int(p.w);
+            const float d2 = sqdist3(cx, cy, cz, p.x, p.y, p.z);
+            if (d2 < radius2) {
+              atomicOr(&bm[k >> 5], 1u << (k & 31));
+              ++hits;
+            }
+          }
+        }
+      }
+    }
+    hits = __reduce_add_sync(0xffffffffu, hits);
+    __syncwarp();
+    // ordered extraction of the first nsample set bits (and clearing of the bitmap)
+    int cnt = 0;
+    if (hits > 0) {
+      for (int w0 = 0; w0 < words; w0 += 32) {
+        const int w = w0 + lane;
+        unsigned int bits = (w < words) ? bm[w] : 0u;
+        if (bits) bm[w] = 0u;
+        if (cnt < nsample) {
+          const int c = __popc(bits);
+          int pre = c;  // inclusive warp scan of the per-lane counts
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, pre, o);
+            if (lane >= o) pre += v;
+          }
+          int pos = cnt + pre - c;
+          while (bits && pos < nsample) {
+            const int bit = __ffs(bits) - 1;
+            li[pos++] = (w << 5) + bit;
+            bits &= bits - 1;
+          }
+          cnt += __shfl_sync(0xffffffffu, pre, 31);
+        }
+      }
+      cnt = min(cnt, nsample);
+    }
+    __syncwarp();
+    const int first = cnt > 0 ? li[0] : 0;
+    __syncwarp();
+    for (int s = cnt + lane; s < nsample; s += 32) li[s] = first;
+    __syncwarp();
+    if (idx) {
+      int *o = idx + ((size_t)b * M + j) * nsample;
+      for (int s = lane; s < nsample; s += 32) o[s] = li[s];
+    }
+    if (GROUP) {
+      const int CC = 3 + ga.C;
+      const float *f = ga.features ? ga.features + (size_t)b * ga.feat_scene_stride : nullptr;
+      if (ga.out_layout == 0) {
+        float *o = ga.grouped + (((size_t)b * CC) * M + j) * nsample;
+        const size_t cstride = (size_t)M * nsample;
+        for (int s = lane; s < nsample; s += 32) {
+          const int k = li[s];
+          float rx = __fsub_rn(xyz[(size_t)k * 3 + 0], cx), ry = __fsub_rn(xyz[(size_t)k * 3 + 1], cy), rz = __fsub_rn(xyz[(size_t)k * 3 + 2], cz);
+          if (ga.normalize) { rx = __fmul_rn(rx, ga.inv_radius); ry = __fmul_rn(ry, ga.inv_radius); rz = __fmul_rn(rz, ga.inv_radius); }
+          st_stream(o + s, rx); st_stream(o + cstride + s, ry); st_stream(o + 2 * cstride + s, rz);
+          const float *fk = f + (size_t)k * ga.feat_point_stride;
+          for (int ch = 0; ch < ga.C; ++ch) st_stream(o + (size_t)(3 + ch) * cstride + s, __ldg(fk + (size_t)ch * ga.feat_chan_stride));
+        }
+      } else {
+        const int CP = ga.out_layout == 2 ? ((CC + 3) & ~3) : CC;
+        float *o = ga.grouped + ((size_t)b * M + j) * (size_t)nsample * CP;
+        const int total = nsample * CP;
+        for (int t = lane; t < total; t += 32) {
+          const int s = t / CP, ch = t - s * CP;
+          const int k = li[s];
+          float v;
+          if (ch >= CC) {
+            v = 0.f;
+          } else if (ch < 3) {
+            v = __fsub_rn(xyz[(size_t)k * 3 + ch], ch == 0 ? cx : (ch == 1 ? cy : cz));
+            if (ga.normalize) v = __fmul_rn(v, ga.inv_radius);
+          } else {
+            v = __ldg(f + (size_t)k * ga.feat_point_stride + (size_t)(ch - 3) * ga.feat_chan_stride);
+          }
+          st_stream(o + t, v);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace
+}  // namespace s2c
+
+extern "C" long long s2c_ball_query_grid_workspace_bytes(int B, int n) {
+  using namespace s2c;
+  // params (64 B per scene) | sorted (B, n) float4 | cell_start (B, kMaxCells+1) | cursor (B, kMaxCells)
+  return (long long)B * 64 + (long long)B * n * 16 + (long long)B * (kMaxCells + 1) * 4 + (long long)B * kMaxCells * 4 + 512;
+}
+
+extern "C" int s2c_query_and_group_grid(const float *xyz, const float *new_xyz, const float *features, int B, int n, int M,
+                                        int C, int feat_layout, long long feat_stride, float radius, int nsample,
+                                        int normalize_xyz, int out_layout, int *idx, float *grouped, void *workspace,
+                                        long long workspace_bytes, void *stream) {
+  using namespace s2c;
+  S2C_REQUIRE(B >= 0 && n >= 1 && M >= 0 && C >= 0, "query_and_group_grid: bad sizes");
+  S2C_REQUIRE(nsample >= 1 && nsample <= 1024, "query_and_group_grid: nsample=%d outside [1,1024]", nsample);
+  S2C_REQUIRE(radius > 0.f, "query_and_group_grid: radius must be positive");
+  S2C_REQUIRE(feat_layout == 0 || feat_layout == 1, "query_and_group_grid: feat_layout must be 0 or 1");
+  S2C_REQUIRE(out_layout >= 0 && out_layout <= 2, "query_and_group_grid: out_layout must be 0, 1 or 2");
+  if (B == 0 || M == 0) return S2C_OK;
+  S2C_REQUIRE(xyz && new_xyz && (idx || grouped) && workspace, "query_and_group_grid: null pointer");
+  S2C_REQUIRE(C == 0 || features || !grouped, "query_and_group_grid: features is null but C=%d", C);
+  S2C_REQUIRE(workspace_bytes >= s2c_ball_query_grid_workspace_bytes(B, n), "query_and_group_grid: workspace too small");
+  S2C_REQUIRE(B <= 65535, "query_and_group_grid: B too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char *ws = (unsigned char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  GridParams *params = (GridParams *)ws;
+  float4 *sorted = (float4 *)(ws + (size_t)B * 64);
+  int *cell_start = (int *)(sorted + (size_t)B * n);
+  int *cursor = cell_start + (size_t)B * (kMaxCells + 1);
+  grid_build_kernel<<<B, kBuildThreads, 0, st>>>(xyz, n, radius, params, cell_start, sorted, cursor);
+  S2C_CHECK_LAUNCH("grid_build");
+  GroupArgs ga = {};
+  ga.features = features; ga.grouped = grouped; ga.C = C;
+  if (feat_layout == 0) { ga.feat_point_stride = 1; ga.feat_chan_stride = n; ga.feat_scene_stride = (long long)C * n; }
+  else {
+    S2C_REQUIRE(feat_stride >= C, "query_and_group_grid: feat_stride %lld < C=%d", feat_stride, C);
+    ga.feat_point_stride = feat_stride; ga.feat_chan_stride = 1; ga.feat_scene_stride = (long long)n * feat_stride;
+  }
+  ga.out_layout = out_layout; ga.normalize = normalize_xyz ? 1 : 0; ga.inv_radius = normalize_xyz ? (1.0f / radius) : 1.0f;
+  const int words = (n + 31) / 32;
+  int warps = 8;
+  while (warps > 1 && (size_t)warps * (words + nsample) * 4 > 200 * 1024) warps >>= 1;
+  const size_t smem = (size_t)warps * (words + nsample) * 4;
+  S2C_REQUIRE(smem <= 227 * 1024, "query_and_group_grid: n=%d too large for the per-warp bitmap", n);
+  const int ctas_x = min(ceil_div(M, warps), 4 * kNumSMs / max(B, 1) + 1);
+  dim3 grid((unsigned)ctas_x, (unsigned)B);
+  if (grouped) {
+    S2C_CUDA(cudaFuncSetAttribute(grid_query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "grid_query smem");
+    grid_query_kernel<true><<<grid, warps * 32, smem, st>>>(new_xyz, xyz, n, M, radius, nsample, params, cell_start, sorted, words, idx, ga);
+  } else {
+    S2C_CUDA(cudaFuncSetAttribute(grid_query_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "grid_query smem");
+    grid_query_kernel<false><<<grid, warps * 32, smem, st>>>(new_xyz, xyz, n, M, radius, nsample, params, cell_start, sorted, words, idx, ga);
+  }
+  S2C_CHECK_LAUNCH("grid_query");
+  return S2C_OK;
+}

@@ -8,7 +8,13 @@ outputs, and enqueues on the current stream of the tensors' device; violations r
 """
 import torch
 
-from ..._lib import call
+import os
+
+from ..._lib import LIB, call
+
+# ball queries over at least this many points go through the uniform-grid pre-filter (S2C_BALL_GRID_MIN=0: always,
+# a huge value: never); below it the brute-force scan is as fast and needs no workspace
+GRID_MIN_POINTS = int(os.environ.get("S2C_BALL_GRID_MIN", "4096"))
 
 
 def _chk(t, name, dtype):
@@ -91,8 +97,14 @@ def ball_query(new_xyz, xyz, radius, nsample):
     n = xyz.shape[1]
     idx = torch.empty((B, M, int(nsample)), dtype=torch.int32, device=new_xyz.device)
     with _guard(new_xyz):
-        call("s2c_ball_query", new_xyz.data_ptr(), xyz.data_ptr(), B, n, M, float(radius), int(nsample),
-             idx.data_ptr(), None, _stream(new_xyz))
+        if n >= GRID_MIN_POINTS and radius > 0:
+            ws_bytes = LIB.s2c_ball_query_grid_workspace_bytes(B, n)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xyz.device)
+            call("s2c_query_and_group_grid", xyz.data_ptr(), new_xyz.data_ptr(), None, B, n, M, 0, 0, 0, float(radius),
+                 int(nsample), 0, 0, idx.data_ptr(), None, ws.data_ptr(), ws_bytes, _stream(new_xyz))
+        else:
+            call("s2c_ball_query", new_xyz.data_ptr(), xyz.data_ptr(), B, n, M, float(radius), int(nsample),
+                 idx.data_ptr(), None, _stream(new_xyz))
     return idx
 
 
@@ -189,10 +201,18 @@ def query_and_group(xyz, new_xyz, features, radius, nsample, normalize_xyz, feat
         grouped = torch.empty((B, M, int(nsample), Cp), dtype=torch.float32, device=xyz.device)
     else:
         grouped = torch.empty((B, 3 + C, M, int(nsample)), dtype=torch.float32, device=xyz.device)
+    layout = (2 if pad4 else 1) if channels_last else 0
     with _guard(xyz):
-        call("s2c_query_and_group", xyz.data_ptr(), new_xyz.data_ptr(), fptr, B, n, M, C, flayout, fstride,
-             float(radius), int(nsample), 1 if normalize_xyz else 0, (2 if pad4 else 1) if channels_last else 0,
-             idx.data_ptr(), grouped.data_ptr(), _stream(xyz))
+        if n >= GRID_MIN_POINTS and radius > 0:
+            ws_bytes = LIB.s2c_ball_query_grid_workspace_bytes(B, n)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xyz.device)
+            call("s2c_query_and_group_grid", xyz.data_ptr(), new_xyz.data_ptr(), fptr, B, n, M, C, flayout, fstride,
+                 float(radius), int(nsample), 1 if normalize_xyz else 0, layout, idx.data_ptr(), grouped.data_ptr(),
+                 ws.data_ptr(), ws_bytes, _stream(xyz))
+        else:
+            call("s2c_query_and_group", xyz.data_ptr(), new_xyz.data_ptr(), fptr, B, n, M, C, flayout, fstride,
+                 float(radius), int(nsample), 1 if normalize_xyz else 0, layout, idx.data_ptr(), grouped.data_ptr(),
+                 _stream(xyz))
     if channels_last:
         grouped = grouped.permute(0, 3, 1, 2)  # logical (B,Cp,M,ns) over channels-last storage (Cp > 3+C: zero pad)
     return grouped, idx

@@ -4,7 +4,7 @@
 // ball_query.cu test every (centre, point) pair: M*n = 82 M distance tests per scene at SA1.  The RESULT, however,
 // only depends on the points inside the ball: "the nsample smallest indices k with d2(k) < r^2, in increasing order".
 // So:
-//   1. grid_build_kernel (one CTA per scene): bounding box, uniform grid with cell edge >= r*(1+1e-3) (capped at
+//   1. grid_build_kernel (one 8-CTA cluster per scene, phases separated by cluster barriers): bounding box, uniform grid with cell edge >= r*(1+1e-3) (capped at
 //      65 536 cells), counting sort of the point indices by cell (order inside a cell is irrelevant).
 //   2. query kernel (one warp per centre): visit the 3x3 runs of x-adjacent cells around the centre (each run is one
 //      contiguous range of the sorted array), test ONLY those candidates with exactly the reference's fp32
@@ -40,21 +40,37 @@ __device__ __forceinline__ int cell_coord(float x, float lo, float inv, int ncel
 }
 
 // ---- 1. build: bbox -> grid params -> counts -> exclusive scan -> scatter ---------------------------------------
+// One thread-block CLUSTER of kBuildCluster CTAs per scene; the phases are separated by cluster barriers
+// (release/acquire at cluster scope orders the global-memory traffic between the CTAs of the scene).
+constexpr int kBuildCluster = 8;
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(kBuildThreads)
 grid_build_kernel(const float *__restrict__ xyz, int n, float radius, GridParams *__restrict__ params,
                   int *__restrict__ cell_start /* (B, kMaxCells+1) */, float4 *__restrict__ sorted /* (B, n): x,y,z,index */,
-                  int *__restrict__ cursor /* (B, kMaxCells) scratch */) {
+                  int *__restrict__ cursor /* (B, kMaxCells) scratch */, float *__restrict__ bbox /* (B, CL, 6) scratch */) {
   __shared__ float s_red[6][32];
   __shared__ GridParams gp;
   __shared__ int s_scan[kBuildThreads];
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x / kBuildCluster, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rank = (int)cluster_rank();
+  const int gtid = rank * kBuildThreads + tid, gthreads = kBuildCluster * kBuildThreads;
   xyz += (size_t)b * n * 3;
   cell_start += (size_t)b * (kMaxCells + 1);
   sorted += (size_t)b * n;
   cursor += (size_t)b * kMaxCells;
-  // bounding box
+  bbox += (size_t)b * kBuildCluster * 6;
+  // ---- phase 1: bounding box (per-CTA partials through global scratch)
   float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
-  for (int k = tid; k < n; k += kBuildThreads) {
+  for (int k = gtid; k < n; k += gthreads) {
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       const float v = xyz[(size_t)k * 3 + a];
@@ -70,11 +86,17 @@ grid_build_kernel(const float *__restrict__ xyz, int n, float radius, GridParams
     if (lane == 0) { s_red[a][warp] = mn[a]; s_red[3 + a][warp] = mx[a]; }
   }
   __syncthreads();
-  if (tid == 0) {
+  if (tid < 6) {
+    float v = s_red[tid][0];
+    for (int w = 1; w < kBuildThreads / 32; ++w) v = tid < 3 ? fminf(v, s_red[tid][w]) : fmaxf(v, s_red[tid][w]);
+    bbox[rank * 6 + tid] = v;
+  }
+  cluster_sync_all();
+  if (tid == 0) {  // every CTA derives the same grid parameters
     float lo[3], hi[3];
     for (int a = 0; a < 3; ++a) {
-      lo[a] = s_red[a][0]; hi[a] = s_red[3 + a][0];
-      for (int w = 1; w < kBuildThreads / 32; ++w) { lo[a] = fminf(lo[a], s_red[a][w]); hi[a] = fmaxf(hi[a], s_red[3 + a][w]); }
+      lo[a] = bbox[a]; hi[a] = bbox[3 + a];
+      for (int r = 1; r < kBuildCluster; ++r) { lo[a] = fminf(lo[a], bbox[r * 6 + a]); hi[a] = fmaxf(hi[a], bbox[r * 6 + 3 + a]); }
     }
     float cs = radius * 1.001f;  // cell edge: strictly larger than any per-axis offset of a hit
     if (!(cs > 0.f)) cs = 1.f;
@@ -95,51 +117,54 @@ grid_build_kernel(const float *__restrict__ xyz, int n, float radius, GridParams
     }
     gp.lo[0] = lo[0]; gp.lo[1] = lo[1]; gp.lo[2] = lo[2];
     gp.inv = 1.0f / cs;
-    params[b] = gp;
+    if (rank == 0) params[b] = gp;
   }
   __syncthreads();
   const int ncell = gp.ncell;
-  for (int c = tid; c < ncell; c += kBuildThreads) cursor[c] = 0;
-  __syncthreads();
-  // counts (cursor doubles as the histogram)
-  for (int k = tid; k < n; k += kBuildThreads) {
+  // ---- phase 2: clear the histogram
+  for (int c = gtid; c < ncell; c += gthreads) cursor[c] = 0;
+  cluster_sync_all();
+  // ---- phase 3: counts (cursor doubles as the histogram)
+  for (int k = gtid; k < n; k += gthreads) {
     const int ix = min(max(cell_coord(xyz[(size_t)k * 3 + 0], gp.lo[0], gp.inv, gp.n[0]), 0), gp.n[0] - 1);
     const int iy = min(max(cell_coord(xyz[(size_t)k * 3 + 1], gp.lo[1], gp.inv, gp.n[1]), 0), gp.n[1] - 1);
     const int iz = min(max(cell_coord(xyz[(size_t)k * 3 + 2], gp.lo[2], gp.inv, gp.n[2]), 0), gp.n[2] - 1);
     atomicAdd(&cursor[(iz * gp.n[1] + iy) * gp.n[0] + ix], 1);
   }
-  __syncthreads();
-  // exclusive scan of the counts: each thread owns a contiguous slice of cells
-  const int per = (ncell + kBuildThreads - 1) / kBuildThreads;
-  const int c0 = tid * per, c1 = min(c0 + per, ncell);
-  int local = 0;
-  for (int c = c0; c < c1; ++c) local += cursor[c];
-  s_scan[tid] = local;
-  __syncthreads();
-  for (int o = 1; o < kBuildThreads; o <<= 1) {  // Hillis-Steele inclusive scan over the 1024 slice totals
-    const int v = tid >= o ? s_scan[tid - o] : 0;
+  cluster_sync_all();
+  // ---- phase 4: exclusive scan of the counts (CTA 0; each thread owns a contiguous slice of cells)
+  if (rank == 0) {
+    const int per = (ncell + kBuildThreads - 1) / kBuildThreads;
+    const int c0 = tid * per, c1 = min(c0 + per, ncell);
+    int local = 0;
+    for (int c = c0; c < c1; ++c) local += cursor[c];
+    s_scan[tid] = local;
     __syncthreads();
-    s_scan[tid] += v;
-    __syncthreads();
+    for (int o = 1; o < kBuildThreads; o <<= 1) {  // Hillis-Steele inclusive scan over the 1024 slice totals
+      const int v = tid >= o ? s_scan[tid - o] : 0;
+      __syncthreads();
+      s_scan[tid] += v;
+      __syncthreads();
+    }
+    int run = s_scan[tid] - local;
+    for (int c = c0; c < c1; ++c) {
+      const int cnt = cursor[c];
+      cell_start[c] = run;
+      cursor[c] = run;  // becomes the write cursor of the scatter
+      run += cnt;
+    }
+    if (tid == 0) cell_start[ncell] = n;
   }
-  int run = s_scan[tid] - local;
-  for (int c = c0; c < c1; ++c) {
-    const int cnt = cursor[c];
-    cell_start[c] = run;
-    cursor[c] = run;  // becomes the write cursor of the scatter
-    run += cnt;
-  }
-  if (tid == kBuildThreads - 1) cell_start[ncell] = n;
-  __syncthreads();
-  if (tid == 0) cell_start[ncell] = n;
-  __syncthreads();
-  for (int k = tid; k < n; k += kBuildThreads) {
-    const int ix = min(max(cell_coord(xyz[(size_t)k * 3 + 0], gp.lo[0], gp.inv, gp.n[0]), 0), gp.n[0] - 1);
-    const int iy = min(max(cell_coord(xyz[(size_t)k * 3 + 1], gp.lo[1], gp.inv, gp.n[1]), 0), gp.n[1] - 1);
-    const int iz = min(max(cell_coord(xyz[(size_t)k * 3 + 2], gp.lo[2], gp.inv, gp.n[2]), 0), gp.n[2] - 1);
+  cluster_sync_all();
+  // ---- phase 5: scatter
+  for (int k = gtid; k < n; k += gthreads) {
+    const float x = xyz[(size_t)k * 3 + 0], y = xyz[(size_t)k * 3 + 1], z = xyz[(size_t)k * 3 + 2];
+    const int ix = min(max(cell_coord(x, gp.lo[0], gp.inv, gp.n[0]), 0), gp.n[0] - 1);
+    const int iy = min(max(cell_coord(y, gp.lo[1], gp.inv, gp.n[1]), 0), gp.n[1] - 1);
+    const int iz = min(max(cell_coord(z, gp.lo[2], gp.inv, gp.n[2]), 0), gp.n[2] - 1);
     const int pos = atomicAdd(&cursor[(iz * gp.n[1] + iy) * gp.n[0] + ix], 1);
     // the candidate scan reads coordinates and index with ONE coalesced 16-byte load per point
-    sorted[pos] = make_float4(xyz[(size_t)k * 3 + 0], xyz[(size_t)k * 3 + 1], xyz[(size_t)k * 3 + 2], __int_as_float(k));
+    sorted[pos] = make_float4(x, y, z, __int_as_float(k));
   }
 }
 
@@ -279,7 +304,8 @@ grid_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ x
 extern "C" long long s2c_ball_query_grid_workspace_bytes(int B, int n) {
   using namespace s2c;
   // params (64 B per scene) | sorted (B, n) float4 | cell_start (B, kMaxCells+1) | cursor (B, kMaxCells)
-  return (long long)B * 64 + (long long)B * n * 16 + (long long)B * (kMaxCells + 1) * 4 + (long long)B * kMaxCells * 4 + 512;
+  return (long long)B * 64 + (long long)B * n * 16 + (long long)B * (kMaxCells + 1) * 4 + (long long)B * kMaxCells * 4 +
+         (long long)B * kBuildCluster * 6 * 4 + 512;
 }
 
 extern "C" int s2c_query_and_group_grid(const float *xyz, const float *new_xyz, const float *features, int B, int n, int M,
@@ -303,8 +329,18 @@ extern "C" int s2c_query_and_group_grid(const float *xyz, const float *new_xyz, 
   float4 *sorted = (float4 *)(ws + (size_t)B * 64);
   int *cell_start = (int *)(sorted + (size_t)B * n);
   int *cursor = cell_start + (size_t)B * (kMaxCells + 1);
-  grid_build_kernel<<<B, kBuildThreads, 0, st>>>(xyz, n, radius, params, cell_start, sorted, cursor);
-  S2C_CHECK_LAUNCH("grid_build");
+  float *bbox = (float *)(cursor + (size_t)B * kMaxCells);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * kBuildCluster));
+    cfg.blockDim = dim3(kBuildThreads);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kBuildCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    S2C_CUDA(cudaLaunchKernelEx(&cfg, grid_build_kernel, xyz, n, radius, params, cell_start, sorted, cursor, bbox), "grid_build launch");
+  }
   GroupArgs ga = {};
   ga.features = features; ga.grouped = grouped; ga.C = C;
   if (feat_layout == 0) { ga.feat_point_stride = 1; ga.feat_chan_stride = n; ga.feat_scene_stride = (long long)C * n; }

@@ -160,6 +160,17 @@ class TopDownSceneCaptionModule(nn.Module):
         hidden_2 = self.recurrent_cell_2(lang_input, hidden_2)
         return hidden_1, hidden_2, masks
 
+    def _step_core(self, topdown_input, obj_feats, hidden_1, hidden_2, object_masks, mapped_feats):
+        """_step after the map_topdown fusion layer (whose input-only terms the caller has hoisted)."""
+        hidden_1 = self.recurrent_cell_1(topdown_input, hidden_1)
+        combined = torch.tanh(mapped_feats + self.map_hidd(hidden_1).unsqueeze(1))
+        scores = self.attend(combined).masked_fill(object_masks == 0, float("-1e30"))  # (B,K,1)
+        masks = F.softmax(scores, dim=1)
+        attended = (obj_feats * masks).sum(1)
+        lang_input = self.map_lang(torch.cat([attended, hidden_1], dim=-1))
+        hidden_2 = self.recurrent_cell_2(lang_input, hidden_2)
+        return hidden_1, hidden_2, masks
+
     def _query_locals(self, data_dict, target_ids, object_masks, include_self=True,
                       overlay_threshold=CONF.TRAIN.OVERLAID_THRESHOLD):
         """target_ids (B) or (B,T) -> 0/1 float mask (B,K) or (B,T,K) of the num_locals nearest proposals."""
@@ -211,16 +222,28 @@ class TopDownSceneCaptionModule(nn.Module):
         if self.use_relation:
             obj_feats = self._add_relation_feat(data_dict, obj_feats, target_ids)
 
+        # Loop-invariant work hoisted out of the recurrence (same arithmetic up to fp32 summation order):
+        #   map_feat(obj_feats)                      -- the reference recomputes it every step (caption_module.py:275)
+        #   map_topdown's word / target-feature terms -- W_td [w_t, h2, target] = W_w w_t + W_h h2 + W_f target + b:
+        #       W_w w_t for all steps in one GEMM, W_f target + b once; only W_h h2 stays in the loop
+        #   classifier(h2)                           -- one (B*T, 512) x (512, V) GEMM after the loop
+        T = max(num_words - 1, 1)
+        E, H = self.emb_size, self.hidden_size
         mapped = self.map_feat(obj_feats)
+        w_td, b_td = self.map_topdown[0].weight, self.map_topdown[0].bias
+        pre_word = F.linear(word_embs[:, :T], w_td[:, :E])                 # (B,T,emb)
+        pre_tgt = F.linear(target_feats, w_td[:, E + H:], b_td)            # (B,emb)
+        w_td_h = w_td[:, E:E + H]
         step_masks = valid_masks.unsqueeze(-1)
         hidden_1 = torch.zeros(B, self.hidden_size, device=dev)
         hidden_2 = torch.zeros(B, self.hidden_size, device=dev)
-        outputs, masks = [], []
-        for step_id in range(max(num_words - 1, 1)):
-            hidden_1, hidden_2, step_mask = self._step(word_embs[:, step_id], target_feats, obj_feats, hidden_1,
-                                                       hidden_2, step_masks, mapped)
-            outputs.append(self.classifier(hidden_2).unsqueeze(1))
+        hiddens, masks = [], []
+        for step_id in range(T):
+            u = torch.relu(pre_word[:, step_id] + pre_tgt + F.linear(hidden_2, w_td_h))
+            hidden_1, hidden_2, step_mask = self._step_core(u, obj_feats, hidden_1, hidden_2, step_masks, mapped)
+            hiddens.append(hidden_2)
             masks.append(step_mask)
+        outputs = [self.classifier(torch.stack(hiddens, dim=1))]          # (B,T,V)
         good_bbox_masks = target_ious > min_iou
         data_dict["lang_cap"] = torch.cat(outputs, dim=1)       # (B,T,V)
         data_dict["pred_ious"] = _masked_mean(target_ious, good_bbox_masks)

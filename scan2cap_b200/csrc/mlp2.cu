@@ -195,10 +195,11 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
   unsigned char *op_base = smem;
   unsigned char *raw_base = smem + OS * OP_BYTES;
   float *s_pro = reinterpret_cast<float *>(raw_base + (size_t)RS * RAW_BYTES);  // [NPRO][KC*BK] coefficients
-  uint64_t *bars = reinterpret_cast<uint64_t *>(s_pro + NPRO * KC * BK);
-  uint64_t *raw_full = bars, *raw_empty = bars + 4, *op_full = bars + 8, *op_empty = bars + 10, *acc_full = bars + 12,
-           *acc_empty = bars + 14;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+  float *s_epi = s_pro + NPRO * KC * BK;                                         // [4 warps][32 rows][36] epilogue staging
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_epi + 4 * 32 * 36);
+  uint64_t *raw_full = bars, *raw_empty = bars + 8, *op_full = bars + 16, *op_empty = bars + 18, *acc_full = bars + 20,
+           *acc_empty = bars + 22;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 24);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool has_pro = g.p0 != nullptr;
@@ -362,65 +363,60 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
       }
     }
   } else {
-    // ===================== epilogue: TMEM -> registers -> global rows (+ column statistics)
+    // ===================== epilogue: TMEM -> registers -> per-warp smem transpose -> coalesced global rows (+ statistics)
+    // tcgen05.ld hands every thread one accumulator ROW; storing that directly would scatter each warp store over
+    // 32 cache lines.  The 32x32 block goes through shared memory instead and leaves as 4 rows x 128 B per instruction;
+    // the same (row, 16-byte segment) mapping loads the ReLU-mask operand and needs only two shuffles for the column sums.
     const int q = warp & 3;  // the TMEM lane quarter this warp may access
     const bool has_stats = g.stat_sum != nullptr;
-    float acc_s[N / 32], acc_q[N / 32];
+    float *sE = s_epi + q * 32 * 36;
+    const int er = lane >> 3, es = lane & 7;  // read-back mapping: rows er, er+4, ..., segment es
+    float4 acc_s[N / 32], acc_q[N / 32];
 #pragma unroll
-    for (int i = 0; i < N / 32; ++i) { acc_s[i] = 0.f; acc_q[i] = 0.f; }
+    for (int i = 0; i < N / 32; ++i) { acc_s[i] = make_float4(0.f, 0.f, 0.f, 0.f); acc_q[i] = acc_s[i]; }
     for (long long t = 0; t < my_tiles; ++t) {
       const int ab = (int)(t & 1);
-      const long long row = ((long long)blockIdx.x + t * gridDim.x) * BM + q * 32 + lane;
+      const long long row_base = ((long long)blockIdx.x + t * gridDim.x) * BM + q * 32;
       mbar_wait(&acc_full[ab], (uint32_t)((t >> 1) & 1));
       tc_fence_after();
 #pragma unroll
       for (int cb = 0; cb < N / 32; ++cb) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * N + cb * 32), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4 *>(sE + lane * 36 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        float4 e_sc = make_float4(1.f, 1.f, 1.f, 1.f), e_sh = make_float4(0.f, 0.f, 0.f, 0.f);
         if (EPI == EPI_MASK_STATS) {
-          // gradient w.r.t. the previous layer's rectified output -> mask by its ReLU, store, and reduce the two
-          // per-channel sums its BatchNorm backward needs: sum(g) and sum(g * y)
-          float yv[32];
+          e_sc = __ldg(reinterpret_cast<const float4 *>(g.e_scale + cb * 32 + es * 4));
+          e_sh = __ldg(reinterpret_cast<const float4 *>(g.e_shift + cb * 32 + es * 4));
+        }
+        float4 ps = make_float4(0.f, 0.f, 0.f, 0.f), pq = ps;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) yv[j] = 0.f;
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + er;
+          const long long row = row_base + rr;
+          float4 a = *reinterpret_cast<const float4 *>(sE + rr * 36 + es * 4);
           if (row < g.R) {
-            const float4 *yp = reinterpret_cast<const float4 *>(g.Yprev + row * g.ldyp + cb * 32);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 t4 = __ldg(yp + j);
-              yv[4 * j] = t4.x; yv[4 * j + 1] = t4.y; yv[4 * j + 2] = t4.z; yv[4 * j + 3] = t4.w;
+            if (EPI == EPI_MASK_STATS) {
+              // gradient w.r.t. the previous layer's rectified output: mask by its ReLU, reduce sum(g) and sum(g*y)
+              const float4 y = __ldg(reinterpret_cast<const float4 *>(g.Yprev + row * g.ldyp + cb * 32 + es * 4));
+              a.x = fmaf(y.x, e_sc.x, e_sh.x) > 0.f ? a.x : 0.f; a.y = fmaf(y.y, e_sc.y, e_sh.y) > 0.f ? a.y : 0.f;
+              a.z = fmaf(y.z, e_sc.z, e_sh.z) > 0.f ? a.z : 0.f; a.w = fmaf(y.w, e_sc.w, e_sh.w) > 0.f ? a.w : 0.f;
+              pq.x = fmaf(a.x, y.x, pq.x); pq.y = fmaf(a.y, y.y, pq.y); pq.z = fmaf(a.z, y.z, pq.z); pq.w = fmaf(a.w, y.w, pq.w);
+            } else {
+              pq.x = fmaf(a.x, a.x, pq.x); pq.y = fmaf(a.y, a.y, pq.y); pq.z = fmaf(a.z, a.z, pq.z); pq.w = fmaf(a.w, a.w, pq.w);
             }
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float esc = __ldg(g.e_scale + cb * 32 + j), esh = __ldg(g.e_shift + cb * 32 + j);
-            v[j] = (row < g.R && fmaf(yv[j], esc, esh) > 0.f) ? v[j] : 0.f;
-          }
-          if (row < g.R) {
-            float4 *dst = reinterpret_cast<float4 *>(g.C + row * g.ldc + cb * 32);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          if (has_stats) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) yv[j] *= v[j];
-            acc_s[cb] += warp_colsum32(v, lane);
-            acc_q[cb] += warp_colsum32(yv, lane);
-          }
-        } else {
-          if (row < g.R) {
-            float4 *dst = reinterpret_cast<float4 *>(g.C + row * g.ldc + cb * 32);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          if (has_stats) {  // rows beyond R were staged as zeros, so they add nothing
-            float sq[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
-            acc_s[cb] += warp_colsum32(v, lane);
-            acc_q[cb] += warp_colsum32(sq, lane);
+            ps.x += a.x; ps.y += a.y; ps.z += a.z; ps.w += a.w;
+            *reinterpret_cast<float4 *>(g.C + row * g.ldc + cb * 32 + es * 4) = a;
           }
         }
+        if (has_stats) {
+          acc_s[cb].x += ps.x; acc_s[cb].y += ps.y; acc_s[cb].z += ps.z; acc_s[cb].w += ps.w;
+          acc_q[cb].x += pq.x; acc_q[cb].y += pq.y; acc_q[cb].z += pq.z; acc_q[cb].w += pq.w;
+        }
+        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[ab]);
@@ -428,8 +424,19 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
     if (has_stats) {
 #pragma unroll
       for (int cb = 0; cb < N / 32; ++cb) {
-        atomicAdd(g.stat_sum + cb * 32 + lane, (double)acc_s[cb]);
-        atomicAdd(g.stat_sumsq + cb * 32 + lane, (double)acc_q[cb]);
+        float4 a = acc_s[cb], b = acc_q[cb];
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {  // the four lanes that share a segment
+          a.x += __shfl_xor_sync(0xffffffffu, a.x, o); a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+          a.z += __shfl_xor_sync(0xffffffffu, a.z, o); a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
+          b.x += __shfl_xor_sync(0xffffffffu, b.x, o); b.y += __shfl_xor_sync(0xffffffffu, b.y, o);
+          b.z += __shfl_xor_sync(0xffffffffu, b.z, o); b.w += __shfl_xor_sync(0xffffffffu, b.w, o);
+        }
+        if (lane < 8) {
+          double *s1 = g.stat_sum + cb * 32 + lane * 4, *s2 = g.stat_sumsq + cb * 32 + lane * 4;
+          atomicAdd(s1 + 0, (double)a.x); atomicAdd(s1 + 1, (double)a.y); atomicAdd(s1 + 2, (double)a.z); atomicAdd(s1 + 3, (double)a.w);
+          atomicAdd(s2 + 0, (double)b.x); atomicAdd(s2 + 1, (double)b.y); atomicAdd(s2 + 2, (double)b.z); atomicAdd(s2 + 3, (double)b.w);
+        }
       }
     }
   }
@@ -441,7 +448,7 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
 size_t gemm2_smem(int N, int K, int RS, int raw_tiles, int npro) {
   const int KC = (K + BK - 1) / BK;
   return (size_t)OS * (2 * BM * BK * 4 + 2 * (size_t)N * BK * 4) + (size_t)RS * raw_tiles * BM * BK * 4 +
-         (size_t)npro * KC * BK * 4 + 16 * 8 + 16;
+         (size_t)npro * KC * BK * 4 + 4 * 32 * 36 * 4 + 24 * 8 + 16;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -490,8 +497,8 @@ int launch_gemm2(const Gemm2Args &g0, const float *A2, long long lda2, cudaStrea
   if (rc) return rc;
   rc = make_tmap(&tmap2, A2 ? A2 : g.A, g.R, g.K, A2 ? lda2 : g.lda);
   if (rc) return rc;
-  int RS = 3;
-  if (const char *e = getenv("S2C_MLP_RS")) RS = atoi(e) >= 1 && atoi(e) <= 3 ? atoi(e) : 3;  // tuning / debugging knob
+  int RS = 4;  // raw-tile ring depth = bytes the TMA engine keeps in flight per SM (16 KB per stage and raw tile)
+  if (const char *e = getenv("S2C_MLP_RS")) RS = atoi(e) >= 1 && atoi(e) <= 8 ? atoi(e) : 4;  // tuning / debugging knob
   while (RS > 1 && gemm2_smem(N, g.K, RS, raw_tiles, npro) > 227 * 1024) --RS;
   const size_t smem = gemm2_smem(N, g.K, RS, raw_tiles, npro);
   if (smem > 227 * 1024) {
@@ -527,14 +534,28 @@ extern "C" int s2c_mlp_layer_fwd_v2(const float *A, long long lda, long long R, 
   S2C_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)C & 15) == 0 && ((uintptr_t)wprep & 15) == 0, "mlp_layer_fwd_v2: A, C and wprep must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const int KC = (K + BK - 1) / BK;
-  w_prep_kernel<<<ceil_div(KC * N * 8, 256), 256, 0, st>>>(W, N, K, K, 1, (unsigned char *)wprep);
-  S2C_CHECK_LAUNCH("w_prep");
+  if (N != 256) {
+    w_prep_kernel<<<ceil_div(KC * N * 8, 256), 256, 0, st>>>(W, N, K, K, 1, (unsigned char *)wprep);
+    S2C_CHECK_LAUNCH("w_prep");
+  }
   Gemm2Args g = {};
   g.A = A; g.lda = lda; g.K = K; g.p0 = pro_scale; g.p1 = pro_shift; g.wprep = (const unsigned char *)wprep;
   g.C = C; g.ldc = ldc; g.stat_sum = stat_sum; g.stat_sumsq = stat_sumsq; g.R = R;
   if (N == 64) return launch_gemm2<64, PRO_BNRELU, EPI_STORE_STATS>(g, nullptr, 0, st);
   if (N == 128) return launch_gemm2<128, PRO_BNRELU, EPI_STORE_STATS>(g, nullptr, 0, st);
-  return launch_gemm2<256, PRO_BNRELU, EPI_STORE_STATS>(g, nullptr, 0, st);
+  // N = 256: two passes over 128 output channels each (the operand + staging footprint of a 256-wide tile does not
+  // leave room for a double-buffered pipeline in 227 KB); w_prep wrote the chunks of all 256 rows, so prepare per half
+  for (int h = 0; h < 2; ++h) {
+    unsigned char *wp = (unsigned char *)wprep + (size_t)h * KC * 128 * 256;
+    w_prep_kernel<<<ceil_div(KC * 128 * 8, 256), 256, 0, st>>>(W + (size_t)h * 128 * K, 128, K, K, 1, wp);
+    S2C_CHECK_LAUNCH("w_prep");
+    Gemm2Args gh = g;
+    gh.wprep = wp; gh.C = C + h * 128;
+    if (stat_sum) { gh.stat_sum = stat_sum + h * 128; gh.stat_sumsq = stat_sumsq + h * 128; }
+    const int rc = launch_gemm2<128, PRO_BNRELU, EPI_STORE_STATS>(gh, nullptr, 0, st);
+    if (rc) return rc;
+  }
+  return S2C_OK;
 }
 
 // Backward "data" kernel of one layer l of the shared MLP (tensor cores, same pipeline as the forward):
@@ -564,20 +585,34 @@ extern "C" int s2c_mlp_layer_bwd_data(const float *G, long long ldg, const float
   cudaStream_t st = (cudaStream_t)stream;
   const int KC = (K + BK - 1) / BK;
   // B operand = W_l^T: B[n][k] = W[k][n]
-  w_prep_kernel<<<ceil_div(KC * N * 8, 256), 256, 0, st>>>(W, N, K, N, 0, (unsigned char *)wprep);
-  S2C_CHECK_LAUNCH("w_prep");
+  if (N != 256) {
+    w_prep_kernel<<<ceil_div(KC * N * 8, 256), 256, 0, st>>>(W, N, K, N, 0, (unsigned char *)wprep);
+    S2C_CHECK_LAUNCH("w_prep");
+  }
   Gemm2Args g = {};
   g.K = K; g.p0 = a; g.p1 = b; g.p2 = c; g.wprep = (const unsigned char *)wprep; g.C = C; g.ldc = ldc; g.dY_out = dY_out;
   g.Yprev = Yprev; g.ldyp = ldyp; g.e_scale = prev_scale; g.e_shift = prev_shift;
   g.stat_sum = stat_sum; g.stat_sumsq = stat_sumsq; g.R = R;
   if (pool) {
     g.A = nullptr; g.lda = 0; g.p3 = last_scale; g.p4 = last_shift; g.dpool = dpool; g.argmax = argmax; g.ns = ns;
-    if (N == 64) return launch_gemm2<64, PRO_POOL, EPI_MASK_STATS>(g, Y, ldy, st);
-    if (N == 128) return launch_gemm2<128, PRO_POOL, EPI_MASK_STATS>(g, Y, ldy, st);
-    return launch_gemm2<256, PRO_POOL, EPI_MASK_STATS>(g, Y, ldy, st);
+  } else {
+    g.A = G; g.lda = ldg;
   }
-  g.A = G; g.lda = ldg;
-  if (N == 64) return launch_gemm2<64, PRO_AFFINE2, EPI_MASK_STATS>(g, Y, ldy, st);
-  if (N == 128) return launch_gemm2<128, PRO_AFFINE2, EPI_MASK_STATS>(g, Y, ldy, st);
-  return launch_gemm2<256, PRO_AFFINE2, EPI_MASK_STATS>(g, Y, ldy, st);
+  const int halves = N == 256 ? 2 : 1, NH = N / halves;   // 256 output channels: two 128-wide passes (see the forward)
+  for (int h = 0; h < halves; ++h) {
+    Gemm2Args gh = g;
+    if (halves == 2) {
+      unsigned char *wp = (unsigned char *)wprep + (size_t)h * KC * 128 * 256;
+      w_prep_kernel<<<ceil_div(KC * 128 * 8, 256), 256, 0, st>>>(W + h * 128, 128, K, N, 0, wp);
+      S2C_CHECK_LAUNCH("w_prep");
+      gh.wprep = wp; gh.C = C + h * 128; gh.Yprev = Yprev + h * 128; gh.e_scale = prev_scale + h * 128; gh.e_shift = prev_shift + h * 128;
+      gh.stat_sum = stat_sum + h * 128; gh.stat_sumsq = stat_sumsq + h * 128;
+      if (h == 1) gh.dY_out = nullptr;  // dY does not depend on the output half: written once
+    }
+    int rc;
+    if (pool) rc = NH == 64 ? launch_gemm2<64, PRO_POOL, EPI_MASK_STATS>(gh, Y, ldy, st) : launch_gemm2<128, PRO_POOL, EPI_MASK_STATS>(gh, Y, ldy, st);
+    else rc = NH == 64 ? launch_gemm2<64, PRO_AFFINE2, EPI_MASK_STATS>(gh, Y, ldy, st) : launch_gemm2<128, PRO_AFFINE2, EPI_MASK_STATS>(gh, Y, ldy, st);
+    if (rc) return rc;
+  }
+  return S2C_OK;
 }

@@ -285,16 +285,26 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     # single-kernel timing for the roofline: the same step issued eagerly, CUDA events around the SA1
     # query+group launch (events cannot bracket a node inside a replayed graph)
-    qg_name = "s2c_query_and_group"
-    qg_events, qg_steps = [], min(args.steps, 5)
+    qg_name, qg_grid = "s2c_query_and_group", "s2c_query_and_group_grid"
+    qg_events, qg_steps, qg_kernel = [], min(args.steps, 5), None
     if engine is not None:
         resident = to_device(host, device, num_words)
-        L.TIMING = {qg_name: []}
+        L.TIMING = {qg_name: [], qg_grid: []}
         for _ in range(qg_steps):
             flush.zero_()
             engine.run_eager(dict(resident))
         torch.cuda.synchronize()
-        qg_events = L.TIMING[qg_name]
+        if L.TIMING[qg_grid]:
+            # SA1 (n = 40 000 >= S2C_BALL_GRID_MIN) is the only call of the step that takes the uniform-grid entry
+            # point: grid_build_kernel + grid_query_kernel<GROUP>, both inside the timed bracket
+            per = len(L.TIMING[qg_grid]) // qg_steps
+            qg_events = [e for i, e in enumerate(L.TIMING[qg_grid]) if i % per == 0]
+            qg_kernel = "grid_build_kernel + grid_query_kernel<GROUP>"
+        else:
+            # SA1 is the first query_and_group call of every step (5 per step: SA1-4 + vote aggregation)
+            per = len(L.TIMING[qg_name]) // qg_steps
+            qg_events = [e for i, e in enumerate(L.TIMING[qg_name]) if i % per == 0]
+            qg_kernel = "ball_query_kernel<GROUP>"
         L.TIMING = None
     timed(2, True)
     ms_e2e, last_loss = timed(args.steps, True)
@@ -329,10 +339,7 @@ def main():
         line["config"]["reference"] = ("unmodified lib/pointnet2 CUDA kernels (sm_100 build, oracle/_ref) + literal "
                                        "restatement of the reference Python layers; CUDA_LAUNCH_BLOCKING unset")
     if qg_events:
-        # SA1 is the first query_and_group call of every step (5 calls per step: SA1-4 + vote aggregation)
-        per_step = len(qg_events) // qg_steps
-        sa1 = [e for i, e in enumerate(qg_events) if i % per_step == 0]
-        t_ms = float(np.mean([s.elapsed_time(e) for s, e in sa1]))
+        t_ms = float(np.mean([s.elapsed_time(e) for s, e in qg_events]))
         M, ns = 2048, 64
         alg = B * (12 * N + 12 * M + 4 * C * N + 4 * M * ns + 4 * (3 + C) * M * ns)
         achieved = alg / (t_ms * 1e-3) / 1e9
@@ -341,7 +348,7 @@ def main():
         if os.path.exists(tp):
             with open(tp) as f:
                 traffic = json.load(f).get(args.config, {}).get("traffic")
-        line["roofline"] = {"bound": "hbm", "kernel": "ball_query_kernel<GROUP> (SA1: N=%d, M=2048, nsample=64, C=%d)" % (N, C),
+        line["roofline"] = {"bound": "hbm", "kernel": "%s (SA1: N=%d, M=2048, nsample=64, C=%d)" % (qg_kernel, N, C),
                             "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                             "traffic": traffic, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": t_ms,
                             "peak_source": pk_src}

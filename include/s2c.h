@@ -226,6 +226,32 @@ S2C_API int s2c_query_and_group_grid(const float *xyz, const float *new_xyz, con
                                      int nsample, int normalize_xyz, int out_layout, int *idx, float *grouped,
                                      void *workspace, long long workspace_bytes, void *stream);
 
+/* bn_finalize -- per-layer BatchNorm bookkeeping of the fused shared-MLP path in ONE launch (replaces nn.BatchNorm2d's
+ *   statistics handling, lib/pointnet2/pytorch_utils.py:88-120 / torch batch_norm):
+ *   use_batch_stats: mean = sum/R, var = max(sumsq/R - mean^2, 0) from the float64 column sums of the GEMM epilogue,
+ *   else the running statistics; update_running: running = (1-momentum)*running + momentum*{mean, unbiased var},
+ *   ++num_batches_tracked (may be NULL).  Outputs [N]: mean, invstd (float64) and the folded fp32 affine
+ *   scale = gamma*invstd, shift = beta - mean*scale that the next kernel applies in its operand prologue. */
+S2C_API int s2c_bn_finalize(const double *sum, const double *sumsq, long long R, int N, const float *gamma,
+                            const float *beta, double eps, double momentum, int use_batch_stats, int update_running,
+                            float *running_mean, float *running_var, long long *num_batches_tracked, double *mean,
+                            double *invstd, float *scale, float *shift, void *stream);
+
+/* bn_backward_coeffs -- BatchNorm backward of one layer as the per-channel affine map dY = a*g + b*y + c
+ *   (batch statistics; b = c = 0 in evaluation mode) plus grad_gamma = sum g*xhat and grad_beta = sum g, from the
+ *   float64 sums (sum g, sum g*y) a backward GEMM / pooling epilogue produced.  All arrays [N]. */
+S2C_API int s2c_bn_backward_coeffs(const double *sum_g, const double *sum_gy, const double *mean,
+                                   const double *invstd, const float *gamma, long long R, int N, int batch_stats,
+                                   float *grad_gamma, float *grad_beta, float *a, float *b, float *c, void *stream);
+
+/* group_rows_grad -- gradient of grouped rows w.r.t. a point-major tensor (group_points_grad_kernel,
+ *   group_points_gpu.cu:43-64, on the channels-last layout of the fused path):
+ *   rows (B, T, ld) gradient of the grouped tensor, channels [c0, c0+C) wanted; idx (B, T) the neighbour list;
+ *   out (B, n, C) = scale * sum over t with idx[b,t]==k of rows[b,t,c0:c0+C]  (zero-filled here, fp32 atomics --
+ *   one red.global.add.v4.f32 per 4 channels when C is a multiple of 4 and out is 16-byte aligned). */
+S2C_API int s2c_group_rows_grad(const float *rows, long long ld, int c0, int C, const int *idx, int B, long long T,
+                                int n, float scale, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,26 +14,16 @@
 // with coalesced stores -- the (B,M,ns) index tensor and the two grouped tensors of the reference
 // never make a round trip through HBM.
 #include "s2c_common.cuh"
+#include "group_epilogue.cuh"
 
 namespace s2c {
 namespace {
 
 constexpr int kWarps = 8;        // warps per CTA
-constexpr int kCPW = 4;          // centres per warp
+                                 // centres per warp: template parameter CPW (4 when the grid is large enough, else 2 / 1)
 constexpr int kTile = 2048;      // points per shared-memory tile
-constexpr int kCentresPerCta = kWarps * kCPW;
 
-struct GroupArgs {
-  const float *features;  // may be null (C == 0)
-  float *grouped;         // may be null (query only)
-  int C;
-  long long feat_point_stride, feat_chan_stride, feat_scene_stride;
-  int out_layout;  // 0: (B,3+C,M,ns)  1: (B,M,ns,3+C)  2: (B,M,ns,Cp), Cp = 3+C rounded up to 4, zero padded
-  float inv_radius;  // 1 if !normalize_xyz
-  int normalize;
-};
-
-template <bool GROUP>
+template <bool GROUP, int kCPW>
 __global__ void __launch_bounds__(kWarps * 32)
 ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz, int n, int M, float radius,
                   int nsample, int *__restrict__ idx, int *__restrict__ cnt_out, GroupArgs ga) {
@@ -41,6 +31,7 @@ ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ x
   float *sx = reinterpret_cast<float *>(smem_raw);
   float *sy = sx + kTile;
   float *sz = sy + kTile;
+  constexpr int kCentresPerCta = kWarps * kCPW;
   int *sidx = reinterpret_cast<int *>(sz + kTile);  // [kCentresPerCta][nsample]
 
   const int b = blockIdx.y;
@@ -117,64 +108,33 @@ ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ x
     }
     if (cnt_out && lane == 0) cnt_out[(size_t)b * M + j] = c;
     if (GROUP) {
-      const int CC = 3 + ga.C;
       const float *f = ga.features ? ga.features + (size_t)b * ga.feat_scene_stride : nullptr;
-      const float ccx = cx[q], ccy = cy[q], ccz = cz[q];
-      if (ga.out_layout == 0) {
-        // (B,3+C,M,ns): lanes run over s, one 4*ns-byte contiguous run per channel
-        float *o = ga.grouped + (((size_t)b * CC) * M + j) * nsample;
-        const size_t cstride = (size_t)M * nsample;
-        for (int s = lane; s < nsample; s += 32) {
-          const int k = li[s];
-          float rx = __fsub_rn(xyz[(size_t)k * 3 + 0], ccx);
-          float ry = __fsub_rn(xyz[(size_t)k * 3 + 1], ccy);
-          float rz = __fsub_rn(xyz[(size_t)k * 3 + 2], ccz);
-          if (ga.normalize) {
-            rx = __fmul_rn(rx, ga.inv_radius); ry = __fmul_rn(ry, ga.inv_radius); rz = __fmul_rn(rz, ga.inv_radius);
-          }
-          st_stream(o + s, rx);
-          st_stream(o + cstride + s, ry);
-          st_stream(o + 2 * cstride + s, rz);
-          const float *fk = f + (size_t)k * ga.feat_point_stride;
-          for (int ch = 0; ch < ga.C; ++ch)
-            st_stream(o + (size_t)(3 + ch) * cstride + s, __ldg(fk + (size_t)ch * ga.feat_chan_stride));
-        }
-      } else {
-        // (B,M,ns,Cp): the centre's whole block is one contiguous run of ns*Cp floats (Cp = 3+C, or padded to 4)
-        const int CP = ga.out_layout == 2 ? ((CC + 3) & ~3) : CC;
-        float *o = ga.grouped + ((size_t)b * M + j) * (size_t)nsample * CP;
-        const int total = nsample * CP;
-        for (int t = lane; t < total; t += 32) {
-          const int s = t / CP, ch = t - s * CP;
-          const int k = li[s];
-          float v;
-          if (ch >= CC) {
-            v = 0.f;
-          } else if (ch < 3) {
-            v = __fsub_rn(xyz[(size_t)k * 3 + ch], ch == 0 ? ccx : (ch == 1 ? ccy : ccz));
-            if (ga.normalize) v = __fmul_rn(v, ga.inv_radius);
-          } else {
-            v = __ldg(f + (size_t)k * ga.feat_point_stride + (size_t)(ch - 3) * ga.feat_chan_stride);
-          }
-          st_stream(o + t, v);
-        }
-      }
+      group_epilogue(ga, xyz, f, li, nsample, lane, cx[q], cy[q], cz[q], b, M, j);
     }
   }
 }
 
-size_t smem_bytes(int nsample) { return (size_t)3 * kTile * sizeof(float) + (size_t)kCentresPerCta * nsample * sizeof(int); }
+template <bool GROUP, int CPW>
+int launch_cpw(const float *new_xyz, const float *xyz, int B, int n, int M, float radius, int nsample, int *idx,
+               int *cnt, const GroupArgs &ga, cudaStream_t st) {
+  const size_t smem = (size_t)3 * kTile * sizeof(float) + (size_t)kWarps * CPW * nsample * sizeof(int);
+  auto kern = ball_query_kernel<GROUP, CPW>;
+  S2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ball_query smem attr");
+  dim3 grid((unsigned)ceil_div(M, kWarps * CPW), (unsigned)B);
+  kern<<<grid, kWarps * 32, smem, st>>>(new_xyz, xyz, n, M, radius, nsample, idx, cnt, ga);
+  S2C_CHECK_LAUNCH("ball_query launch");
+  return S2C_OK;
+}
 
 template <bool GROUP>
 int launch(const float *new_xyz, const float *xyz, int B, int n, int M, float radius, int nsample, int *idx,
            int *cnt, const GroupArgs &ga, cudaStream_t st) {
-  const size_t smem = smem_bytes(nsample);
-  auto kern = ball_query_kernel<GROUP>;
-  S2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ball_query smem attr");
-  dim3 grid((unsigned)ceil_div(M, kCentresPerCta), (unsigned)B);
-  kern<<<grid, kWarps * 32, smem, st>>>(new_xyz, xyz, n, M, radius, nsample, idx, cnt, ga);
-  S2C_CHECK_LAUNCH("ball_query launch");
-  return S2C_OK;
+  // 4 centres per warp amortise the shared-memory reads of the scan; with few centres (SA3/SA4, vote aggregation)
+  // fewer centres per warp keep at least ~2 CTAs per SM busy in the store-bound gather epilogue
+  const long long want = 2LL * kNumSMs;
+  if ((long long)ceil_div(M, kWarps * 4) * B >= want) return launch_cpw<GROUP, 4>(new_xyz, xyz, B, n, M, radius, nsample, idx, cnt, ga, st);
+  if ((long long)ceil_div(M, kWarps * 2) * B >= want) return launch_cpw<GROUP, 2>(new_xyz, xyz, B, n, M, radius, nsample, idx, cnt, ga, st);
+  return launch_cpw<GROUP, 1>(new_xyz, xyz, B, n, M, radius, nsample, idx, cnt, ga, st);
 }
 
 }  // namespace

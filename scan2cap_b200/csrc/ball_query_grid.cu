@@ -10,6 +10,8 @@
 //      contiguous range of the sorted array), test ONLY those candidates with exactly the reference's fp32
 //      expression, and set bit k of a per-warp bitmap for every hit; the first nsample set bits of the bitmap, read in
 //      index order, are the reference's neighbour list.  Padding / empty-ball rules as in the reference.
+//      The bitmap is two-level (a summary word per 32 bitmap words) so the ordered extraction touches only the
+//      non-empty words (~#hits) instead of all n/32; the 9 runs are scanned as ONE flattened candidate range.
 //   The gather epilogue (centre subtraction, 1/r, concat, channels-last output) is the one of ball_query.cu.
 // Candidate count per centre drops from n (40 000) to ~200, so the kernel becomes a gather bound by the bytes it
 // writes instead of by distance arithmetic.
@@ -19,6 +21,7 @@
 // argument is < 1e-2 of a cell, far below the 1e-3*r/cs... margin built into the cell edge: a hit can never be more
 // than one cell away from its centre's cell in any axis.
 #include "s2c_common.cuh"
+#include "group_epilogue.cuh"
 
 namespace s2c {
 namespace {
@@ -59,7 +62,7 @@ grid_build_kernel(const float *__restrict__ xyz, int n, float radius, GridParams
                   int *__restrict__ cursor /* (B, kMaxCells) scratch */, float *__restrict__ bbox /* (B, CL, 6) scratch */) {
   __shared__ float s_red[6][32];
   __shared__ GridParams gp;
-  __shared__ int s_scan[kBuildThreads];
+  __shared__ int s_scan[kBuildThreads / 32];
   const int b = blockIdx.x / kBuildCluster, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rank = (int)cluster_rank();
   const int gtid = rank * kBuildThreads + tid, gthreads = kBuildCluster * kBuildThreads;
@@ -132,26 +135,44 @@ grid_build_kernel(const float *__restrict__ xyz, int n, float radius, GridParams
     atomicAdd(&cursor[(iz * gp.n[1] + iy) * gp.n[0] + ix], 1);
   }
   cluster_sync_all();
-  // ---- phase 4: exclusive scan of the counts (CTA 0; each thread owns a contiguous slice of cells)
+  // ---- phase 4: exclusive scan of the counts (CTA 0).  Each warp owns one contiguous chunk of cells and walks it
+  //      32 cells at a time (coalesced) with a running carry; the 32 chunk totals are scanned by warp 0 and the chunk
+  //      base is added in a second, cache-hot pass that also initialises the scatter cursors.
   if (rank == 0) {
-    const int per = (ncell + kBuildThreads - 1) / kBuildThreads;
-    const int c0 = tid * per, c1 = min(c0 + per, ncell);
-    int local = 0;
-    for (int c = c0; c < c1; ++c) local += cursor[c];
-    s_scan[tid] = local;
-    __syncthreads();
-    for (int o = 1; o < kBuildThreads; o <<= 1) {  // Hillis-Steele inclusive scan over the 1024 slice totals
-      const int v = tid >= o ? s_scan[tid - o] : 0;
-      __syncthreads();
-      s_scan[tid] += v;
-      __syncthreads();
+    constexpr int kW = kBuildThreads / 32;
+    const int chunk = ((ncell + kW - 1) / kW + 31) & ~31;
+    const int c0 = warp * chunk, c1 = min(c0 + chunk, ncell);
+    int carry = 0;
+    for (int cb = c0; cb < c1; cb += 32) {
+      const int c = cb + lane;
+      const int cnt = c < c1 ? cursor[c] : 0;
+      int inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+      }
+      if (c < c1) cell_start[c] = carry + inc - cnt;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
     }
-    int run = s_scan[tid] - local;
-    for (int c = c0; c < c1; ++c) {
-      const int cnt = cursor[c];
-      cell_start[c] = run;
-      cursor[c] = run;  // becomes the write cursor of the scatter
-      run += cnt;
+    if (lane == 0) s_scan[warp] = carry;
+    __syncthreads();
+    if (warp == 0) {
+      const int tot = s_scan[lane];
+      int inc = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+      }
+      s_scan[lane] = inc - tot;
+    }
+    __syncthreads();
+    const int base = s_scan[warp];
+    for (int c = c0 + lane; c < c1; c += 32) {
+      const int v = cell_start[c] + base;
+      cell_start[c] = v;
+      cursor[c] = v;  // becomes the write cursor of the scatter
     }
     if (tid == 0) cell_start[ncell] = n;
   }
@@ -169,22 +190,21 @@ grid_build_kernel(const float *__restrict__ xyz, int n, float radius, GridParams
 }
 
 // ---- 2. query (+ gather) ---------------------------------------------------------------------------------
-struct GroupArgs {
-  const float *features; float *grouped; int C;
-  long long feat_point_stride, feat_chan_stride, feat_scene_stride;
-  int out_layout; float inv_radius; int normalize;
-};
-
+// Per-warp shared memory: bm[words] hit bitmap | sm[swords] summary (bit w&31 of sm[w>>5] <=> bm[w] != 0) |
+// wl[nsample] ordered list of the first non-empty bitmap words | li[nsample] the neighbour list.
 template <bool GROUP>
 __global__ void __launch_bounds__(256)
 grid_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz, int n, int M, float radius, int nsample,
                   const GridParams *__restrict__ params, const int *__restrict__ cell_start, const float4 *__restrict__ sorted,
-                  int words /* bitmap words per warp */, int *__restrict__ idx, GroupArgs ga) {
-  extern __shared__ unsigned int smem_u[];
+                  int words, int swords, int *__restrict__ idx, GroupArgs ga) {
+  extern __shared__ __align__(16) unsigned int smem_u[];
   const int warps = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned int *bm = smem_u + (size_t)warp * words;
-  int *li = reinterpret_cast<int *>(smem_u + (size_t)warps * words) + (size_t)warp * nsample;
+  const size_t per_warp = (size_t)words + swords + 2 * (size_t)nsample;
+  unsigned int *bm = smem_u + (size_t)warp * per_warp;
+  unsigned int *sm = bm + words;
+  int *wl = reinterpret_cast<int *>(sm + swords);
+  int *li = wl + nsample;
   const int b = blockIdx.y;
   xyz += (size_t)b * n * 3;
   new_xyz += (size_t)b * M * 3;
@@ -192,65 +212,104 @@ grid_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ x
   sorted += (size_t)b * n;
   const GridParams gp = params[b];
   const float radius2 = __fmul_rn(radius, radius);
-  for (int w = lane; w < words; w += 32) bm[w] = 0u;
+  for (int w = lane; w < words + swords; w += 32) bm[w] = 0u;  // bm and sm are adjacent
   __syncwarp();
+  const float *f = (GROUP && ga.features) ? ga.features + (size_t)b * ga.feat_scene_stride : nullptr;
 
   for (int j = blockIdx.x * warps + warp; j < M; j += gridDim.x * warps) {
     const float cx = new_xyz[j * 3 + 0], cy = new_xyz[j * 3 + 1], cz = new_xyz[j * 3 + 2];
     const int ix = cell_coord(cx, gp.lo[0], gp.inv, gp.n[0]);
     const int iy = cell_coord(cy, gp.lo[1], gp.inv, gp.n[1]);
     const int iz = cell_coord(cz, gp.lo[2], gp.inv, gp.n[2]);
-    int hits = 0;
     const int x0 = max(ix - 1, 0), x1 = min(ix + 1, gp.n[0] - 1);
-    if (x0 <= x1) {
-      for (int dz = -1; dz <= 1; ++dz) {
-        const int z = iz + dz;
-        if (z < 0 || z >= gp.n[2]) continue;
-        for (int dy = -1; dy <= 1; ++dy) {
-          const int y = iy + dy;
-          if (y < 0 || y >= gp.n[1]) continue;
-          const int row = (z * gp.n[1] + y) * gp.n[0];
-          const int s = cell_start[row + x0], e = cell_start[row + x1 + 1];  // x-adjacent cells are contiguous
-          for (int t = s + lane; t < e; t += 32) {
-            const float4 p = __ldg(sorted + t);
-            const int k = __float_as_int(p.w);
-            const float d2 = sqdist3(cx, cy, cz, p.x, p.y, p.z);
-            if (d2 < radius2) {
-              atomicOr(&bm[k >> 5], 1u << (k & 31));
-              ++hits;
-            }
-          }
-        }
+    // the 3x3 (z,y) neighbourhood = 9 runs of x-adjacent cells, each one contiguous range of `sorted`:
+    // lane r < 9 fetches run r's bounds, then the 9 ranges are scanned as one flattened candidate range
+    int rs = 0, rl = 0;
+    if (lane < 9 && x0 <= x1) {
+      const int z = iz + lane / 3 - 1, y = iy + lane % 3 - 1;
+      if (z >= 0 && z < gp.n[2] && y >= 0 && y < gp.n[1]) {
+        const int row = (z * gp.n[1] + y) * gp.n[0];
+        rs = __ldg(cell_start + row + x0);
+        rl = __ldg(cell_start + row + x1 + 1) - rs;
       }
     }
-    hits = __reduce_add_sync(0xffffffffu, hits);
-    __syncwarp();
-    // ordered extraction of the first nsample set bits (and clearing of the bitmap)
-    int cnt = 0;
-    if (hits > 0) {
-      for (int w0 = 0; w0 < words; w0 += 32) {
-        const int w = w0 + lane;
-        unsigned int bits = (w < words) ? bm[w] : 0u;
-        if (bits) bm[w] = 0u;
-        if (cnt < nsample) {
-          const int c = __popc(bits);
-          int pre = c;  // inclusive warp scan of the per-lane counts
+    int inc = rl;
 #pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, pre, o);
-            if (lane >= o) pre += v;
-          }
-          int pos = cnt + pre - c;
-          while (bits && pos < nsample) {
-            const int bit = __ffs(bits) - 1;
-            li[pos++] = (w << 5) + bit;
-            bits &= bits - 1;
-          }
-          cnt += __shfl_sync(0xffffffffu, pre, 31);
-        }
-      }
-      cnt = min(cnt, nsample);
+    for (int o = 1; o < 16; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
     }
+    const int total = __shfl_sync(0xffffffffu, inc, 8);
+    const int my_excl = inc - rl, my_adj = rs - my_excl;  // candidate t of run r lives at sorted[t + adj_r]
+    int excl[9], adj[9];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      excl[r] = __shfl_sync(0xffffffffu, my_excl, r);
+      adj[r] = __shfl_sync(0xffffffffu, my_adj, r);
+    }
+#pragma unroll 2
+    for (int t = lane; t < total; t += 32) {
+      int a = adj[0];
+#pragma unroll
+      for (int r = 1; r < 9; ++r) a = t >= excl[r] ? adj[r] : a;  // runs are in increasing t order: the last match wins
+      const float4 p = __ldg(sorted + t + a);
+      const int k = __float_as_int(p.w);
+      const float d2 = sqdist3(cx, cy, cz, p.x, p.y, p.z);
+      if (d2 < radius2) {
+        atomicOr(&bm[k >> 5], 1u << (k & 31));
+        atomicOr(&sm[k >> 10], 1u << ((k >> 5) & 31));
+      }
+    }
+    __syncwarp();
+    // ---- ordered extraction, level 1: the first nsample non-empty bitmap words, in index order (others are cleared)
+    int nw = 0;
+    for (int s0 = 0; s0 < swords; s0 += 32) {
+      const int s = s0 + lane;
+      unsigned int bits = (s < swords) ? sm[s] : 0u;
+      if (!__any_sync(0xffffffffu, bits != 0u)) continue;
+      if (bits) sm[s] = 0u;
+      const int c = __popc(bits);
+      int pre = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += v;
+      }
+      int pos = nw + pre - c;
+      while (bits) {
+        const int w = (s << 5) + __ffs(bits) - 1;
+        bits &= bits - 1;
+        if (pos < nsample) wl[pos] = w; else bm[w] = 0u;  // words beyond the first nsample cannot contribute
+        ++pos;
+      }
+      nw += __shfl_sync(0xffffffffu, pre, 31);
+    }
+    nw = min(nw, nsample);
+    __syncwarp();
+    // ---- level 2: the first nsample set bits of those words
+    int cnt = 0;
+    for (int i0 = 0; i0 < nw; i0 += 32) {
+      const int i = i0 + lane;
+      const int w = i < nw ? wl[i] : 0;
+      unsigned int bits = i < nw ? bm[w] : 0u;
+      if (i < nw) bm[w] = 0u;
+      if (cnt < nsample) {
+        const int c = __popc(bits);
+        int pre = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, pre, o);
+          if (lane >= o) pre += v;
+        }
+        int pos = cnt + pre - c;
+        while (bits && pos < nsample) {
+          li[pos++] = (w << 5) + __ffs(bits) - 1;
+          bits &= bits - 1;
+        }
+        cnt += __shfl_sync(0xffffffffu, pre, 31);
+      }
+    }
+    cnt = min(cnt, nsample);
     __syncwarp();
     const int first = cnt > 0 ? li[0] : 0;
     __syncwarp();
@@ -260,40 +319,7 @@ grid_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ x
       int *o = idx + ((size_t)b * M + j) * nsample;
       for (int s = lane; s < nsample; s += 32) o[s] = li[s];
     }
-    if (GROUP) {
-      const int CC = 3 + ga.C;
-      const float *f = ga.features ? ga.features + (size_t)b * ga.feat_scene_stride : nullptr;
-      if (ga.out_layout == 0) {
-        float *o = ga.grouped + (((size_t)b * CC) * M + j) * nsample;
-        const size_t cstride = (size_t)M * nsample;
-        for (int s = lane; s < nsample; s += 32) {
-          const int k = li[s];
-          float rx = __fsub_rn(xyz[(size_t)k * 3 + 0], cx), ry = __fsub_rn(xyz[(size_t)k * 3 + 1], cy), rz = __fsub_rn(xyz[(size_t)k * 3 + 2], cz);
-          if (ga.normalize) { rx = __fmul_rn(rx, ga.inv_radius); ry = __fmul_rn(ry, ga.inv_radius); rz = __fmul_rn(rz, ga.inv_radius); }
-          st_stream(o + s, rx); st_stream(o + cstride + s, ry); st_stream(o + 2 * cstride + s, rz);
-          const float *fk = f + (size_t)k * ga.feat_point_stride;
-          for (int ch = 0; ch < ga.C; ++ch) st_stream(o + (size_t)(3 + ch) * cstride + s, __ldg(fk + (size_t)ch * ga.feat_chan_stride));
-        }
-      } else {
-        const int CP = ga.out_layout == 2 ? ((CC + 3) & ~3) : CC;
-        float *o = ga.grouped + ((size_t)b * M + j) * (size_t)nsample * CP;
-        const int total = nsample * CP;
-        for (int t = lane; t < total; t += 32) {
-          const int s = t / CP, ch = t - s * CP;
-          const int k = li[s];
-          float v;
-          if (ch >= CC) {
-            v = 0.f;
-          } else if (ch < 3) {
-            v = __fsub_rn(xyz[(size_t)k * 3 + ch], ch == 0 ? cx : (ch == 1 ? cy : cz));
-            if (ga.normalize) v = __fmul_rn(v, ga.inv_radius);
-          } else {
-            v = __ldg(f + (size_t)k * ga.feat_point_stride + (size_t)(ch - 3) * ga.feat_chan_stride);
-          }
-          st_stream(o + t, v);
-        }
-      }
-    }
+    if (GROUP) group_epilogue(ga, xyz, f, li, nsample, lane, cx, cy, cz, b, M, j);
     __syncwarp();
   }
 }
@@ -349,19 +375,20 @@ extern "C" int s2c_query_and_group_grid(const float *xyz, const float *new_xyz, 
     ga.feat_point_stride = feat_stride; ga.feat_chan_stride = 1; ga.feat_scene_stride = (long long)n * feat_stride;
   }
   ga.out_layout = out_layout; ga.normalize = normalize_xyz ? 1 : 0; ga.inv_radius = normalize_xyz ? (1.0f / radius) : 1.0f;
-  const int words = (n + 31) / 32;
+  const int words = (n + 31) / 32, swords = (words + 31) / 32;
+  const size_t per_warp = (size_t)(words + swords + 2 * nsample) * 4;
   int warps = 8;
-  while (warps > 1 && (size_t)warps * (words + nsample) * 4 > 200 * 1024) warps >>= 1;
-  const size_t smem = (size_t)warps * (words + nsample) * 4;
+  while (warps > 1 && (size_t)warps * per_warp > 200 * 1024) warps >>= 1;
+  const size_t smem = (size_t)warps * per_warp;
   S2C_REQUIRE(smem <= 227 * 1024, "query_and_group_grid: n=%d too large for the per-warp bitmap", n);
   const int ctas_x = min(ceil_div(M, warps), 4 * kNumSMs / max(B, 1) + 1);
   dim3 grid((unsigned)ctas_x, (unsigned)B);
   if (grouped) {
     S2C_CUDA(cudaFuncSetAttribute(grid_query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "grid_query smem");
-    grid_query_kernel<true><<<grid, warps * 32, smem, st>>>(new_xyz, xyz, n, M, radius, nsample, params, cell_start, sorted, words, idx, ga);
+    grid_query_kernel<true><<<grid, warps * 32, smem, st>>>(new_xyz, xyz, n, M, radius, nsample, params, cell_start, sorted, words, swords, idx, ga);
   } else {
     S2C_CUDA(cudaFuncSetAttribute(grid_query_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "grid_query smem");
-    grid_query_kernel<false><<<grid, warps * 32, smem, st>>>(new_xyz, xyz, n, M, radius, nsample, params, cell_start, sorted, words, idx, ga);
+    grid_query_kernel<false><<<grid, warps * 32, smem, st>>>(new_xyz, xyz, n, M, radius, nsample, params, cell_start, sorted, words, swords, idx, ga);
   }
   S2C_CHECK_LAUNCH("grid_query");
   return S2C_OK;

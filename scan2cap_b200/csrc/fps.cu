@@ -331,6 +331,8 @@ extern "C" int s2c_furthest_point_sampling(const float *xyz, int B, int N, int m
     if (ppt <= 8) S2C_FPS(8, 1024, CL);     \
     if (ppt <= 10) S2C_FPS(10, 1024, CL);   \
     if (ppt <= 12) S2C_FPS(12, 1024, CL);   \
+    if (CL == 16 && ppt <= 13) S2C_FPS(13, 1024, CL); \
+    if (CL == 16 && ppt <= 16) S2C_FPS(16, 1024, CL); \
   }
   S2C_FPS_CL(2)
   S2C_FPS_CL(4)
@@ -346,7 +348,7 @@ extern "C" int s2c_furthest_point_sampling(const float *xyz, int B, int N, int m
       S2C_FPS(12, 1024, 16);
     }
   }
-  set_error("furthest_point_sampling: N=%d exceeds the register-resident capacity (196608 points/scene)", N);
+  set_error("furthest_point_sampling: N=%d exceeds the register-resident capacity (262144 points/scene)", N);
   return S2C_ERR_UNSUPPORTED;
 #undef S2C_FPS
 #undef S2C_FPS_CL

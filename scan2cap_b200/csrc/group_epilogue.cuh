@@ -1,0 +1,102 @@
+// Gather epilogue shared by the two fused query+group kernels (ball_query.cu: brute-force scan for small point sets,
+// ball_query_grid.cu: uniform-grid pre-filter).  Given one centre's neighbour list (in shared memory) a warp writes
+// that centre's block of the grouped tensor:
+//     cat([ (xyz[idx] - centre) * (1/r if normalize), features[idx] ])          (QueryAndGroup.forward,
+//                                                         lib/pointnet2/pointnet2_utils.py:317-376)
+// in one of three layouts.  Arithmetic is bit-identical to the reference's: fp32 subtract, then a multiply by the
+// fp32 reciprocal of the radius (torch's tensor / python-scalar on CUDA multiplies by the reciprocal).
+#pragma once
+#include "s2c_common.cuh"
+
+namespace s2c {
+
+struct GroupArgs {
+  const float *features;  // may be null (C == 0)
+  float *grouped;         // may be null (query only)
+  int C;
+  long long feat_point_stride, feat_chan_stride, feat_scene_stride;
+  int out_layout;  // 0: (B,3+C,M,ns)  1: (B,M,ns,3+C)  2: (B,M,ns,Cp), Cp = 3+C rounded up to 4, zero padded
+  float inv_radius;  // 1 if !normalize_xyz
+  int normalize;
+};
+
+// li: this centre's nsample neighbour indices (shared memory, already padded); (cx,cy,cz): the centre;
+// xyz / f: this scene's coordinates / features; bMj = b*M + j.
+__device__ __forceinline__ void group_epilogue(const GroupArgs &ga, const float *__restrict__ xyz,
+                                               const float *__restrict__ f, const int *li, int nsample, int lane,
+                                               float cx, float cy, float cz, int b, int M, int j) {
+  const int CC = 3 + ga.C;
+  if (ga.out_layout == 0) {
+    // (B,3+C,M,ns): lanes run over s, one 4*ns-byte contiguous run per channel
+    float *o = ga.grouped + (((size_t)b * CC) * M + j) * nsample;
+    const size_t cstride = (size_t)M * nsample;
+    for (int s = lane; s < nsample; s += 32) {
+      const int k = li[s];
+      float rx = __fsub_rn(xyz[(size_t)k * 3 + 0], cx);
+      float ry = __fsub_rn(xyz[(size_t)k * 3 + 1], cy);
+      float rz = __fsub_rn(xyz[(size_t)k * 3 + 2], cz);
+      if (ga.normalize) {
+        rx = __fmul_rn(rx, ga.inv_radius); ry = __fmul_rn(ry, ga.inv_radius); rz = __fmul_rn(rz, ga.inv_radius);
+      }
+      st_stream(o + s, rx);
+      st_stream(o + cstride + s, ry);
+      st_stream(o + 2 * cstride + s, rz);
+      const float *fk = f + (size_t)k * ga.feat_point_stride;
+      for (int ch = 0; ch < ga.C; ++ch)
+        st_stream(o + (size_t)(3 + ch) * cstride + s, __ldg(fk + (size_t)ch * ga.feat_chan_stride));
+    }
+    return;
+  }
+  // (B,M,ns,Cp): the centre's whole block is one contiguous run of ns*Cp floats (Cp = 3+C, or padded to 4)
+  const int CP = ga.out_layout == 2 ? ((CC + 3) & ~3) : CC;
+  float *o = ga.grouped + ((size_t)b * M + j) * (size_t)nsample * CP;
+  if (ga.out_layout == 2 && (ga.feat_chan_stride == 1 || ga.C == 0)) {
+    // 16-byte stores: slot q = (sample s, channels 4w..4w+3).  Slot 0 of a sample holds the three offsets and the
+    // first feature; the feature run of a point is read with 4-byte loads (it starts 3 floats into a 16-byte
+    // group), consecutive lanes covering consecutive 16-byte pieces of the same point's feature vector.
+    const int W = CP >> 2;
+    const int total = nsample * W;
+    const float invW = 1.0f / (float)W;
+    for (int q = lane; q < total; q += 32) {
+      const int s = __float2int_rz(((float)q + 0.5f) * invW);  // q / W (exact: |(q+.5)/W - integer| >= .5/W)
+      const int w = q - s * W;
+      const int k = li[s];
+      float4 v;
+      if (w == 0) {
+        v.x = __fsub_rn(xyz[(size_t)k * 3 + 0], cx);
+        v.y = __fsub_rn(xyz[(size_t)k * 3 + 1], cy);
+        v.z = __fsub_rn(xyz[(size_t)k * 3 + 2], cz);
+        if (ga.normalize) {
+          v.x = __fmul_rn(v.x, ga.inv_radius); v.y = __fmul_rn(v.y, ga.inv_radius); v.z = __fmul_rn(v.z, ga.inv_radius);
+        }
+        v.w = ga.C > 0 ? __ldg(f + (size_t)k * ga.feat_point_stride) : 0.f;
+      } else {
+        const int c = 4 * w - 3;  // first feature channel of this slot
+        const float *fk = f + (size_t)k * ga.feat_point_stride + c;
+        v.x = c + 0 < ga.C ? __ldg(fk + 0) : 0.f;
+        v.y = c + 1 < ga.C ? __ldg(fk + 1) : 0.f;
+        v.z = c + 2 < ga.C ? __ldg(fk + 2) : 0.f;
+        v.w = c + 3 < ga.C ? __ldg(fk + 3) : 0.f;
+      }
+      st_stream4(o + 4 * (size_t)q, v);
+    }
+    return;
+  }
+  const int total = nsample * CP;
+  for (int t = lane; t < total; t += 32) {
+    const int s = t / CP, ch = t - s * CP;
+    const int k = li[s];
+    float v;
+    if (ch >= CC) {
+      v = 0.f;
+    } else if (ch < 3) {
+      v = __fsub_rn(xyz[(size_t)k * 3 + ch], ch == 0 ? cx : (ch == 1 ? cy : cz));
+      if (ga.normalize) v = __fmul_rn(v, ga.inv_radius);
+    } else {
+      v = __ldg(f + (size_t)k * ga.feat_point_stride + (size_t)(ch - 3) * ga.feat_chan_stride);
+    }
+    st_stream(o + t, v);
+  }
+}
+
+}  // namespace s2c

@@ -109,3 +109,46 @@ def mlp_layer_bwd_weight(dY, X, P, xs=None, xh=None, a=None, b=None, c=None, Y=N
              ptr(a), ptr(b), ptr(c), X.data_ptr(), X.stride(0), ptr(xs), ptr(xh), R, C, int(P), dW.data_ptr(), P,
              _stream(dY))
     return dW
+
+
+def bn_finalize(s1, s2, R, bn, training):
+    """One launch: BatchNorm statistics of a layer -> (mean f64, invstd f64, scale f32, shift f32) [N]; updates the
+    module's running statistics in training mode (s1/s2 = float64 column sums; None -> running statistics)."""
+    N = bn.weight.shape[0]
+    dev = bn.weight.device
+    use_batch = bool(training or not bn.track_running_stats)
+    update = bool(training and bn.track_running_stats)
+    f64 = torch.empty((2, N), dtype=torch.float64, device=dev)
+    f32 = torch.empty((2, N), dtype=torch.float32, device=dev)
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    mom = bn.momentum if bn.momentum is not None else 0.0
+    with _guard(bn.weight):
+        call("s2c_bn_finalize", ptr(s1) if use_batch else None, ptr(s2) if use_batch else None, int(R), N,
+             bn.weight.data_ptr(), bn.bias.data_ptr(), float(bn.eps), float(mom), int(use_batch), int(update),
+             ptr(bn.running_mean), ptr(bn.running_var), ptr(bn.num_batches_tracked) if update else None,
+             f64[0].data_ptr(), f64[1].data_ptr(), f32[0].data_ptr(), f32[1].data_ptr(), _stream(bn.weight))
+    return f64[0], f64[1], f32[0], f32[1]
+
+
+def bn_backward_coeffs(sum_g, sum_gy, mean, invstd, gamma, R, batch_stats):
+    """One launch: -> (grad_gamma, grad_beta, a, b, c) fp32 [N] with dY = a*g + b*y + c."""
+    N = gamma.shape[0]
+    out = torch.empty((5, N), dtype=torch.float32, device=gamma.device)
+    with _guard(gamma):
+        call("s2c_bn_backward_coeffs", sum_g.data_ptr(), sum_gy.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+             gamma.data_ptr(), int(R), N, int(bool(batch_stats)), out[0].data_ptr(), out[1].data_ptr(),
+             out[2].data_ptr(), out[3].data_ptr(), out[4].data_ptr(), _stream(gamma))
+    return out[0], out[1], out[2], out[3], out[4]
+
+
+def group_rows_grad(rows, c0, C, idx, n, scale=1.0):
+    """rows (B, T, ld) channels-last gradient of a grouped tensor, idx (B, ...) with T entries per scene ->
+    (B, n, C) point-major gradient of the gathered tensor (scatter-add of channels [c0, c0+C), times scale)."""
+    B, T, ld = rows.shape
+    assert rows.is_cuda and rows.dtype == torch.float32 and rows.is_contiguous() and idx.dtype == torch.int32
+    assert idx.is_contiguous() and idx.numel() == B * T
+    out = torch.empty((B, n, C), dtype=torch.float32, device=rows.device)
+    with _guard(rows):
+        call("s2c_group_rows_grad", rows.data_ptr(), ld, int(c0), int(C), idx.data_ptr(), B, T, int(n), float(scale),
+             out.data_ptr(), _stream(rows))
+    return out

@@ -19,25 +19,9 @@ from . import _ext_mlp
 
 
 def _bn_coefficients(s1, s2, R, bn, training):
-    """mean / invstd (float64) of this layer's BatchNorm and the folded fp32 (scale, shift); updates running stats."""
-    if training or not bn.track_running_stats:
-        mean = s1 / R
-        var = (s2 / R - mean * mean).clamp_min_(0.0)
-        if training and bn.track_running_stats:
-            with torch.no_grad():
-                mom = bn.momentum if bn.momentum is not None else 0.0
-                unbiased = var * (float(R) / max(R - 1, 1))
-                bn.running_mean.mul_(1 - mom).add_(mean.to(bn.running_mean.dtype), alpha=mom)
-                bn.running_var.mul_(1 - mom).add_(unbiased.to(bn.running_var.dtype), alpha=mom)
-                if bn.num_batches_tracked is not None:
-                    bn.num_batches_tracked.add_(1)
-    else:
-        mean = bn.running_mean.double()
-        var = bn.running_var.double()
-    invstd = torch.rsqrt(var + bn.eps)
-    scale = bn.weight.double() * invstd
-    shift = bn.bias.double() - mean * scale
-    return mean, invstd, scale.float(), shift.float()
+    """mean / invstd (float64) of this layer's BatchNorm and the folded fp32 (scale, shift); updates running stats
+    (one s2c_bn_finalize launch; semantics of torch's batch_norm: unbiased running variance, momentum blend)."""
+    return _ext_mlp.bn_finalize(s1, s2, R, bn, training)
 
 
 class _FusedMLPPool(Function):
@@ -85,17 +69,9 @@ class _FusedMLPPool(Function):
             """BatchNorm backward of layer l as dY = a*g + b*y + c; also its gamma / beta gradients."""
             mean, invstd, _, _ = coefs[l]
             gamma = params[3 * l + 1]
-            sum_gx = (sum_gy - mean * sum_g) * invstd             # sum of g * xhat
-            grads[3 * l + 1] = sum_gx.to(gamma.dtype)
-            grads[3 * l + 2] = sum_g.to(gamma.dtype)
-            a = gamma.double() * invstd
-            if batch_stats[l]:
-                b = -a * invstd * (sum_gx / R)
-                c = -a * (sum_g / R) - b * mean
-            else:
-                b = torch.zeros_like(a)
-                c = torch.zeros_like(a)
-            return a.float(), b.float(), c.float()
+            grads[3 * l + 1], grads[3 * l + 2], a, b, c = _ext_mlp.bn_backward_coeffs(
+                sum_g, sum_gy, mean, invstd, gamma, R, batch_stats[l])
+            return a, b, c
 
         # last layer: its masked gradient is the pooled gradient at the arg-max sample -> sums straight from dpool
         l = L - 1

@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 from torch.autograd import Function
 
-from . import _ext
+from . import _ext, _ext_mlp
 
 
 class FurthestPointSampling(Function):
@@ -127,6 +127,21 @@ class _FusedQueryAndGroup(Function):
     def backward(ctx, grad, _grad_idx):
         idx, n = ctx.idx, ctx.n
         g_xyz = g_new = g_feat = None
+        B, Cp, M, ns = grad.shape
+        rows = grad.permute(0, 2, 3, 1)  # channels-last storage (what the fused MLP backward hands back) -> (B,M,ns,Cp)
+        if rows.is_contiguous() and grad.dtype == torch.float32:
+            # one scatter-add launch per gathered tensor, straight from the channels-last rows into point-major
+            # gradients: no (B,C,M,ns) re-layout copies, contiguous (vectorised) atomics per neighbour
+            rows = rows.reshape(B, M * ns, Cp)
+            if ctx.needs_input_grad[0]:
+                g_xyz = _ext_mlp.group_rows_grad(rows, 0, 3, idx, n, ctx.scale)  # (B,n,3)
+            if ctx.needs_input_grad[1]:
+                g_new = -(grad[:, :3].sum(-1) * ctx.scale).transpose(1, 2)
+            if ctx.has_feat and ctx.needs_input_grad[2]:
+                g_feat = _ext_mlp.group_rows_grad(rows, 3, ctx.C, idx, n)  # (B,n,C)
+                if not ctx.feat_point_major:
+                    g_feat = g_feat.transpose(1, 2)
+            return g_xyz, g_new, g_feat, None, None, None, None, None, None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             gx = grad[:, :3] * ctx.scale  # (B,3,M,ns)
             if ctx.needs_input_grad[0]:

@@ -107,3 +107,35 @@ def test_mlp_layer_bwd_weight_matches_float64(R, C, P, ldx, affine, xpro):
     torch.cuda.synchronize()
     err = float((got.double() - want).abs().max() / want.abs().max())
     assert err < 2e-5, "wgrad error %g" % err
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("training", [True, False])
+def test_bn_coefficient_kernels_match_torch_batchnorm(training):
+    """s2c_bn_finalize / s2c_bn_backward_coeffs vs nn.BatchNorm1d (forward, running statistics, backward)."""
+    from scan2cap_b200.lib.pointnet2 import _ext_mlp
+    torch.manual_seed(0)
+    R, N = 5000, 96
+    y = (torch.randn(R, N, device="cuda") * 3 + 1.5).requires_grad_(True)
+    bn_ref = torch.nn.BatchNorm1d(N).cuda()
+    bn = torch.nn.BatchNorm1d(N).cuda()
+    with torch.no_grad():
+        bn_ref.weight.uniform_(0.5, 1.5); bn_ref.bias.uniform_(-1, 1)
+        bn_ref.running_mean.uniform_(-1, 1); bn_ref.running_var.uniform_(0.5, 2)
+    bn.load_state_dict(bn_ref.state_dict())
+    bn_ref.train(training); bn.train(training)
+    out_ref = bn_ref(y)
+    g = torch.randn_like(out_ref)
+    out_ref.backward(g)
+    yd = y.detach().double()
+    mean, invstd, scale, shift = _ext_mlp.bn_finalize(yd.sum(0), (yd * yd).sum(0), R, bn, training)
+    torch.testing.assert_close(torch.addcmul(shift, y.detach(), scale), out_ref.detach(), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(bn.running_mean, bn_ref.running_mean, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(bn.running_var, bn_ref.running_var, rtol=1e-6, atol=1e-6)
+    assert int(bn.num_batches_tracked) == int(bn_ref.num_batches_tracked)
+    gd = g.double()
+    gg, gb, a, b, c = _ext_mlp.bn_backward_coeffs(gd.sum(0), (gd * yd).sum(0), mean, invstd, bn.weight, R, training)
+    torch.testing.assert_close(gg, bn_ref.weight.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(gb, bn_ref.bias.grad, rtol=1e-4, atol=1e-4)
+    dy = a * g + b * y.detach() + c
+    torch.testing.assert_close(dy, y.grad, rtol=1e-4, atol=1e-5)

@@ -89,9 +89,10 @@ def test_ball_query_sa_shapes(n, M, r, ns, ext, oracle, ref_ext):
 
 @pytest.mark.parametrize("feat_pm", [False, True])
 @pytest.mark.parametrize("cl", [False, True])
-@pytest.mark.parametrize("C,normalize", [(0, True), (1, True), (4, False), (37, True)])
-def test_query_and_group_fused(feat_pm, cl, C, normalize, ext, oracle):
-    n, M, r, ns = 3000, 200, 0.3, 32
+@pytest.mark.parametrize("C,normalize", [(0, True), (1, True), (4, False), (37, True), (128, True)])
+@pytest.mark.parametrize("n", [3000, 6000])  # below / above S2C_BALL_GRID_MIN: brute-force scan / uniform-grid kernels
+def test_query_and_group_fused(feat_pm, cl, C, normalize, n, ext, oracle):
+    M, r, ns = 200, 0.3, 32
     pc, _ = synthetic.make_point_clouds(2, n, use_height=False, seed=11)
     xyz = pc[..., :3].copy()
     rng = np.random.default_rng(5)
@@ -204,6 +205,33 @@ def test_large_group_and_grad_sa1_shape(ext, oracle):
     g = rng.standard_normal((B, C, M, ns)).astype(np.float32)
     np.testing.assert_allclose(N(ext.group_points_grad(T(g), T(idx), n)), oracle.group_points_grad(g, idx, n),
                                rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("n,M,r,ns", [(200000, 2048, 0.09, 64), (120000, 1500, 0.12, 16)])
+def test_sweep_sizes_fps_and_ball_query(n, M, r, ns, ext, oracle):
+    """BASELINE.json configs[4] upper end: N up to 200 000 points per scene (16-CTA clusters, spilled variants)."""
+    pc, _ = synthetic.make_point_clouds(1, n, use_height=False, seed=3)
+    xyz = pc[..., :3].copy()
+    idx, new_xyz = ext.furthest_point_sampling_with_xyz(T(xyz), M)
+    np.testing.assert_array_equal(N(idx), oracle.furthest_point_sampling(xyz, M))
+    got = ext.ball_query(new_xyz, T(xyz), r, ns)
+    np.testing.assert_array_equal(N(got), oracle.ball_query(N(new_xyz), xyz, r, ns))
+
+
+@pytest.mark.parametrize("C,c0,ld", [(128, 3, 132), (3, 0, 132), (37, 3, 40), (256, 3, 260)])
+def test_group_rows_grad_matches_index_add(C, c0, ld, ext):
+    """channels-last scatter-add (gradient of the grouped rows) vs a float64 index_add of the same rows."""
+    from scan2cap_b200.lib.pointnet2 import _ext_mlp
+    B, n, M, ns = 2, 700, 96, 16
+    g = torch.Generator(device="cuda").manual_seed(C)
+    rows = torch.randn((B, M * ns, ld), generator=g, device="cuda")
+    idx = torch.randint(0, n, (B, M, ns), generator=g, device="cuda", dtype=torch.int32)
+    out = _ext_mlp.group_rows_grad(rows, c0, C, idx, n, scale=0.5)
+    want = torch.zeros((B, n, C), dtype=torch.float64, device="cuda")
+    for b in range(B):
+        want[b].index_add_(0, idx[b].reshape(-1).long(), rows[b, :, c0:c0 + C].double() * 0.5)
+    # tolerance: fp32 atomics in arbitrary order (the reference's group_points_grad is atomicAdd too)
+    torch.testing.assert_close(out.double(), want, rtol=1e-5, atol=1e-5)
 
 
 def test_errors_raise(ext):

@@ -252,6 +252,36 @@ S2C_API int s2c_bn_backward_coeffs(const double *sum_g, const double *sum_gy, co
 S2C_API int s2c_group_rows_grad(const float *rows, long long ld, int c0, int C, const int *idx, int B, long long T,
                                 int n, float scale, float *out, void *stream);
 
+/* caption_decode_fwd / caption_decode_bwd -- the teacher-forced top-down caption decoder of
+ *   TopDownSceneCaptionModule.forward_sample_batch (models/caption_module.py:428-500, step :250-292) for all T
+ *   words in ONE launch per direction (a thread-block cluster walks the recurrence; see csrc/caption.cu).
+ *   Sizes: B scenes, T words, K proposals, E = emb_size, H = hidden_size, F = feat_size (E, F multiples of 4, H of 64).
+ *   Inputs (fp32): pre_word (B,T,E) = W_td[:, :E] w_t ; pre_tgt (B,E) = W_td[:, E+H:] target + b_td ;
+ *     mapped (B,K,H) = map_feat(obj) ; obj (B,K,F) ; valid (B,K) 0/1 local-context mask ;
+ *     w_tdh = W_td[:, E:E+H] (E rows, stride ld_tdh) ; GRU cells (w_ih (3H,E), w_hh (3H,H), b_ih, b_hh (3H)) ;
+ *     w_hidd (H,H) ; w_att (H) ; w_lang (E,F+H), b_lang (E).
+ *   Per-step outputs, all (T,B,.): u, lang (E) ; h1, r1, z1, n1, hn1, q, r2, z2, n2, hn2, h2 (H) ; probs (K) =
+ *     softmax over the valid proposals (exact zeros elsewhere; uniform 1/K for a scene with no valid proposal,
+ *     as softmax of K equal -1e30 scores) ; att (F).  h2 is the decoder output, probs the attention map.
+ *   Backward: d_h2 (T,B,H) and optional d_probs (T,B,K) in; transposed weights wt_* (row-major W^T) in;
+ *     per-step gradients out, (T,B,.): dgi2, dgh2, dgi1, dgh1 (3H) ; dlang, du (E) ; datt (F) ; dq (H) ;
+ *     d_mapped (B,K,H) and d_obj (B,K,F) are ACCUMULATED INTO (zero-fill them first) ;
+ *     d_watt (ceil(B/8), H): per-cluster partial sums of d w_att.  The weight gradients are GEMMs over those
+ *     (T*B)-row stacks and are left to the caller. */
+typedef struct s2c_caption_params {
+  int B, T, K, E, H, F;
+  long long ld_tdh;
+  const float *pre_word, *pre_tgt, *mapped, *obj, *valid;
+  const float *w_tdh, *w_ih1, *w_hh1, *b_ih1, *b_hh1, *w_hidd, *w_att, *w_lang, *b_lang, *w_ih2, *w_hh2, *b_ih2, *b_hh2;
+  float *u, *h1, *r1, *z1, *n1, *hn1, *q, *probs, *att, *lang, *r2, *z2, *n2, *hn2, *h2;
+  /* backward only */
+  const float *wt_tdh, *wt_ih1, *wt_hh1, *wt_hidd, *wt_lang, *wt_ih2, *wt_hh2;
+  const float *d_h2, *d_probs;
+  float *dgi2, *dgh2, *dlang, *datt, *dq, *dgi1, *dgh1, *du, *d_mapped, *d_obj, *d_watt;
+} s2c_caption_params;
+S2C_API int s2c_caption_decode_fwd(const s2c_caption_params *params, void *stream);
+S2C_API int s2c_caption_decode_bwd(const s2c_caption_params *params, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

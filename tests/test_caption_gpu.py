@@ -1,0 +1,137 @@
+"""Cluster-kernel caption decoder (csrc/caption.cu) vs a float64 PyTorch evaluation of the same recurrence
+(the per-word step of the reference, models/caption_module.py:250-292, teacher-forced as in :428-500)."""
+import copy
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 2e-4  # of the tensor's max magnitude; the bar for float features / logits is 1e-3 (BASELINE.json north_star)
+
+
+def _reference(pre_word, pre_tgt, mapped, obj, valid, w_tdh, c1, map_hidd, attend, map_lang, c2):
+    B, T, _ = pre_word.shape
+    H = mapped.shape[2]
+    h1 = pre_word.new_zeros(B, H)
+    h2 = pre_word.new_zeros(B, H)
+    hs, ps = [], []
+    for t in range(T):
+        u = torch.relu(pre_word[:, t] + pre_tgt + F.linear(h2, w_tdh))
+        h1 = c1(u, h1)
+        comb = torch.tanh(mapped + map_hidd(h1).unsqueeze(1))
+        scores = attend(comb).masked_fill(valid.unsqueeze(-1) == 0, float("-1e30"))
+        p = F.softmax(scores, dim=1)
+        att = (obj * p).sum(1)
+        lang = torch.relu(map_lang(torch.cat([att, h1], -1)))
+        h2 = c2(lang, h2)
+        hs.append(h2)
+        ps.append(p)
+    return torch.stack(hs, 1), torch.cat(ps, -1)
+
+
+@pytest.mark.parametrize("B,T,K,E,H,Fd,nvalid", [
+    (8, 6, 256, 300, 512, 128, 11),   # the training shape (10 locals + self)
+    (3, 4, 40, 300, 512, 128, 5),     # partial cluster; scene 1 gets NO valid proposal (uniform attention)
+    (11, 3, 64, 64, 128, 32, 64),     # two clusters, every proposal valid, small widths (8-CTA or 16-CTA slices)
+    (4, 31, 256, 300, 512, 128, 11),  # BASELINE config c4 batch, longest description
+])
+def test_topdown_decode_matches_float64(B, T, K, E, H, Fd, nvalid):
+    from scan2cap_b200.lib import caption_decoder
+    torch.manual_seed(B * 100 + T)
+    mk = lambda *s: (torch.randn(*s, device=DEV) * 0.5)
+    pre_word, pre_tgt, mapped, obj = mk(B, T, E), mk(B, E), mk(B, K, H), mk(B, K, Fd)
+    valid = torch.zeros(B, K, device=DEV)
+    for b in range(B):
+        if not (B == 3 and b == 1):
+            valid[b, torch.randperm(K, device=DEV)[:nvalid]] = 1.0
+    w_td = mk(E, E + H + Fd) * 0.2
+    c1, c2 = nn.GRUCell(E, H).to(DEV), nn.GRUCell(E, H).to(DEV)
+    map_hidd, attend = nn.Linear(H, H, bias=False).to(DEV), nn.Linear(H, 1, bias=False).to(DEV)
+    map_lang = nn.Linear(Fd + H, E).to(DEV)
+    mods = [c1, c2, map_hidd, attend, map_lang]
+    inputs = [pre_word, pre_tgt, mapped, obj, w_td]
+    for t in inputs:
+        t.requires_grad_(True)
+    g_h, g_p = mk(B, T, H), mk(B, K, T)
+
+    def run(fn, dtype):
+        ins = [t.detach().to(dtype).requires_grad_(True) for t in inputs]
+        ms = [copy.deepcopy(m).to(dtype) for m in mods]
+        w_tdh = ins[4][:, E:E + H]
+        hid, attn = fn(ins[0], ins[1], ins[2], ins[3], valid.to(dtype), w_tdh, ms[0], ms[2], ms[3], ms[4], ms[1])
+        loss = (hid * g_h.to(dtype)).sum() + (attn * g_p.to(dtype)).sum()
+        params = [p for m in ms for p in m.parameters()]
+        grads = torch.autograd.grad(loss, ins + params, allow_unused=True)
+        return hid, attn, grads
+
+    def fused(pw, pt, mp, ob, va, wt, m_c1, m_hidd, m_att, m_lang, m_c2):
+        return caption_decoder.topdown_decode(pw, pt, mp, ob, va, wt, m_c1, m_hidd, m_att, m_lang, m_c2)
+
+    hid_r, attn_r, grads_r = run(_reference, torch.float64)
+    hid_o, attn_o, grads_o = run(fused, torch.float32)
+
+    def close(a, b, what):
+        scale = float(b.abs().max()) + 1e-12
+        err = float((a.double() - b).abs().max()) / scale
+        assert err < TOL, "%s: max error %.3e of scale %.3e" % (what, err, scale)
+
+    close(hid_o, hid_r, "hiddens")
+    close(attn_o, attn_r, "attention")
+    has_valid = valid.sum(1) > 0  # masked proposals get exactly zero attention (a scene without any: uniform 1/K)
+    masked = (valid[has_valid] == 0).unsqueeze(-1).expand(-1, -1, T)
+    if masked.any():
+        assert float(attn_o[has_valid][masked].abs().max()) == 0.0
+    if not bool(has_valid.all()):
+        assert torch.allclose(attn_o[~has_valid], torch.full_like(attn_o[~has_valid], 1.0 / K))
+    names = ["pre_word", "pre_tgt", "mapped", "obj", "w_td"] + ["param%d" % i for i in range(len(grads_r) - 5)]
+    for n, a, b in zip(names, grads_o, grads_r):
+        assert (a is None) == (b is None), n
+        if a is not None:
+            close(a, b, "grad " + n)
+
+
+def test_module_fused_and_stepwise_paths_agree(monkeypatch):
+    """TopDownSceneCaptionModule.forward (training mode) through the cluster kernels vs the step-by-step path."""
+    import numpy as np
+    from scan2cap_b200 import synthetic
+    from scan2cap_b200.models import caption_module as cm
+    V = 60
+    vocab, emb, _ = synthetic.make_vocabulary(V)
+    torch.manual_seed(3)
+    m = cm.TopDownSceneCaptionModule(vocab, emb, num_locals=10, query_mode="center", use_relation=False).to(DEV)
+    B, K = 4, 256
+    rng = np.random.default_rng(0)
+    centres = torch.from_numpy(rng.uniform(-3, 3, (B, K, 1, 3))).to(DEV)
+    half = torch.from_numpy(rng.uniform(0.2, 0.8, (B, K, 1, 3))).to(DEV)
+    signs = torch.tensor([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], dtype=torch.float64,
+                         device=DEV).view(1, 1, 8, 3)
+    corners = centres + half * signs
+    data = {
+        "bbox_feature": torch.randn(B, K, 128, device=DEV, requires_grad=True),
+        "bbox_mask": (torch.rand(B, K, device=DEV) > 0.4).long(),
+        "bbox_corner": corners,
+        "ref_box_corner_label": corners[:, 5].clone(),
+        "lang_feat": torch.randn(B, 32, 300, device=DEV),
+        "lang_len": torch.tensor([9, 14, 7, 12], device=DEV),
+        "num_words": 14,
+    }
+    outs = {}
+    for fused in (True, False):
+        monkeypatch.setattr(cm, "USE_FUSED_DECODER", fused)
+        m.zero_grad()
+        d = dict(data)
+        d["bbox_feature"] = data["bbox_feature"].detach().clone().requires_grad_(True)
+        o = m(d, True, False)
+        (o["lang_cap"].square().mean() + o["topdown_attn"].square().sum()).backward()
+        outs[fused] = (o["lang_cap"].detach(), o["topdown_attn"].detach(), d["bbox_feature"].grad.clone(),
+                       [p.grad.clone() for p in m.parameters()])
+    a, b = outs[True], outs[False]
+    for x, y, n in ((a[0], b[0], "lang_cap"), (a[1], b[1], "topdown_attn"), (a[2], b[2], "d bbox_feature")):
+        err = float((x - y).abs().max() / (y.abs().max() + 1e-12))
+        assert err < 1e-3, (n, err)
+    for (n, _), x, y in zip(m.named_parameters(), a[3], b[3]):
+        err = float((x - y).abs().max() / (y.abs().max() + 1e-12))
+        assert err < 1e-3, ("grad " + n, err)

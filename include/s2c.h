@@ -282,6 +282,22 @@ typedef struct s2c_caption_params {
 S2C_API int s2c_caption_decode_fwd(const s2c_caption_params *params, void *stream);
 S2C_API int s2c_caption_decode_bwd(const s2c_caption_params *params, void *stream);
 
+/* gemm_tn -- out (M,N) = A^T X with A (R, lda), X (R, ldx) fp32 row-major and a SHORT reduction length R (the T*B rows
+ *   of the caption decoder): the weight gradients dW = dGates^T Inputs that autograd computes with cuBLAS after the
+ *   recurrence (caption_module.py:428-500).  colsum (M), optional: column sums of A (the bias gradients). */
+S2C_API int s2c_gemm_tn(const float *A, long long lda, const float *X, long long ldx, int R, int M, int N, float *out,
+                        long long ldo, float *colsum, void *stream);
+
+/* mlp_layer_bwd_input -- input gradient of the FIRST layer of a shared MLP on the tensor cores:
+ *       C (R, N; ldc) = (a*G + b*Y + c) * W[:, block of N columns]
+ *   G (R, ldg) the layer's masked upstream gradient, Y (R, ldy) its pre-BatchNorm output, a/b/c [K] from
+ *   s2c_bn_backward_coeffs, W the Conv2d weight (K rows, row stride ldw) offset by the caller to the wanted block of
+ *   input columns; N in {64,128,256}.  dY_out (R, K) optional.  wprep: ceil(K/32)*N*256 bytes.
+ *   Replaces the dgrad of SharedMLP's first Conv2d (pytorch_utils.py:88-95 under autograd). */
+S2C_API int s2c_mlp_layer_bwd_input(const float *G, long long ldg, const float *Y, long long ldy, long long R, int K,
+                                    const float *a, const float *b, const float *c, const float *W, long long ldw, int N,
+                                    float *C, long long ldc, float *dY_out, void *wprep, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,8 @@ SIGNATURES = {
     "s2c_bn_finalize": [P, P, c_ll, c_int, P, P, ctypes.c_double, ctypes.c_double, c_int, c_int, P, P, P, P, P, P, P, P],
     "s2c_bn_backward_coeffs": [P, P, P, P, P, c_ll, c_int, c_int, P, P, P, P, P, P],
     "s2c_group_rows_grad": [P, c_ll, c_int, c_int, P, c_int, c_ll, c_int, c_float, P, P],
+    "s2c_mlp_layer_bwd_input": [P, c_ll, P, c_ll, c_ll, c_int, P, P, P, P, c_ll, c_int, P, c_ll, P, P, P],
+    "s2c_gemm_tn": [P, c_ll, P, c_ll, c_int, c_int, c_int, P, c_ll, P, P],
     "s2c_caption_decode_fwd": [P, P],
     "s2c_caption_decode_bwd": [P, P],
     "s2c_knn_adjacency": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.c_double, P, P, P],

@@ -8,10 +8,10 @@
 //      65 536 cells), counting sort of the point indices by cell (order inside a cell is irrelevant).
 //   2. query kernel (one warp per centre): visit the 3x3 runs of x-adjacent cells around the centre (each run is one
 //      contiguous range of the sorted array), test ONLY those candidates with exactly the reference's fp32
-//      expression, and set bit k of a per-warp bitmap for every hit; the first nsample set bits of the bitmap, read in
-//      index order, are the reference's neighbour list.  Padding / empty-ball rules as in the reference.
-//      The bitmap is two-level (a summary word per 32 bitmap words) so the ordered extraction touches only the
-//      non-empty words (~#hits) instead of all n/32; the 9 runs are scanned as ONE flattened candidate range.
+//      expression, collecting the hit indices in a small per-warp list; the list sorted by index (each hit's rank =
+//      number of smaller hits) and cut at nsample is the reference's neighbour list.  Padding / empty-ball rules as
+//      in the reference.  The 9 runs are scanned as ONE flattened candidate range; more than 1024 hits (denser than
+//      any indoor scan) fall back to a repeated minimum search over the candidates.
 //   The gather epilogue (centre subtraction, 1/r, concat, channels-last output) is the one of ball_query.cu.
 // Candidate count per centre drops from n (40 000) to ~200, so the kernel becomes a gather bound by the bytes it
 // writes instead of by distance arithmetic.
@@ -190,21 +190,20 @@ grid_build_kernel(const float *__restrict__ xyz, int n, float radius, GridParams
 }
 
 // ---- 2. query (+ gather) ---------------------------------------------------------------------------------
-// Per-warp shared memory: bm[words] hit bitmap | sm[swords] summary (bit w&31 of sm[w>>5] <=> bm[w] != 0) |
-// wl[nsample] ordered list of the first non-empty bitmap words | li[nsample] the neighbour list.
+// Per-warp shared memory: hk[kHitCap] the hit indices of the current centre (unordered) | li[nsample] its neighbour
+// list.  The footprint does not depend on n, so 48 warps per SM stay resident for the gather at any scene size.
+constexpr int kHitCap = 1024;
+
 template <bool GROUP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 grid_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz, int n, int M, float radius, int nsample,
                   const GridParams *__restrict__ params, const int *__restrict__ cell_start, const float4 *__restrict__ sorted,
-                  int words, int swords, int *__restrict__ idx, GroupArgs ga) {
-  extern __shared__ __align__(16) unsigned int smem_u[];
+                  int *__restrict__ idx, GroupArgs ga) {
+  extern __shared__ __align__(16) int smem_i[];
   const int warps = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t per_warp = (size_t)words + swords + 2 * (size_t)nsample;
-  unsigned int *bm = smem_u + (size_t)warp * per_warp;
-  unsigned int *sm = bm + words;
-  int *wl = reinterpret_cast<int *>(sm + swords);
-  int *li = wl + nsample;
+  int *hk = smem_i + (size_t)warp * (kHitCap + nsample);
+  int *li = hk + kHitCap;
   const int b = blockIdx.y;
   xyz += (size_t)b * n * 3;
   new_xyz += (size_t)b * M * 3;
@@ -212,8 +211,6 @@ grid_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ x
   sorted += (size_t)b * n;
   const GridParams gp = params[b];
   const float radius2 = __fmul_rn(radius, radius);
-  for (int w = lane; w < words + swords; w += 32) bm[w] = 0u;  // bm and sm are adjacent
-  __syncwarp();
   const float *f = (GROUP && ga.features) ? ga.features + (size_t)b * ga.feat_scene_stride : nullptr;
 
   for (int j = blockIdx.x * warps + warp; j < M; j += gridDim.x * warps) {
@@ -247,69 +244,59 @@ grid_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ x
       excl[r] = __shfl_sync(0xffffffffu, my_excl, r);
       adj[r] = __shfl_sync(0xffffffffu, my_adj, r);
     }
-#pragma unroll 2
-    for (int t = lane; t < total; t += 32) {
-      int a = adj[0];
+    // ---- collect the hits (any order); H counts all of them, only the first kHitCap are stored
+    int H = 0;
+    for (int t0 = 0; t0 < total; t0 += 32) {
+      const int t = t0 + lane;
+      bool hit = false;
+      int k = 0;
+      if (t < total) {
+        int a = adj[0];
 #pragma unroll
-      for (int r = 1; r < 9; ++r) a = t >= excl[r] ? adj[r] : a;  // runs are in increasing t order: the last match wins
-      const float4 p = __ldg(sorted + t + a);
-      const int k = __float_as_int(p.w);
-      const float d2 = sqdist3(cx, cy, cz, p.x, p.y, p.z);
-      if (d2 < radius2) {
-        atomicOr(&bm[k >> 5], 1u << (k & 31));
-        atomicOr(&sm[k >> 10], 1u << ((k >> 5) & 31));
+        for (int r = 1; r < 9; ++r) a = t >= excl[r] ? adj[r] : a;  // runs are in increasing t order: the last match wins
+        const float4 p = __ldg(sorted + t + a);
+        k = __float_as_int(p.w);
+        hit = sqdist3(cx, cy, cz, p.x, p.y, p.z) < radius2;
       }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const int pos = H + __popc(m & ((1u << lane) - 1u));
+        if (pos < kHitCap) hk[pos] = k;
+      }
+      H += __popc(m);
     }
     __syncwarp();
-    // ---- ordered extraction, level 1: the first nsample non-empty bitmap words, in index order (others are cleared)
-    int nw = 0;
-    for (int s0 = 0; s0 < swords; s0 += 32) {
-      const int s = s0 + lane;
-      unsigned int bits = (s < swords) ? sm[s] : 0u;
-      if (!__any_sync(0xffffffffu, bits != 0u)) continue;
-      if (bits) sm[s] = 0u;
-      const int c = __popc(bits);
-      int pre = c;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, pre, o);
-        if (lane >= o) pre += v;
+    int cnt;
+    if (H <= kHitCap) {
+      // ---- ordered selection by rank: the neighbour list is the hits sorted by index, cut at nsample
+      for (int i = lane; i < H; i += 32) {
+        const int k = hk[i];
+        int rank = 0;
+        for (int q = 0; q < H; ++q) rank += hk[q] < k ? 1 : 0;  // broadcast reads
+        if (rank < nsample) li[rank] = k;
       }
-      int pos = nw + pre - c;
-      while (bits) {
-        const int w = (s << 5) + __ffs(bits) - 1;
-        bits &= bits - 1;
-        if (pos < nsample) wl[pos] = w; else bm[w] = 0u;  // words beyond the first nsample cannot contribute
-        ++pos;
-      }
-      nw += __shfl_sync(0xffffffffu, pre, 31);
-    }
-    nw = min(nw, nsample);
-    __syncwarp();
-    // ---- level 2: the first nsample set bits of those words
-    int cnt = 0;
-    for (int i0 = 0; i0 < nw; i0 += 32) {
-      const int i = i0 + lane;
-      const int w = i < nw ? wl[i] : 0;
-      unsigned int bits = i < nw ? bm[w] : 0u;
-      if (i < nw) bm[w] = 0u;
-      if (cnt < nsample) {
-        const int c = __popc(bits);
-        int pre = c;
+      cnt = min(H, nsample);
+    } else {
+      // ---- more hits than the list holds (very dense neighbourhoods): repeated minimum search over the candidates
+      cnt = 0;
+      int prev = -1;
+      while (cnt < nsample) {
+        int best = 0x7fffffff;
+        for (int t = lane; t < total; t += 32) {
+          int a = adj[0];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int v = __shfl_up_sync(0xffffffffu, pre, o);
-          if (lane >= o) pre += v;
+          for (int r = 1; r < 9; ++r) a = t >= excl[r] ? adj[r] : a;
+          const float4 p = __ldg(sorted + t + a);
+          const int k = __float_as_int(p.w);
+          if (k > prev && k < best && sqdist3(cx, cy, cz, p.x, p.y, p.z) < radius2) best = k;
         }
-        int pos = cnt + pre - c;
-        while (bits && pos < nsample) {
-          li[pos++] = (w << 5) + __ffs(bits) - 1;
-          bits &= bits - 1;
-        }
-        cnt += __shfl_sync(0xffffffffu, pre, 31);
+        best = __reduce_min_sync(0xffffffffu, best);
+        if (best == 0x7fffffff) break;
+        if (lane == 0) li[cnt] = best;
+        prev = best;
+        ++cnt;
       }
     }
-    cnt = min(cnt, nsample);
     __syncwarp();
     const int first = cnt > 0 ? li[0] : 0;
     __syncwarp();
@@ -375,20 +362,17 @@ extern "C" int s2c_query_and_group_grid(const float *xyz, const float *new_xyz, 
     ga.feat_point_stride = feat_stride; ga.feat_chan_stride = 1; ga.feat_scene_stride = (long long)n * feat_stride;
   }
   ga.out_layout = out_layout; ga.normalize = normalize_xyz ? 1 : 0; ga.inv_radius = normalize_xyz ? (1.0f / radius) : 1.0f;
-  const int words = (n + 31) / 32, swords = (words + 31) / 32;
-  const size_t per_warp = (size_t)(words + swords + 2 * nsample) * 4;
-  int warps = 8;
-  while (warps > 1 && (size_t)warps * per_warp > 200 * 1024) warps >>= 1;
-  const size_t smem = (size_t)warps * per_warp;
-  S2C_REQUIRE(smem <= 227 * 1024, "query_and_group_grid: n=%d too large for the per-warp bitmap", n);
-  const int ctas_x = min(ceil_div(M, warps), 4 * kNumSMs / max(B, 1) + 1);
+  const int warps = 8;
+  const size_t smem = (size_t)warps * (kHitCap + nsample) * 4;
+  S2C_REQUIRE(smem <= 227 * 1024, "query_and_group_grid: nsample=%d too large", nsample);
+  const int ctas_x = min(ceil_div(M, warps), max(1, 16 * kNumSMs / max(B, 1)));
   dim3 grid((unsigned)ctas_x, (unsigned)B);
   if (grouped) {
     S2C_CUDA(cudaFuncSetAttribute(grid_query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "grid_query smem");
-    grid_query_kernel<true><<<grid, warps * 32, smem, st>>>(new_xyz, xyz, n, M, radius, nsample, params, cell_start, sorted, words, swords, idx, ga);
+    grid_query_kernel<true><<<grid, warps * 32, smem, st>>>(new_xyz, xyz, n, M, radius, nsample, params, cell_start, sorted, idx, ga);
   } else {
     S2C_CUDA(cudaFuncSetAttribute(grid_query_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "grid_query smem");
-    grid_query_kernel<false><<<grid, warps * 32, smem, st>>>(new_xyz, xyz, n, M, radius, nsample, params, cell_start, sorted, words, swords, idx, ga);
+    grid_query_kernel<false><<<grid, warps * 32, smem, st>>>(new_xyz, xyz, n, M, radius, nsample, params, cell_start, sorted, idx, ga);
   }
   S2C_CHECK_LAUNCH("grid_query");
   return S2C_OK;

@@ -50,7 +50,7 @@ __device__ __forceinline__ float gemv_quad(const float *__restrict__ w0, const f
   float a[32];
 #pragma unroll
   for (int m = 0; m < 32; ++m) a[m] = 0.f;
-#pragma unroll 2
+#pragma unroll 4
   for (int k = lane * 4; k < K; k += 128) {
     const float4 q0 = ldw4(w0 + k), q1 = ldw4(w1 + k), q2 = ldw4(w2 + k), q3 = ldw4(w3 + k);
 #pragma unroll
@@ -119,9 +119,10 @@ namespace {
 
 // Shared-memory plan (floats): XA[8][XLD] | XB[8][XLD] | G[6*hs][8] | probs[8][K] | sc[8][K] | att[8][F] | vk[8][K] (int) | nv[8] | flag[8]
 //   forward:  XLD = max(F+H, H) ; backward: XLD = 3H
+constexpr int kMaxPairs = 128;  // (row, valid proposal) pairs whose feature rows are cached in shared memory
 struct SmemPlan {
-  float *XA, *XB, *G, *probs, *sc, *att;
-  int *vk, *nv, *uniform;
+  float *XA, *XB, *G, *probs, *sc, *att, *objs;
+  int *vk, *nv, *uniform, *pb;  // pb[r]: first pair of row r; pb[8]: total (or -1 when the cache is not used)
 };
 __device__ __forceinline__ SmemPlan plan(float *base, int xld, int hs, int K, int F) {
   SmemPlan p;
@@ -133,16 +134,20 @@ __device__ __forceinline__ SmemPlan plan(float *base, int xld, int hs, int K, in
   p.att = base; base += kRows * F;
   p.vk = reinterpret_cast<int *>(base); base += kRows * K;
   p.nv = reinterpret_cast<int *>(base); base += kRows;
-  p.uniform = reinterpret_cast<int *>(base);
+  p.uniform = reinterpret_cast<int *>(base); base += kRows;
+  p.pb = reinterpret_cast<int *>(base); base += 12;
+  p.objs = base;
   return p;
 }
 size_t plan_bytes(int xld, int hs, int K, int F) {
-  return sizeof(float) * ((size_t)2 * kRows * xld + (size_t)6 * hs * kRows + (size_t)3 * kRows * K + (size_t)kRows * F + 2 * kRows) + 16;
+  return sizeof(float) * ((size_t)2 * kRows * xld + (size_t)6 * hs * kRows + (size_t)3 * kRows * K + (size_t)kRows * F + 2 * kRows + 12 +
+                          (size_t)kMaxPairs * F) + 16;
 }
 
 // valid-object lists of the cluster's rows (constant over the steps).  A row without any valid object gets the
 // uniform distribution over all K objects (softmax of K equal -1e30 scores), flagged in `uniform`.
-__device__ __forceinline__ void build_valid_lists(const SmemPlan &sp, const float *valid, int rb, int nb, int K) {
+__device__ __forceinline__ void build_valid_lists(const SmemPlan &sp, const float *valid, const float *obj, int rb, int nb,
+                                                  int K, int F) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp < kRows) {
     const int r = warp;
@@ -168,6 +173,30 @@ __device__ __forceinline__ void build_valid_lists(const SmemPlan &sp, const floa
   }
   for (int i = threadIdx.x; i < kRows * K; i += kThreads) sp.probs[i] = 0.f;
   __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int r = 0; r < kRows; ++r) { sp.pb[r] = tot; tot += sp.nv[r]; }
+    sp.pb[kRows] = tot <= kMaxPairs ? tot : -1;
+  }
+  __syncthreads();
+  if (sp.pb[kRows] >= 0) {  // the valid set is the same for every word: keep those proposals' features on chip
+    const int f4 = F >> 2;
+    for (int r = 0; r < nb; ++r) {
+      const int n = sp.nv[r];
+      for (int i = threadIdx.x; i < n * f4; i += kThreads) {
+        const int ii = i / f4, c = (i - ii * f4) * 4;
+        const int k = sp.vk[r * K + ii];
+        *reinterpret_cast<float4 *>(sp.objs + (size_t)(sp.pb[r] + ii) * F + c) =
+            __ldg(reinterpret_cast<const float4 *>(obj + ((size_t)(rb + r) * K + k) * F + c));
+      }
+    }
+  }
+  __syncthreads();
+}
+// feature row of the ii-th valid proposal of row r: shared-memory cache, or global memory when the cache is off
+__device__ __forceinline__ const float *obj_row(const SmemPlan &sp, const float *obj, int rb, int r, int ii, int K, int F) {
+  return sp.pb[kRows] >= 0 ? sp.objs + (size_t)(sp.pb[r] + ii) * F
+                           : obj + ((size_t)(rb + r) * K + sp.vk[r * K + ii]) * F;
 }
 
 // ================================================================== forward
@@ -183,7 +212,7 @@ caption_fwd_kernel(const s2c_caption_params P) {
   const Slices S = make_slices(c, CL, H, E, F);
   const int XLD = F + H;
   const SmemPlan sp = plan(smem, XLD, S.hs, K, F);
-  build_valid_lists(sp, P.valid, rb, nb, K);
+  build_valid_lists(sp, P.valid, P.obj, rb, nb, K, F);
   const int li = lane >> 3, lr = lane & 7;  // this lane's (row-in-quad, batch row) after gemv_quad
 
   for (int t = 0; t < T; ++t) {
@@ -253,7 +282,24 @@ caption_fwd_kernel(const s2c_caption_params P) {
             const int k = sp.vk[r * K + i];
             const float *mp = P.mapped + ((size_t)(rb + r) * K + k) * H;
             float s = 0.f;
-            for (int h = lane; h < H; h += 32) s = fmaf(tanhf(mp[h] + sp.XA[r * XLD + h]), P.w_att[h], s);
+            for (int h0 = 0; h0 < H; h0 += 512) {  // 4 independent 16-byte loads per lane before any tanh
+              float4 m4[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int h = h0 + j * 128 + lane * 4;
+                m4[j] = h < H ? __ldg(reinterpret_cast<const float4 *>(mp + h)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int h = h0 + j * 128 + lane * 4;
+                if (h < H) {
+                  const float4 qv = *reinterpret_cast<const float4 *>(sp.XA + r * XLD + h);
+                  const float4 wv = __ldg(reinterpret_cast<const float4 *>(P.w_att + h));
+                  s = fmaf(tanhf(m4[j].x + qv.x), wv.x, s); s = fmaf(tanhf(m4[j].y + qv.y), wv.y, s);
+                  s = fmaf(tanhf(m4[j].z + qv.z), wv.z, s); s = fmaf(tanhf(m4[j].w + qv.w), wv.w, s);
+                }
+              }
+            }
 #pragma unroll
             for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (lane == 0) sp.sc[r * K + i] = s;
@@ -288,10 +334,8 @@ caption_fwd_kernel(const s2c_caption_params P) {
         float a = 0.f;
         if (r < nb) {
           const int n = sp.nv[r];
-          for (int ii = 0; ii < n; ++ii) {
-            const int k = sp.vk[r * K + ii];
-            a = fmaf(sp.probs[r * K + k], P.obj[((size_t)(rb + r) * K + k) * F + f], a);
-          }
+          for (int ii = 0; ii < n; ++ii)
+            a = fmaf(sp.probs[r * K + sp.vk[r * K + ii]], obj_row(sp, P.obj, rb, r, ii, K, F)[f], a);
         }
         sp.att[i] = a;
       }
@@ -365,7 +409,7 @@ caption_bwd_kernel(const s2c_caption_params P) {
   // carried gradients of this CTA's hidden units: acc1/acc2 [hs][8] live in G's tail? -> dedicated arrays in G:
   // G layout here: [0, hs*8): dh1 carried / total, [hs*8, 2*hs*8): dh2 carried / total, [2*hs*8, 3*hs*8): scratch
   float *d1 = sp.G, *d2 = sp.G + S.hs * kRows, *dsv = sp.sc;  // dsv[r][i]: d score of (row, i-th valid object)
-  build_valid_lists(sp, P.valid, rb, nb, K);
+  build_valid_lists(sp, P.valid, P.obj, rb, nb, K, F);
   for (int i = threadIdx.x; i < 2 * S.hs * kRows; i += kThreads) sp.G[i] = 0.f;
   __syncthreads();
   const int li = lane >> 3, lr = lane & 7;
@@ -441,7 +485,7 @@ caption_bwd_kernel(const s2c_caption_params P) {
       const int n = sp.nv[r];
       for (int i = warp; i < n; i += kWarps) {
         const int k = sp.vk[r * K + i];
-        const float *ob = P.obj + ((size_t)(rb + r) * K + k) * F;
+        const float *ob = obj_row(sp, P.obj, rb, r, i, K, F);
         float s = 0.f;
         for (int f = lane; f < F; f += 32) s = fmaf(sp.att[r * F + f], ob[f], s);
 #pragma unroll
@@ -471,15 +515,27 @@ caption_bwd_kernel(const s2c_caption_params P) {
         float dq = 0.f;
         if (!sp.uniform[r]) {
           const int n = sp.nv[r];
-          for (int ii = 0; ii < n; ++ii) {
-            const int k = sp.vk[r * K + ii];
-            const size_t mo = ((size_t)(rb + r) * K + k) * H + j;
-            const float cb = tanhf(P.mapped[mo] + qv);
-            const float ds = dsv[r * K + ii];
-            const float dpre = ds * wa * (1.f - cb * cb);
-            P.d_mapped[mo] += dpre;
-            dq += dpre;
-            dwatt = fmaf(ds, cb, dwatt);
+          for (int i0 = 0; i0 < n; i0 += 4) {  // 4 proposals at a time: all loads issued before the first use
+            float mv[4], dm[4];
+            size_t mo[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int ii = min(i0 + u, n - 1);
+              mo[u] = ((size_t)(rb + r) * K + sp.vk[r * K + ii]) * H + j;
+              mv[u] = __ldg(P.mapped + mo[u]);
+              dm[u] = P.d_mapped[mo[u]];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (i0 + u < n) {
+                const float cb = tanhf(mv[u] + qv);
+                const float ds = dsv[r * K + i0 + u];
+                const float dpre = ds * wa * (1.f - cb * cb);
+                P.d_mapped[mo[u]] = dm[u] + dpre;
+                dq += dpre;
+                dwatt = fmaf(ds, cb, dwatt);
+              }
+            }
           }
         }
         P.dq[(tb + r) * H + j] = dq;

@@ -15,7 +15,7 @@ struct GroupArgs {
   float *grouped;         // may be null (query only)
   int C;
   long long feat_point_stride, feat_chan_stride, feat_scene_stride;
-  int out_layout;  // 0: (B,3+C,M,ns)  1: (B,M,ns,3+C)  2: (B,M,ns,Cp), Cp = 3+C rounded up to 4, zero padded
+  int out_layout;  // 0: (B,3+C,M,ns)  1: (B,M,ns,3+C)  2: (B,M,ns,Cp) rows [x,y,z,0 | C features | zero pad], Cp = 4 + ceil4(C)
   float inv_radius;  // 1 if !normalize_xyz
   int normalize;
 };
@@ -47,16 +47,19 @@ __device__ __forceinline__ void group_epilogue(const GroupArgs &ga, const float 
     }
     return;
   }
-  // (B,M,ns,Cp): the centre's whole block is one contiguous run of ns*Cp floats (Cp = 3+C, or padded to 4)
-  const int CP = ga.out_layout == 2 ? ((CC + 3) & ~3) : CC;
-  float *o = ga.grouped + ((size_t)b * M + j) * (size_t)nsample * CP;
-  if (ga.out_layout == 2 && (ga.feat_chan_stride == 1 || ga.C == 0)) {
-    // 16-byte stores: slot q = (sample s, channels 4w..4w+3).  Slot 0 of a sample holds the three offsets and the
-    // first feature; the feature run of a point is read with 4-byte loads (it starts 3 floats into a 16-byte
-    // group), consecutive lanes covering consecutive 16-byte pieces of the same point's feature vector.
+  // (B,M,ns,Cp): the centre's whole block is one contiguous run of ns*Cp floats
+  if (ga.out_layout == 2) {
+    // rows [x, y, z, 0 | features | zero pad]: the feature block starts 16-byte aligned, so it can be written (and,
+    // when the source rows are aligned too, read) 4 channels at a time, and its gradient comes back as an aligned
+    // block the tensor-core dgrad / the vectorised scatter-add can address directly.
+    const int CP = 4 + ((ga.C + 3) & ~3);
+    float *o = ga.grouped + ((size_t)b * M + j) * (size_t)nsample * CP;
     const int W = CP >> 2;
     const int total = nsample * W;
     const float invW = 1.0f / (float)W;
+    const bool unit = ga.feat_chan_stride == 1;
+    const bool vec = unit && (ga.feat_point_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0;
+#pragma unroll 4
     for (int q = lane; q < total; q += 32) {
       const int s = __float2int_rz(((float)q + 0.5f) * invW);  // q / W (exact: |(q+.5)/W - integer| >= .5/W)
       const int w = q - s * W;
@@ -69,19 +72,26 @@ __device__ __forceinline__ void group_epilogue(const GroupArgs &ga, const float 
         if (ga.normalize) {
           v.x = __fmul_rn(v.x, ga.inv_radius); v.y = __fmul_rn(v.y, ga.inv_radius); v.z = __fmul_rn(v.z, ga.inv_radius);
         }
-        v.w = ga.C > 0 ? __ldg(f + (size_t)k * ga.feat_point_stride) : 0.f;
+        v.w = 0.f;
       } else {
-        const int c = 4 * w - 3;  // first feature channel of this slot
-        const float *fk = f + (size_t)k * ga.feat_point_stride + c;
-        v.x = c + 0 < ga.C ? __ldg(fk + 0) : 0.f;
-        v.y = c + 1 < ga.C ? __ldg(fk + 1) : 0.f;
-        v.z = c + 2 < ga.C ? __ldg(fk + 2) : 0.f;
-        v.w = c + 3 < ga.C ? __ldg(fk + 3) : 0.f;
+        const int c = 4 * (w - 1);  // first feature channel of this slot
+        const float *fk = f + (size_t)k * ga.feat_point_stride + (size_t)c * ga.feat_chan_stride;
+        if (vec && c + 3 < ga.C) {
+          v = __ldg(reinterpret_cast<const float4 *>(fk));
+        } else {
+          const size_t cs = (size_t)ga.feat_chan_stride;
+          v.x = c + 0 < ga.C ? __ldg(fk) : 0.f;
+          v.y = c + 1 < ga.C ? __ldg(fk + cs) : 0.f;
+          v.z = c + 2 < ga.C ? __ldg(fk + 2 * cs) : 0.f;
+          v.w = c + 3 < ga.C ? __ldg(fk + 3 * cs) : 0.f;
+        }
       }
       st_stream4(o + 4 * (size_t)q, v);
     }
     return;
   }
+  const int CP = CC;
+  float *o = ga.grouped + ((size_t)b * M + j) * (size_t)nsample * CP;
   const int total = nsample * CP;
   for (int t = lane; t < total; t += 32) {
     const int s = t / CP, ch = t - s * CP;

@@ -616,3 +616,42 @@ extern "C" int s2c_mlp_layer_bwd_data(const float *G, long long ldg, const float
   }
   return S2C_OK;
 }
+
+// Input gradient of the FIRST layer of a shared MLP (no previous BatchNorm / ReLU to mask with, no statistics):
+//     dY = a[k]*G + b[k]*Y + c[k]            BatchNorm backward of layer 0 (affine per channel)
+//     C  = dY * W[:, w0 : w0+N]              (R, N) written with leading dimension ldc
+//   W is the layer's Conv2d weight (K rows) with row stride ldw; the caller offsets W (and C) to select a block of N
+//   input columns -- e.g. the feature block of the grouped rows [xyz, 0, features], or one half of a concatenation.
+//   N in {64,128,256}.  dY_out (R, K), optional: dY written back for the weight-gradient GEMM.
+//   Replaces cuDNN's dgrad of the first 1x1 convolution (pytorch_utils.py:88-95 under autograd).
+extern "C" int s2c_mlp_layer_bwd_input(const float *G, long long ldg, const float *Y, long long ldy, long long R, int K,
+                                       const float *a, const float *b, const float *c, const float *W, long long ldw,
+                                       int N, float *C, long long ldc, float *dY_out, void *wprep, void *stream) {
+  using namespace s2c;
+  S2C_REQUIRE(R >= 0 && K >= 4 && (K & 3) == 0, "mlp_layer_bwd_input: K=%d must be a positive multiple of 4", K);
+  S2C_REQUIRE(N == 64 || N == 128 || N == 256, "mlp_layer_bwd_input: N=%d must be 64, 128 or 256", N);
+  S2C_REQUIRE((ldg & 3) == 0 && (ldy & 3) == 0 && (ldc & 3) == 0 && ldg >= K && ldy >= K && ldc >= N && ldw >= N,
+              "mlp_layer_bwd_input: bad leading dimensions");
+  if (R == 0) return S2C_OK;
+  S2C_REQUIRE(G && Y && a && b && c && W && C && wprep, "mlp_layer_bwd_input: null pointer");
+  S2C_REQUIRE(((uintptr_t)G & 15) == 0 && ((uintptr_t)Y & 15) == 0 && ((uintptr_t)C & 15) == 0 && ((uintptr_t)wprep & 15) == 0,
+              "mlp_layer_bwd_input: G, Y, C and wprep must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int KC = (K + BK - 1) / BK;
+  Gemm2Args g = {};
+  g.A = G; g.lda = ldg; g.K = K; g.p0 = a; g.p1 = b; g.p2 = c; g.C = C; g.ldc = ldc; g.dY_out = dY_out; g.R = R;
+  const int halves = N == 256 ? 2 : 1, NH = N / halves;
+  for (int h = 0; h < halves; ++h) {
+    Gemm2Args gh = g;
+    unsigned char *wp = (unsigned char *)wprep + (size_t)h * KC * NH * 256;
+    // B operand = (W block)^T: B[n][k] = W[k*ldw + n]
+    w_prep_kernel<<<ceil_div(KC * NH * 8, 256), 256, 0, st>>>(W + h * NH, NH, K, (int)ldw, 0, wp);
+    S2C_CHECK_LAUNCH("w_prep");
+    gh.wprep = wp; gh.C = C + h * NH;
+    if (h == 1) gh.dY_out = nullptr;
+    const int rc = NH == 64 ? launch_gemm2<64, PRO_AFFINE2, EPI_STORE_STATS>(gh, Y, ldy, st)
+                            : launch_gemm2<128, PRO_AFFINE2, EPI_STORE_STATS>(gh, Y, ldy, st);
+    if (rc) return rc;
+  }
+  return S2C_OK;
+}

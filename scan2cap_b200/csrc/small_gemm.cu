@@ -1,0 +1,72 @@
+// out (M, N) = A^T X over a SHORT reduction (R rows = T*B of the caption decoder, a few hundred): the weight gradients
+// dW = dGates^T * Inputs after the decoder's backward recurrence (models/caption_module.py:428-500 under autograd).
+// cuBLAS' SIMT heuristics pick split-K kernels with < 50 CTAs for these shapes (85 us for 0.2 GFLOP); a plain
+// 64x64-tile kernel with one CTA per output tile is latency-bound at ~6 us.  Optionally also emits the column sums
+// of A (the bias gradients) from the first tile column.
+#include "s2c_common.cuh"
+
+namespace s2c {
+namespace {
+
+constexpr int TM = 64, TN = 64, TR = 16;
+
+__global__ void __launch_bounds__(256)
+gemm_tn_kernel(const float *__restrict__ A, long long lda, const float *__restrict__ X, long long ldx, int R, int M, int N,
+               float *__restrict__ out, long long ldo, float *__restrict__ colsum) {
+  __shared__ float As[TR][TM + 4], Xs[TR][TN + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float cs[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int r0 = 0; r0 < R; r0 += TR) {
+    for (int i = threadIdx.x; i < TR * TM; i += 256) {
+      const int rr = i / TM, c = i - rr * TM;
+      As[rr][c] = (r0 + rr < R && m0 + c < M) ? A[(size_t)(r0 + rr) * lda + m0 + c] : 0.f;
+      Xs[rr][c] = (r0 + rr < R && n0 + c < N) ? X[(size_t)(r0 + rr) * ldx + n0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < TR; ++rr) {
+      const float4 a = *reinterpret_cast<const float4 *>(&As[rr][ty * 4]);
+      const float4 x = *reinterpret_cast<const float4 *>(&Xs[rr][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        cs[i] += av[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], xv[j], acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < N) out[(size_t)m * ldo + n] = acc[i][j];
+    }
+    if (colsum != nullptr && blockIdx.x == 0 && tx == 0) colsum[m] = cs[i];
+  }
+}
+
+}  // namespace
+}  // namespace s2c
+
+extern "C" int s2c_gemm_tn(const float *A, long long lda, const float *X, long long ldx, int R, int M, int N, float *out,
+                           long long ldo, float *colsum, void *stream) {
+  using namespace s2c;
+  S2C_REQUIRE(R >= 0 && M >= 0 && N >= 0 && lda >= M && ldx >= N && ldo >= N, "gemm_tn: bad sizes");
+  if (M == 0 || N == 0) return S2C_OK;
+  S2C_REQUIRE(A && X && out, "gemm_tn: null pointer");
+  dim3 grid((unsigned)ceil_div(N, TN), (unsigned)ceil_div(M, TM));
+  gemm_tn_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, lda, X, ldx, R, M, N, out, ldo, colsum);
+  S2C_CHECK_LAUNCH("gemm_tn");
+  return S2C_OK;
+}

@@ -111,17 +111,33 @@ class _TopDownDecode(Function):
             h = saved[name]
             return torch.cat([torch.zeros_like(h[:1]), h[:-1]], 0).reshape(T * B, -1)
         h1p, h2p = prev("h1"), prev("h2")
-        d_w_ih2 = g["dgi2"].t() @ rows("lang")
-        d_w_hh2 = g["dgh2"].t() @ h2p
-        d_w_lang = g["dlang"].t() @ torch.cat([rows("att"), rows("h1")], 1)
-        d_w_hidd = g["dq"].t() @ rows("h1")
-        d_w_ih1 = g["dgi1"].t() @ rows("u")
-        d_w_hh1 = g["dgh1"].t() @ h1p
-        d_w_tdh = g["du"].t() @ h2p
+        # outputs of the 7 short-reduction GEMMs (+ bias gradients as column sums) in one buffer
+        shapes = dict(w_ih2=(3 * H, E), w_hh2=(3 * H, H), w_lang=(E, F + H), w_hidd=(H, H), w_ih1=(3 * H, E),
+                      w_hh1=(3 * H, H), w_tdh=(E, H), b_ih2=(3 * H,), b_hh2=(3 * H,), b_lang=(E,), b_ih1=(3 * H,),
+                      b_hh1=(3 * H,), b_td=(E,))
+        sizes = {k: (v[0] * v[1] if len(v) == 2 else v[0]) for k, v in shapes.items()}
+        wbuf = torch.empty((sum(sizes.values()),), dtype=torch.float32, device=dev)
+        d, off = {}, 0
+        for k, v in shapes.items():
+            d[k] = wbuf[off:off + sizes[k]].view(*v)
+            off += sizes[k]
+        lang_in = torch.cat([rows("att"), rows("h1")], 1)
+
+        def gemm_tn(A, X, out, colsum=None):
+            call("s2c_gemm_tn", A.data_ptr(), A.stride(0), X.data_ptr(), X.stride(0), A.shape[0], A.shape[1], X.shape[1],
+                 out.data_ptr(), out.stride(0), colsum.data_ptr() if colsum is not None else None, _stream(buf))
+        with _guard(buf):
+            gemm_tn(g["dgi2"], rows("lang"), d["w_ih2"], d["b_ih2"])
+            gemm_tn(g["dgh2"], h2p, d["w_hh2"], d["b_hh2"])
+            gemm_tn(g["dlang"], lang_in, d["w_lang"], d["b_lang"])
+            gemm_tn(g["dq"], rows("h1"), d["w_hidd"])
+            gemm_tn(g["dgi1"], rows("u"), d["w_ih1"], d["b_ih1"])
+            gemm_tn(g["dgh1"], h1p, d["w_hh1"], d["b_hh1"])
+            gemm_tn(g["du"], h2p, d["w_tdh"], d["b_td"])          # b_td = sum over (t, b) of du: also d pre_tgt's total
         du3 = g["du"].view(T, B, E)
-        return (du3.transpose(0, 1), du3.sum(0), d_mapped, d_obj, None, d_w_tdh,
-                d_w_ih1, d_w_hh1, g["dgi1"].sum(0), g["dgh1"].sum(0), d_w_hidd, d_watt.sum(0).view_as(w_att),
-                d_w_lang, g["dlang"].sum(0), d_w_ih2, d_w_hh2, g["dgi2"].sum(0), g["dgh2"].sum(0))
+        return (du3.transpose(0, 1), du3.sum(0), d_mapped, d_obj, None, d["w_tdh"],
+                d["w_ih1"], d["w_hh1"], d["b_ih1"], d["b_hh1"], d["w_hidd"], d_watt.sum(0).view_as(w_att),
+                d["w_lang"], d["b_lang"], d["w_ih2"], d["w_hh2"], d["b_ih2"], d["b_hh2"])
 
 
 def topdown_decode(pre_word, pre_tgt, mapped, obj, valid, w_tdh, cell1, map_hidd, attend, map_lang, cell2):

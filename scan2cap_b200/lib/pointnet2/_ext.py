@@ -175,9 +175,10 @@ def query_and_group(xyz, new_xyz, features, radius, nsample, normalize_xyz, feat
 
     features: None, (B,C,n) [default] or, with feat_point_major, a (B,n,C) view whose last dim is
     contiguous (row stride may exceed C).  grouped: (B,3+C,M,ns) contiguous, or with channels_last the
-    same logical shape in torch.channels_last memory format (physically (B,M,ns,3+C); with pad4 the rows are
-    padded with zeros to a multiple of 4 floats so that they are 16-byte aligned, and the returned tensor has
-    Cp = ceil4(3+C) channels, the last Cp-3-C of them zero).
+    same logical shape in torch.channels_last memory format (physically (B,M,ns,3+C)).  With pad4 the rows are laid
+    out [x, y, z, 0 | C features | zero pad] with Cp = 4 + ceil4(C) floats: rows AND their feature block are 16-byte
+    aligned (TMA operand of the fused MLP; aligned gradient block for the tensor-core dgrad / scatter-add); the
+    returned tensor then has Cp channels in that order.
     """
     _chk(xyz, "xyz", torch.float32)
     _chk(new_xyz, "new_xyz", torch.float32)
@@ -197,7 +198,7 @@ def query_and_group(xyz, new_xyz, features, radius, nsample, normalize_xyz, feat
     idx = torch.empty((B, M, int(nsample)), dtype=torch.int32, device=xyz.device)
     pad4 = bool(pad4 and channels_last)
     if channels_last:
-        Cp = (3 + C + 3) // 4 * 4 if pad4 else 3 + C
+        Cp = 4 + (C + 3) // 4 * 4 if pad4 else 3 + C
         grouped = torch.empty((B, M, int(nsample), Cp), dtype=torch.float32, device=xyz.device)
     else:
         grouped = torch.empty((B, 3 + C, M, int(nsample)), dtype=torch.float32, device=xyz.device)
@@ -214,5 +215,5 @@ def query_and_group(xyz, new_xyz, features, radius, nsample, normalize_xyz, feat
                  float(radius), int(nsample), 1 if normalize_xyz else 0, layout, idx.data_ptr(), grouped.data_ptr(),
                  _stream(xyz))
     if channels_last:
-        grouped = grouped.permute(0, 3, 1, 2)  # logical (B,Cp,M,ns) over channels-last storage (Cp > 3+C: zero pad)
+        grouped = grouped.permute(0, 3, 1, 2)  # logical (B,Cp,M,ns) over channels-last storage
     return grouped, idx

@@ -92,6 +92,20 @@ def mlp_layer_bwd_data(Y, a, b, c, W, Yprev, prev_scale, prev_shift, G=None, dpo
     return gprev, dY, stats[0], stats[1]
 
 
+def mlp_layer_bwd_input(G, Y, a, b, c, W, col0, N, out, want_dY=True):
+    """First-layer input gradient (see include/s2c.h): out[:, col0:col0+N] = (a*G + b*Y + c) @ W[:, col0:col0+N];
+    W (K, ldw) the layer's weight in the column layout of `out` (R, ld).  Returns dY (R, K) or None."""
+    R, K = Y.shape
+    assert W.shape[0] == K and W.stride(1) == 1 and out.stride(1) == 1 and col0 % 4 == 0 and N in (64, 128, 256)
+    dY = torch.empty((R, K), dtype=torch.float32, device=Y.device) if want_dY else None
+    wprep = torch.empty(((K + 31) // 32) * N * 256, dtype=torch.uint8, device=Y.device)
+    with _guard(Y):
+        call("s2c_mlp_layer_bwd_input", G.data_ptr(), G.stride(0), Y.data_ptr(), Y.stride(0), R, K, a.data_ptr(),
+             b.data_ptr(), c.data_ptr(), W.data_ptr() + 4 * col0, W.stride(0), int(N), out.data_ptr() + 4 * col0,
+             out.stride(0), dY.data_ptr() if want_dY else None, wprep.data_ptr(), _stream(Y))
+    return dY
+
+
 def bwd_weight_supported(C, P, *lds):
     MH, NB = (C + 127) // 128, (P + 31) // 32
     return (KERNEL_VERSION == 2 and C <= 256 and NB <= 9 and MH * NB <= 16 and 4 * MH + NB <= 13

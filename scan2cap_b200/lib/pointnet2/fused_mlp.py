@@ -24,9 +24,48 @@ def _bn_coefficients(s1, s2, R, bn, training):
     return _ext_mlp.bn_finalize(s1, s2, R, bn, training)
 
 
+def _first_layer_weight(W, K, lda, xyz_gap):
+    """The first layer's weight in the column layout of `rows` -> (W', K').
+    xyz_gap: rows are [x, y, z, 0 | K-3 features | zero pad] (lda floats): W' = [W[:, :3], 0, W[:, 3:], 0];
+    else rows may be zero-padded to a multiple of 4 columns: W' = [W, 0]."""
+    N = W.shape[0]
+    if xyz_gap:
+        C = K - 3
+        parts = [W[:, :3], W.new_zeros((N, 1)), W[:, 3:]]
+        if lda > 4 + C:
+            parts.append(W.new_zeros((N, lda - 4 - C)))
+        return torch.cat(parts, 1), lda
+    if K % 4 != 0 and lda >= (K + 3) // 4 * 4:
+        k4 = (K + 3) // 4 * 4
+        return torch.nn.functional.pad(W, (0, k4 - K)), k4
+    return W, K
+
+
+def _first_layer_weight_grad(dWp, K, xyz_gap):
+    """inverse column mapping of _first_layer_weight for the gradient."""
+    if xyz_gap:
+        return torch.cat([dWp[:, :3], dWp[:, 4:4 + K - 3]], 1)
+    return dWp[:, :K]
+
+
+def _input_blocks(K, lda, xyz_gap):
+    """Column blocks (col0, width) of the first layer's input whose gradient the tensor-core dgrad kernel can write
+    (widths 256/128/64, 16-byte aligned): the feature block of gap-layout rows, or all columns of plain rows."""
+    col, left = (4, K - 3) if xyz_gap else (0, K)
+    if left <= 0 or left % 64 != 0 or (not xyz_gap and lda != K):
+        return None
+    blocks = []
+    while left > 0:
+        w = 256 if left >= 256 else (128 if left >= 128 else 64)
+        blocks.append((col, w))
+        col += w
+        left -= w
+    return blocks
+
+
 class _FusedMLPPool(Function):
     @staticmethod
-    def forward(ctx, rows, K, G, ns, training, bns, *params):
+    def forward(ctx, rows, K, G, ns, training, bns, xyz_gap, need_xyz_grad, *params):
         """rows (R, lda) fp32 with K valid columns, R = G*ns; params = (W1, gamma1, beta1, W2, ...);
         bns = the BatchNorm modules (running statistics / eps / momentum).  Returns pooled (G, C_last)."""
         L = len(bns)
@@ -36,11 +75,8 @@ class _FusedMLPPool(Function):
         for l in range(L):
             W = params[3 * l].reshape(params[3 * l].shape[0], -1)
             need_stats = training or not bns[l].track_running_stats
-            if l == 0 and k % 4 != 0 and A.shape[1] >= (k + 3) // 4 * 4:
-                # the producer zero-padded the rows to a multiple of 4 columns: pad the weight to match (TMA path)
-                k4 = (k + 3) // 4 * 4
-                W = torch.nn.functional.pad(W, (0, k4 - k))
-                k = k4
+            if l == 0:  # the weight in the column layout of the rows (zero columns where the rows are padding)
+                W, k = _first_layer_weight(W, K, A.shape[1], xyz_gap)
             res = _ext_mlp.mlp_layer_fwd(A, W, scale, shift, want_stats=need_stats, K=k)
             Y, s1, s2 = res if need_stats else (res, None, None)
             mean, invstd, scale, shift = _bn_coefficients(s1, s2, R, bns[l], training)
@@ -49,12 +85,13 @@ class _FusedMLPPool(Function):
             A, k = Y, W.shape[0]
         pooled, argmax = _ext_mlp.pool_fwd(Ys[-1], G, ns, scale, shift, want_argmax=True)
         ctx.save_for_backward(rows, argmax, *Ys, *[t for c in coefs for t in c], *params)
-        ctx.meta = (K, G, ns, L, bool(training), [bool(training or not b.track_running_stats) for b in bns])
+        ctx.meta = (K, G, ns, L, bool(training), [bool(training or not b.track_running_stats) for b in bns],
+                    bool(xyz_gap), bool(need_xyz_grad))
         return pooled
 
     @staticmethod
     def backward(ctx, dpool):
-        K, G, ns, L, training, batch_stats = ctx.meta
+        K, G, ns, L, training, batch_stats, xyz_gap, need_xyz_grad = ctx.meta
         saved = ctx.saved_tensors
         rows, argmax = saved[0], saved[1]
         Ys = saved[2:2 + L]
@@ -102,11 +139,35 @@ class _FusedMLPPool(Function):
                     g = torch.zeros((G, ns, Y.shape[1]), dtype=dpool.dtype, device=dpool.device)
                     g.scatter_(1, argmax.long().unsqueeze(1), dpool.unsqueeze(1))
                     g = g.view(R, -1) * (torch.addcmul(coefs[l][3], Y, coefs[l][2]) > 0)
-                if (l == 0 and not ctx.needs_input_grad[0] and
-                        _ext_mlp.bwd_weight_supported(Y.shape[1], K, g.stride(0), Y.stride(0), rows.stride(0))):
-                    # first layer, no gradient w.r.t. the input (SA1): dY is formed inside the weight-gradient kernel
-                    grads[0] = _ext_mlp.mlp_layer_bwd_weight(g, rows, K, a=a, b=b, c=c, Y=Y).view_as(params[0])
-                    break
+                if l == 0:
+                    Wp, Kp = _first_layer_weight(W, K, rows.shape[1], xyz_gap)
+                    blocks = _input_blocks(K, rows.shape[1], xyz_gap) if ctx.needs_input_grad[0] else None
+                    if (not ctx.needs_input_grad[0] and
+                            _ext_mlp.bwd_weight_supported(Y.shape[1], Kp, g.stride(0), Y.stride(0), rows.stride(0))):
+                        # no gradient w.r.t. the input (SA1): dY is formed inside the weight-gradient kernel
+                        dWp = _ext_mlp.mlp_layer_bwd_weight(g, rows, Kp, a=a, b=b, c=c, Y=Y)
+                        grads[0] = _first_layer_weight_grad(dWp, K, xyz_gap).reshape(params[0].shape)
+                        break
+                    if blocks is not None and _ext_mlp.bwd_data_supported(Y.shape[1], 64):
+                        # input gradient on the tensor cores, block by block, straight into the (R, lda) gradient rows
+                        grad_rows = torch.empty_like(rows)
+                        dY = None
+                        for i, (c0, w) in enumerate(blocks):
+                            d = _ext_mlp.mlp_layer_bwd_input(g, Y, a, b, c, Wp, c0, w, grad_rows, want_dY=(i == 0))
+                            dY = d if i == 0 else dY
+                        if xyz_gap:
+                            if need_xyz_grad:
+                                grad_rows[:, :4] = dY @ Wp[:, :4]
+                            else:
+                                grad_rows[:, :4] = 0.0
+                            if rows.shape[1] > 4 + K - 3:
+                                grad_rows[:, 4 + K - 3:] = 0.0
+                        if _ext_mlp.bwd_weight_supported(Y.shape[1], Kp, dY.stride(0), rows.stride(0)):
+                            dWp = _ext_mlp.mlp_layer_bwd_weight(dY, rows, Kp)
+                        else:
+                            dWp = dY.t() @ rows[:, :Kp]
+                        grads[0] = _first_layer_weight_grad(dWp, K, xyz_gap).reshape(params[0].shape)
+                        break
                 dY = torch.addcmul(c, g, a).addcmul_(Y, b)
                 if l > 0:
                     _, _, sc_p, sh_p = coefs[l - 1]
@@ -116,26 +177,30 @@ class _FusedMLPPool(Function):
                     sum_g = g.sum(0, dtype=torch.float64)
                     sum_gy = (g * Ys[l - 1]).sum(0, dtype=torch.float64)
                 else:
-                    if _ext_mlp.bwd_weight_supported(Y.shape[1], K, dY.stride(0), rows.stride(0)):
-                        grads[0] = _ext_mlp.mlp_layer_bwd_weight(dY, rows, K).view_as(params[0])
+                    Wp, Kp = _first_layer_weight(W, K, rows.shape[1], xyz_gap)
+                    if _ext_mlp.bwd_weight_supported(Y.shape[1], Kp, dY.stride(0), rows.stride(0)):
+                        dWp = _ext_mlp.mlp_layer_bwd_weight(dY, rows, Kp)
                     else:
-                        grads[0] = (dY.t() @ rows[:, :K]).view_as(params[0])
+                        dWp = dY.t() @ rows[:, :Kp]
+                    grads[0] = _first_layer_weight_grad(dWp, K, xyz_gap).reshape(params[0].shape)
                     if ctx.needs_input_grad[0]:
-                        grad_rows = dY @ W
-                        if rows.shape[1] != K:
-                            grad_rows = torch.nn.functional.pad(grad_rows, (0, rows.shape[1] - K))
+                        grad_rows = dY @ Wp
+                        if rows.shape[1] != Kp:
+                            grad_rows = torch.nn.functional.pad(grad_rows, (0, rows.shape[1] - Kp))
             l -= 1
-        return (grad_rows, None, None, None, None, None) + tuple(grads)
+        return (grad_rows, None, None, None, None, None, None, None) + tuple(grads)
 
 
-def fused_mlp_maxpool(rows, K, G, ns, layers, training):
-    """rows (G*ns, >=K) -> (G, C_last): SharedMLP `layers` = [(conv, bn)] then max over each group's ns rows."""
+def fused_mlp_maxpool(rows, K, G, ns, layers, training, xyz_gap=False, need_xyz_grad=True):
+    """rows (G*ns, >=K) -> (G, C_last): SharedMLP `layers` = [(conv, bn)] then max over each group's ns rows.
+    xyz_gap: the rows are [x, y, z, 0 | K-3 features | zero pad] (the padded layout of the fused query+group kernel);
+    need_xyz_grad=False skips the gradient of the three coordinate columns (no grad flows to xyz / new_xyz)."""
     params, bns = [], []
     for conv, bn in layers:
         assert conv.bias is None and bn is not None, "fused path: conv without bias followed by BatchNorm"
         params += [conv.weight, bn.weight, bn.bias]
         bns.append(bn)
-    return _FusedMLPPool.apply(rows, K, G, ns, training, bns, *params)
+    return _FusedMLPPool.apply(rows, K, G, ns, training, bns, xyz_gap, need_xyz_grad, *params)
 
 
 def fusable(layers):

@@ -111,10 +111,12 @@ class PointnetSAModuleVotes(nn.Module):
                                                      self.normalize_xyz, True, True, use_fused)
         B, C, M, ns = grouped.shape
         if use_fused:
-            # rows of the zero-padded, 16-byte aligned channels-last buffer the kernel wrote: (R, Cp), Cin valid
+            # rows of the 16-byte aligned channels-last buffer the kernel wrote: (R, Cp) = [xyz, 0 | features | pad]
             Cin = 3 + (feats_pm.shape[2] if feats_pm is not None else 0)
             rows = grouped.permute(0, 2, 3, 1).reshape(B * M * ns, C)
-            pooled = fused_mlp.fused_mlp_maxpool(rows, Cin, B * M, ns, layers, self.training).view(B, M, -1)
+            pooled = fused_mlp.fused_mlp_maxpool(rows, Cin, B * M, ns, layers, self.training, xyz_gap=True,
+                                                 need_xyz_grad=xyz.requires_grad or new_xyz.requires_grad
+                                                 ).view(B, M, -1)
         else:
             rows = grouped.permute(0, 2, 3, 1).reshape(B * M * ns, C)  # a view: the kernel wrote channels-last
             out = shared_mlp_rows(rows, layers, self.training)

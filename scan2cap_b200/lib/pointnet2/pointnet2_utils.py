@@ -119,6 +119,7 @@ class _FusedQueryAndGroup(Function):
         ctx.scale = (1.0 / radius) if normalize_xyz else 1.0
         ctx.feat_point_major = feat_point_major
         ctx.has_feat = features is not None
+        ctx.feat_col = 4 if (pad4 and channels_last) else 3  # first feature column of the grouped rows
         ctx.C = 0 if features is None else (features.shape[2] if feat_point_major else features.shape[1])
         ctx.mark_non_differentiable(idx)
         return grouped, idx
@@ -138,7 +139,7 @@ class _FusedQueryAndGroup(Function):
             if ctx.needs_input_grad[1]:
                 g_new = -(grad[:, :3].sum(-1) * ctx.scale).transpose(1, 2)
             if ctx.has_feat and ctx.needs_input_grad[2]:
-                g_feat = _ext_mlp.group_rows_grad(rows, 3, ctx.C, idx, n)  # (B,n,C)
+                g_feat = _ext_mlp.group_rows_grad(rows, ctx.feat_col, ctx.C, idx, n)  # (B,n,C)
                 if not ctx.feat_point_major:
                     g_feat = g_feat.transpose(1, 2)
             return g_xyz, g_new, g_feat, None, None, None, None, None, None
@@ -149,7 +150,7 @@ class _FusedQueryAndGroup(Function):
             if ctx.needs_input_grad[1]:
                 g_new = -gx.sum(-1).transpose(1, 2)
         if ctx.has_feat and ctx.needs_input_grad[2]:
-            g_feat = _ext.group_points_grad(grad[:, 3:3 + ctx.C].contiguous(), idx, n)  # (B,C,n)
+            g_feat = _ext.group_points_grad(grad[:, ctx.feat_col:ctx.feat_col + ctx.C].contiguous(), idx, n)  # (B,C,n)
             if ctx.feat_point_major:
                 g_feat = g_feat.transpose(1, 2)
         return g_xyz, g_new, g_feat, None, None, None, None, None, None

@@ -139,3 +139,40 @@ def test_bn_coefficient_kernels_match_torch_batchnorm(training):
     torch.testing.assert_close(gb, bn_ref.bias.grad, rtol=1e-4, atol=1e-4)
     dy = a * g + b * y.detach() + c
     torch.testing.assert_close(dy, y.grad, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Cf,widths,ns,need_xyz", [(128, (128, 128, 256), 32, True), (256, (128, 128, 128), 16, True),
+                                                  (256, (128, 128, 256), 16, False), (4, (64, 64, 128), 64, True)])
+def test_fused_mlp_gap_layout_matches_torch_path(Cf, widths, ns, need_xyz):
+    """Rows in the padded layout of the fused query+group kernel, [x, y, z, 0 | features | pad]: forward, and the
+    backward with the first layer's input gradient on the tensor-core kernel (s2c_mlp_layer_bwd_input)."""
+    import copy
+    from scan2cap_b200.lib.pointnet2 import pytorch_utils as pt_utils
+    from scan2cap_b200.lib.pointnet2.fused_mlp import fused_mlp_maxpool
+    from scan2cap_b200.lib.pointnet2.pointnet2_modules import shared_mlp_rows
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(11)
+    G = 96
+    R = G * ns
+    mlp_a = pt_utils.SharedMLP([3 + Cf] + list(widths), bn=True).to(DEV)
+    mlp_b = copy.deepcopy(mlp_a)
+    x_a = torch.randn(R, 3 + Cf, device=DEV, requires_grad=True)
+    x_b = x_a.detach().clone().requires_grad_(True)
+    Cp = 4 + (Cf + 3) // 4 * 4
+    rows = torch.cat([x_a[:, :3], x_a.new_zeros(R, 1), x_a[:, 3:], x_a.new_zeros(R, Cp - 4 - Cf)], 1)
+    gout = torch.randn(G, widths[-1], device=DEV)
+    out_a = fused_mlp_maxpool(rows, 3 + Cf, G, ns, mlp_a.layer_params(), True, xyz_gap=True, need_xyz_grad=need_xyz)
+    out_b = shared_mlp_rows(x_b, mlp_b.layer_params(), True).view(G, ns, -1).amax(1)
+    rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-12))
+    assert rel(out_a, out_b) < 1e-4
+    (out_a * gout).sum().backward()
+    (out_b * gout).sum().backward()
+    l2 = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-12))
+    assert l2(x_a.grad[:, 3:], x_b.grad[:, 3:]) < 5e-3
+    if need_xyz:
+        assert l2(x_a.grad[:, :3], x_b.grad[:, :3]) < 5e-3
+    else:
+        assert float(x_a.grad[:, :3].abs().max()) == 0.0
+    for (n, pa), (_, pb) in zip(mlp_a.named_parameters(), mlp_b.named_parameters()):
+        assert l2(pa.grad, pb.grad) < 5e-3, n

@@ -118,14 +118,15 @@ def test_query_and_group_fused(feat_pm, cl, C, normalize, n, ext, oracle):
     np.testing.assert_array_equal(N(gidx), idx)
     assert grouped.shape == (2, 3 + C, M, ns)
     np.testing.assert_array_equal(N(grouped), want)
-    if cl:  # padded variant: rows rounded up to 4 floats, pad columns exactly zero
+    if cl:  # padded variant: rows [x, y, z, 0 | features | zero pad], 16-byte aligned rows and feature block
         gp, gidx2 = ext.query_and_group(T(xyz), T(new_xyz), f, r, ns, normalize, feat_point_major=feat_pm,
                                         channels_last=True, pad4=True)
-        Cp = (3 + C + 3) // 4 * 4
+        Cp = 4 + (C + 3) // 4 * 4
         assert gp.shape == (2, Cp, M, ns) and gp.permute(0, 2, 3, 1).is_contiguous()
         np.testing.assert_array_equal(N(gidx2), idx)
-        np.testing.assert_array_equal(N(gp[:, :3 + C]), want)
-        assert float(gp[:, 3 + C:].abs().sum()) == 0.0
+        np.testing.assert_array_equal(N(gp[:, :3]), want[:, :3])
+        np.testing.assert_array_equal(N(gp[:, 4:4 + C]), want[:, 3:])
+        assert float(gp[:, 3].abs().sum()) == 0.0 and float(gp[:, 4 + C:].abs().sum()) == 0.0
 
 
 # ------------------------------------------------------------------ three_nn / interpolate / gather / group

@@ -274,10 +274,13 @@ typedef struct s2c_caption_params {
   const float *pre_word, *pre_tgt, *mapped, *obj, *valid;
   const float *w_tdh, *w_ih1, *w_hh1, *b_ih1, *b_hh1, *w_hidd, *w_att, *w_lang, *b_lang, *w_ih2, *w_hh2, *b_ih2, *b_hh2;
   float *u, *h1, *r1, *z1, *n1, *hn1, *q, *probs, *att, *lang, *r2, *z2, *n2, *hn2, *h2;
+  float *scores; /* (T,B,K) scratch: raw attention scores exchanged between the CTAs of the cluster */
   /* backward only */
   const float *wt_tdh, *wt_ih1, *wt_hh1, *wt_hidd, *wt_lang, *wt_ih2, *wt_hh2;
   const float *d_h2, *d_probs;
   float *dgi2, *dgh2, *dlang, *datt, *dq, *dgi1, *dgh1, *du, *d_mapped, *d_obj, *d_watt;
+  /* optional profiling aid: (T, 8) %globaltimer stamps (ns) taken by CTA 0 at the stage boundaries of every word */
+  long long *dbg_ts;
 } s2c_caption_params;
 S2C_API int s2c_caption_decode_fwd(const s2c_caption_params *params, void *stream);
 S2C_API int s2c_caption_decode_bwd(const s2c_caption_params *params, void *stream);
@@ -297,6 +300,10 @@ S2C_API int s2c_gemm_tn(const float *A, long long lda, const float *X, long long
 S2C_API int s2c_mlp_layer_bwd_input(const float *G, long long ldg, const float *Y, long long ldy, long long R, int K,
                                     const float *a, const float *b, const float *c, const float *W, long long ldw, int N,
                                     float *C, long long ldc, float *dY_out, void *wprep, void *stream);
+
+/* col_sum -- out[c] = sum_r A[r, c] for a tall fp32 matrix A (R, lda), M columns: the bias gradient of a Linear /
+ *   Conv1d layer (ATen's sum(0) under autograd).  out is zero-filled here (fp32 atomics over row chunks). */
+S2C_API int s2c_col_sum(const float *A, long long lda, long long R, int M, float *out, void *stream);
 
 #ifdef __cplusplus
 }

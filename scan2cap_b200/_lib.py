@@ -38,6 +38,7 @@ SIGNATURES = {
     "s2c_bn_backward_coeffs": [P, P, P, P, P, c_ll, c_int, c_int, P, P, P, P, P, P],
     "s2c_group_rows_grad": [P, c_ll, c_int, c_int, P, c_int, c_ll, c_int, c_float, P, P],
     "s2c_mlp_layer_bwd_input": [P, c_ll, P, c_ll, c_ll, c_int, P, P, P, P, c_ll, c_int, P, c_ll, P, P, P],
+    "s2c_col_sum": [P, c_ll, c_ll, c_int, P, P],
     "s2c_gemm_tn": [P, c_ll, P, c_ll, c_int, c_int, c_int, P, c_ll, P, P],
     "s2c_caption_decode_fwd": [P, P],
     "s2c_caption_decode_bwd": [P, P],
@@ -49,12 +50,12 @@ class CaptionParams(ctypes.Structure):
     """struct s2c_caption_params of include/s2c.h (field order matters)."""
     _PTRS = ("pre_word pre_tgt mapped obj valid "
              "w_tdh w_ih1 w_hh1 b_ih1 b_hh1 w_hidd w_att w_lang b_lang w_ih2 w_hh2 b_ih2 b_hh2 "
-             "u h1 r1 z1 n1 hn1 q probs att lang r2 z2 n2 hn2 h2 "
+             "u h1 r1 z1 n1 hn1 q probs att lang r2 z2 n2 hn2 h2 scores "
              "wt_tdh wt_ih1 wt_hh1 wt_hidd wt_lang wt_ih2 wt_hh2 "
              "d_h2 d_probs "
              "dgi2 dgh2 dlang datt dq dgi1 dgh1 du d_mapped d_obj d_watt").split()
     _fields_ = ([(n, c_int) for n in ("B", "T", "K", "E", "H", "F")] + [("ld_tdh", c_ll)] +
-                [(n, c_void_p) for n in _PTRS])
+                [(n, c_void_p) for n in _PTRS] + [("dbg_ts", c_void_p)])
 
 
 class S2CError(RuntimeError):

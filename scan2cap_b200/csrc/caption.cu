@@ -40,6 +40,13 @@ __device__ __forceinline__ float4 ldw4(const float *p) {  // weights: read-only 
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
+__device__ __forceinline__ void stamp(long long *ts, int c, int t, int slot) {
+  if (ts != nullptr && c == 0 && threadIdx.x == 0) {
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    ts[t * 8 + slot] = (long long)v;
+  }
+}
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // out[i][r] = sum_k w_i[k] * x[r][k], i < 4, r < 8.  x: shared memory, row stride xld (multiple of 4), K % 4 == 0.
@@ -117,14 +124,23 @@ using namespace s2c;
 namespace s2c {
 namespace {
 
-// Shared-memory plan (floats): XA[8][XLD] | XB[8][XLD] | G[6*hs][8] | probs[8][K] | sc[8][K] | att[8][F] | vk[8][K] (int) | nv[8] | flag[8]
-//   forward:  XLD = max(F+H, H) ; backward: XLD = 3H
-constexpr int kMaxPairs = 128;  // (row, valid proposal) pairs whose feature rows are cached in shared memory
+// Shared-memory plan (floats): XA[8][XLD] | XB[8][XLD] | G[6*hs][8] | probs[8][K] | sc[8][K] | att[8][F] | vk[8][K] (int) |
+//   nv[8] | uniform[8] | pb[12] | pair_r[kMaxPairs] | pair_k[kMaxPairs] | objs | mcache | dmacc
+//   forward: XLD = F+H ; backward: XLD = 3H.  The valid set of every scene is constant over the words, so (cache
+//   level >= 1) the valid proposals' feature rows and (level 2) their map_feat rows -- forward: this CTA's share of the
+//   (row, proposal) pairs, whole rows; backward: all pairs, this CTA's hidden units, plus the d_mapped accumulators --
+//   stay in shared memory for the whole kernel.
+constexpr int kMaxPairs = 96;  // (row, valid proposal) pairs the caches hold (8 scenes x (10 locals + self) = 88)
 struct SmemPlan {
-  float *XA, *XB, *G, *probs, *sc, *att, *objs;
-  int *vk, *nv, *uniform, *pb;  // pb[r]: first pair of row r; pb[8]: total (or -1 when the cache is not used)
+  float *XA, *XB, *G, *probs, *sc, *att, *objs, *mcache, *dmacc;
+  int *vk, *nv, *uniform, *pb;  // pb[r]: first pair of row r; pb[8]: total pairs, or -1 when the caches are off
+  int *pair_r, *pair_k;
+  int level;
 };
-__device__ __forceinline__ SmemPlan plan(float *base, int xld, int hs, int K, int F) {
+__host__ __device__ __forceinline__ size_t mcache_floats(bool bwd, int CL, int hs, int H) {
+  return bwd ? (size_t)kMaxPairs * hs : (size_t)((kMaxPairs + CL - 1) / CL) * H;
+}
+__device__ __forceinline__ SmemPlan plan(float *base, int xld, int hs, int K, int F, int H, int CL, bool bwd, int level) {
   SmemPlan p;
   p.XA = base; base += kRows * xld;
   p.XB = base; base += kRows * xld;
@@ -136,12 +152,20 @@ __device__ __forceinline__ SmemPlan plan(float *base, int xld, int hs, int K, in
   p.nv = reinterpret_cast<int *>(base); base += kRows;
   p.uniform = reinterpret_cast<int *>(base); base += kRows;
   p.pb = reinterpret_cast<int *>(base); base += 12;
-  p.objs = base;
+  p.pair_r = reinterpret_cast<int *>(base); base += kMaxPairs;
+  p.pair_k = reinterpret_cast<int *>(base); base += kMaxPairs;
+  p.objs = base; base += level >= 1 ? (size_t)kMaxPairs * F : 0;
+  p.mcache = base; base += level >= 2 ? mcache_floats(bwd, CL, hs, H) : 0;
+  p.dmacc = base;
+  p.level = level;
   return p;
 }
-size_t plan_bytes(int xld, int hs, int K, int F) {
-  return sizeof(float) * ((size_t)2 * kRows * xld + (size_t)6 * hs * kRows + (size_t)3 * kRows * K + (size_t)kRows * F + 2 * kRows + 12 +
-                          (size_t)kMaxPairs * F) + 16;
+size_t plan_bytes(int xld, int hs, int K, int F, int H, int CL, bool bwd, int level) {
+  size_t fl = (size_t)2 * kRows * xld + (size_t)6 * hs * kRows + (size_t)3 * kRows * K + (size_t)kRows * F + 2 * kRows + 12 +
+              2 * kMaxPairs;
+  if (level >= 1) fl += (size_t)kMaxPairs * F;
+  if (level >= 2) fl += mcache_floats(bwd, CL, hs, H) * (bwd ? 2 : 1);
+  return sizeof(float) * fl + 16;
 }
 
 // valid-object lists of the cluster's rows (constant over the steps).  A row without any valid object gets the
@@ -176,11 +200,16 @@ __device__ __forceinline__ void build_valid_lists(const SmemPlan &sp, const floa
   if (threadIdx.x == 0) {
     int tot = 0;
     for (int r = 0; r < kRows; ++r) { sp.pb[r] = tot; tot += sp.nv[r]; }
-    sp.pb[kRows] = tot <= kMaxPairs ? tot : -1;
+    sp.pb[kRows] = (sp.level >= 1 && tot <= kMaxPairs) ? tot : -1;
   }
   __syncthreads();
   if (sp.pb[kRows] >= 0) {  // the valid set is the same for every word: keep those proposals' features on chip
     const int f4 = F >> 2;
+    for (int r = 0; r < kRows; ++r)
+      for (int ii = threadIdx.x; ii < sp.nv[r]; ii += kThreads) {
+        sp.pair_r[sp.pb[r] + ii] = r;
+        sp.pair_k[sp.pb[r] + ii] = sp.vk[r * K + ii];
+      }
     for (int r = 0; r < nb; ++r) {
       const int n = sp.nv[r];
       for (int i = threadIdx.x; i < n * f4; i += kThreads) {
@@ -202,7 +231,7 @@ __device__ __forceinline__ const float *obj_row(const SmemPlan &sp, const float 
 // ================================================================== forward
 template <int CL>
 __global__ void __launch_bounds__(kThreads, 1)
-caption_fwd_kernel(const s2c_caption_params P) {
+caption_fwd_kernel(const s2c_caption_params P, const int level) {
   extern __shared__ __align__(16) float smem[];
   const int B = P.B, T = P.T, K = P.K, E = P.E, H = P.H, F = P.F;
   const int c = (int)cl_rank();
@@ -211,14 +240,28 @@ caption_fwd_kernel(const s2c_caption_params P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Slices S = make_slices(c, CL, H, E, F);
   const int XLD = F + H;
-  const SmemPlan sp = plan(smem, XLD, S.hs, K, F);
+  const SmemPlan sp = plan(smem, XLD, S.hs, K, F, H, CL, false, level);
   build_valid_lists(sp, P.valid, P.obj, rb, nb, K, F);
   const int li = lane >> 3, lr = lane & 7;  // this lane's (row-in-quad, batch row) after gemv_quad
+  // level 2: the (row, proposal) pairs are dealt round-robin to the CTAs; each keeps the map_feat rows of its pairs
+  const bool split = level >= 2 && sp.pb[kRows] >= 0;
+  const int n_own = split ? (sp.pb[kRows] - c + CL - 1) / CL : 0;
+  if (split) {
+    const int h4 = H >> 2;
+    for (int i = threadIdx.x; i < n_own * h4; i += kThreads) {
+      const int o = i / h4, hh = (i - o * h4) * 4;
+      const int p = c + o * CL;
+      *reinterpret_cast<float4 *>(sp.mcache + (size_t)o * H + hh) = __ldg(reinterpret_cast<const float4 *>(
+          P.mapped + ((size_t)(rb + sp.pair_r[p]) * K + sp.pair_k[p]) * H + hh));
+    }
+    __syncthreads();
+  }
 
   for (int t = 0; t < T; ++t) {
     const size_t tb = (size_t)t * B + rb;  // first (t, b) row of this cluster in the (T,B,.) buffers
     const size_t tb_prev = (size_t)(t - 1) * B + rb;
     // ---- S1: u = relu(pre_word_t + pre_tgt + W_tdh h2)
+    stamp(P.dbg_ts, c, t, 0);
     load_rows(sp.XB, XLD, t > 0 ? P.h2 + tb_prev * H : nullptr, H, H, nb);
     __syncthreads();
     for (int q = warp; q * 4 < S.e1 - S.e0; q += kWarps) {
@@ -230,8 +273,10 @@ caption_fwd_kernel(const s2c_caption_params P) {
         P.u[(tb + lr) * E + ee] = fmaxf(pre, 0.f);
       }
     }
+    stamp(P.dbg_ts, c, t, 1);
     cl_sync();
     // ---- S2: GRU cell 1 on (u, h1_prev)
+    stamp(P.dbg_ts, c, t, 2);
     load_rows(sp.XA, XLD, P.u + tb * E, E, E, nb);
     load_rows(sp.XB, XLD, t > 0 ? P.h1 + tb_prev * H : nullptr, H, H, nb);
     __syncthreads();
@@ -260,6 +305,7 @@ caption_fwd_kernel(const s2c_caption_params P) {
         P.r1[o] = rg; P.z1[o] = zg; P.n1[o] = ng; P.hn1[o] = ghn; P.h1[o] = hn;
       }
     }
+    stamp(P.dbg_ts, c, t, 3);
     cl_sync();
     // ---- S3: q = W_hidd h1
     load_rows(sp.XB, XLD, P.h1 + tb * H, H, H, nb);
@@ -270,10 +316,34 @@ caption_fwd_kernel(const s2c_caption_params P) {
       if (lr < nb) P.q[(tb + lr) * H + j + li] = v;
     }
     cl_sync();
+    stamp(P.dbg_ts, c, t, 4);
     // ---- S4: attention over the valid objects (every CTA, redundantly), then l = relu(W_lang [att ; h1] + b)
     load_rows(sp.XA, XLD, P.q + tb * H, H, H, nb);
     __syncthreads();
     {
+      if (split) {
+        // scores of this CTA's pairs (map_feat rows on chip), published through `scores`; one more cluster barrier
+        for (int o = warp; o < n_own; o += kWarps) {
+          const int p = c + o * CL, r = sp.pair_r[p];
+          const float *mp = sp.mcache + (size_t)o * H;
+          float s = 0.f;
+          for (int h = lane * 4; h < H; h += 128) {
+            const float4 m4 = *reinterpret_cast<const float4 *>(mp + h);
+            const float4 qv = *reinterpret_cast<const float4 *>(sp.XA + r * XLD + h);
+            const float4 wv = __ldg(reinterpret_cast<const float4 *>(P.w_att + h));
+            s = fmaf(tanhf(m4.x + qv.x), wv.x, s); s = fmaf(tanhf(m4.y + qv.y), wv.y, s);
+            s = fmaf(tanhf(m4.z + qv.z), wv.z, s); s = fmaf(tanhf(m4.w + qv.w), wv.w, s);
+          }
+#pragma unroll
+          for (int o2 = 16; o2; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
+          if (lane == 0 && r < nb) P.scores[(tb + r) * K + sp.pair_k[p]] = s;
+        }
+        cl_sync();
+        for (int p = threadIdx.x; p < sp.pb[kRows]; p += kThreads) {
+          const int r = sp.pair_r[p];
+          if (r < nb) sp.sc[r * K + p - sp.pb[r]] = __ldcg(P.scores + (tb + r) * K + sp.pair_k[p]);
+        }
+      } else {
       // scores: one warp per (row, valid object)
       for (int r = 0; r < nb; ++r) {
         const int n = sp.nv[r];
@@ -305,6 +375,8 @@ caption_fwd_kernel(const s2c_caption_params P) {
             if (lane == 0) sp.sc[r * K + i] = s;
           }
         }
+      }
+      __syncthreads();
       }
       __syncthreads();
       if (warp < nb) {  // softmax of row r = warp over its valid list
@@ -351,6 +423,7 @@ caption_fwd_kernel(const s2c_caption_params P) {
       }
       __syncthreads();
     }
+    stamp(P.dbg_ts, c, t, 5);
     for (int q = warp; q * 4 < S.e1 - S.e0; q += kWarps) {
       const int e = S.e0 + q * 4;
       const float v = gemv_quad(S2C_QUAD_PTRS(P.w_lang, F + H, e, S.e1), F + H, sp.XA, XLD, lane);
@@ -358,6 +431,7 @@ caption_fwd_kernel(const s2c_caption_params P) {
       if (ee < S.e1 && lr < nb) P.lang[(tb + lr) * E + ee] = fmaxf(v + P.b_lang[ee], 0.f);
     }
     cl_sync();
+    stamp(P.dbg_ts, c, t, 6);
     // ---- S5: GRU cell 2 on (l, h2_prev)
     load_rows(sp.XA, XLD, P.lang + tb * E, E, E, nb);
     load_rows(sp.XB, XLD, t > 0 ? P.h2 + tb_prev * H : nullptr, H, H, nb);
@@ -395,7 +469,7 @@ caption_fwd_kernel(const s2c_caption_params P) {
 // Transposed weights (row-major): wt_tdh (H,E), wt_ih* (E,3H), wt_hh* (H,3H), wt_hidd (H,H), wt_lang (F+H,E).
 template <int CL>
 __global__ void __launch_bounds__(kThreads, 1)
-caption_bwd_kernel(const s2c_caption_params P) {
+caption_bwd_kernel(const s2c_caption_params P, const int level) {
   extern __shared__ __align__(16) float smem[];
   const int B = P.B, T = P.T, K = P.K, E = P.E, H = P.H, F = P.F;
   const int c = (int)cl_rank();
@@ -405,12 +479,21 @@ caption_bwd_kernel(const s2c_caption_params P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Slices S = make_slices(c, CL, H, E, F);
   const int XLD = 3 * H;
-  const SmemPlan sp = plan(smem, XLD, S.hs, K, F);
+  const SmemPlan sp = plan(smem, XLD, S.hs, K, F, H, CL, true, level);
   // carried gradients of this CTA's hidden units: acc1/acc2 [hs][8] live in G's tail? -> dedicated arrays in G:
   // G layout here: [0, hs*8): dh1 carried / total, [hs*8, 2*hs*8): dh2 carried / total, [2*hs*8, 3*hs*8): scratch
   float *d1 = sp.G, *d2 = sp.G + S.hs * kRows, *dsv = sp.sc;  // dsv[r][i]: d score of (row, i-th valid object)
   build_valid_lists(sp, P.valid, P.obj, rb, nb, K, F);
   for (int i = threadIdx.x; i < 2 * S.hs * kRows; i += kThreads) sp.G[i] = 0.f;
+  // level 2: map_feat values of all valid pairs for this CTA's hidden units, and their gradient accumulators, on chip
+  const bool mc_on = level >= 2 && sp.pb[kRows] >= 0;
+  if (mc_on) {
+    for (int i = threadIdx.x; i < sp.pb[kRows] * S.hs; i += kThreads) {
+      const int p = i / S.hs, jl = i - p * S.hs;
+      sp.mcache[i] = __ldg(P.mapped + ((size_t)(rb + sp.pair_r[p]) * K + sp.pair_k[p]) * H + S.j0 + jl);
+      sp.dmacc[i] = 0.f;
+    }
+  }
   __syncthreads();
   const int li = lane >> 3, lr = lane & 7;
   float dwatt = 0.f;  // thread (jl = tid/8, r = tid%8) of the first hs*8 threads: partial d w_att[j0+jl]
@@ -513,7 +596,17 @@ caption_bwd_kernel(const s2c_caption_params P) {
       if (r < nb) {
         const float qv = P.q[(tb + r) * H + j], wa = P.w_att[j];
         float dq = 0.f;
-        if (!sp.uniform[r]) {
+        if (!sp.uniform[r] && mc_on) {
+          const int n = sp.nv[r], p0 = sp.pb[r];
+          for (int ii = 0; ii < n; ++ii) {
+            const float cb = tanhf(sp.mcache[(p0 + ii) * S.hs + jl] + qv);
+            const float ds = dsv[r * K + ii];
+            const float dpre = ds * wa * (1.f - cb * cb);
+            sp.dmacc[(p0 + ii) * S.hs + jl] += dpre;
+            dq += dpre;
+            dwatt = fmaf(ds, cb, dwatt);
+          }
+        } else if (!sp.uniform[r]) {
           const int n = sp.nv[r];
           for (int i0 = 0; i0 < n; i0 += 4) {  // 4 proposals at a time: all loads issued before the first use
             float mv[4], dm[4];
@@ -609,6 +702,13 @@ caption_bwd_kernel(const s2c_caption_params P) {
     }
     __syncthreads();
   }
+  if (mc_on) {  // the accumulated d_mapped of the valid pairs, written once
+    __syncthreads();
+    for (int i = threadIdx.x; i < sp.pb[kRows] * S.hs; i += kThreads) {
+      const int p = i / S.hs, jl = i - p * S.hs;
+      if (sp.pair_r[p] < nb) P.d_mapped[((size_t)(rb + sp.pair_r[p]) * K + sp.pair_k[p]) * H + S.j0 + jl] += sp.dmacc[i];
+    }
+  }
   // d w_att: sum the per-(unit,row) partials over the 8 rows; one slot per cluster (summed by the caller)
   if (threadIdx.x < S.hs * kRows) {
     float v = dwatt;
@@ -623,7 +723,9 @@ template <int CL, bool BWD>
 int launch_caption(const s2c_caption_params &P, cudaStream_t st, bool probe_only) {
   auto kern = BWD ? caption_bwd_kernel<CL> : caption_fwd_kernel<CL>;
   const int xld = BWD ? 3 * P.H : P.F + P.H;
-  const size_t smem = plan_bytes(xld, P.H / CL, P.K, P.F);
+  int level = 2;  // the highest cache level whose shared-memory plan fits
+  while (level > 0 && plan_bytes(xld, P.H / CL, P.K, P.F, P.H, CL, BWD, level) > 227 * 1024) --level;
+  const size_t smem = plan_bytes(xld, P.H / CL, P.K, P.F, P.H, CL, BWD, level);
   if (smem > 227 * 1024) return -1;
   S2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "caption smem attr");
   if (CL > 8) S2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1), "caption cluster attr");
@@ -643,7 +745,7 @@ int launch_caption(const s2c_caption_params &P, cudaStream_t st, bool probe_only
     if (e != cudaSuccess) { cudaGetLastError(); return -1; }
     return n > 0 ? 0 : -1;
   }
-  S2C_CUDA(cudaLaunchKernelEx(&cfg, kern, P), BWD ? "caption_decode_bwd launch" : "caption_decode_fwd launch");
+  S2C_CUDA(cudaLaunchKernelEx(&cfg, kern, P, level), BWD ? "caption_decode_bwd launch" : "caption_decode_fwd launch");
   return S2C_OK;
 }
 
@@ -675,7 +777,7 @@ extern "C" int s2c_caption_decode_fwd(const s2c_caption_params *P, void *stream)
                   P->b_ih2 && P->b_hh2,
               "caption_decode_fwd: null input");
   S2C_REQUIRE(P->u && P->h1 && P->r1 && P->z1 && P->n1 && P->hn1 && P->q && P->probs && P->att && P->lang && P->r2 &&
-                  P->z2 && P->n2 && P->hn2 && P->h2,
+                  P->z2 && P->n2 && P->hn2 && P->h2 && P->scores,
               "caption_decode_fwd: null output");
   return dispatch<false>(*P, (cudaStream_t)stream);
 }

@@ -70,3 +70,37 @@ extern "C" int s2c_gemm_tn(const float *A, long long lda, const float *X, long l
   S2C_CHECK_LAUNCH("gemm_tn");
   return S2C_OK;
 }
+
+// Column sums of a tall matrix (bias gradients of the Linear / Conv1d layers): out[c] = sum_r A[r, c].
+namespace s2c {
+namespace {
+__global__ void __launch_bounds__(256)
+col_sum_kernel(const float *__restrict__ A, long long lda, long long R, int M, long long rows_per_cta, float *__restrict__ out) {
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = r0 + rows_per_cta < R ? r0 + rows_per_cta : R;
+  for (int c = threadIdx.x; c < M; c += 256) {
+    float s0 = 0.f, s1 = 0.f;
+    long long r = r0;
+    for (; r + 1 < r1; r += 2) { s0 += A[r * lda + c]; s1 += A[(r + 1) * lda + c]; }
+    if (r < r1) s0 += A[r * lda + c];
+    atomicAdd(out + c, s0 + s1);
+  }
+}
+}  // namespace
+}  // namespace s2c
+
+extern "C" int s2c_col_sum(const float *A, long long lda, long long R, int M, float *out, void *stream) {
+  using namespace s2c;
+  S2C_REQUIRE(R >= 0 && M >= 0 && lda >= M, "col_sum: bad sizes");
+  if (M == 0) return S2C_OK;
+  S2C_REQUIRE(out, "col_sum: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  S2C_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)M, st), "col_sum memset");
+  if (R == 0) return S2C_OK;
+  S2C_REQUIRE(A, "col_sum: null pointer");
+  const long long rows_per_cta = R / (2 * kNumSMs) + 1 > 32 ? R / (2 * kNumSMs) + 1 : 32;
+  const unsigned grid = (unsigned)ceil_div_ll(R, rows_per_cta);
+  col_sum_kernel<<<grid, 256, 0, st>>>(A, lda, R, M, rows_per_cta, out);
+  S2C_CHECK_LAUNCH("col_sum");
+  return S2C_OK;
+}

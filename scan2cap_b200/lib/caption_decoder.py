@@ -14,6 +14,9 @@ from .._lib import CaptionParams, call
 from .pointnet2._ext import _guard, _stream
 
 
+DEBUG_TS = None  # set to a list to collect (T, 8) globaltimer stamps of every forward call
+
+
 def supported(pre_word, mapped, obj):
     E, H, F = pre_word.shape[2], mapped.shape[2], obj.shape[2]
     return (pre_word.is_cuda and pre_word.dtype == torch.float32 and E % 4 == 0 and F % 4 == 0 and H % 64 == 0
@@ -53,6 +56,11 @@ class _TopDownDecode(Function):
             setattr(P, name, w.data_ptr())
         for name, t in saved.items():
             setattr(P, name, t.data_ptr())
+        scores = torch.empty((T, B, K), dtype=torch.float32, device=dev)  # scratch of the forward kernel
+        P.scores = scores.data_ptr()
+        if DEBUG_TS is not None:  # profiling aid (tools/caption_probe.py): per-word stage time stamps
+            DEBUG_TS.append(torch.zeros((T, 8), dtype=torch.int64, device=dev))
+            P.dbg_ts = DEBUG_TS[-1].data_ptr()
         with _guard(pre_word):
             call("s2c_caption_decode_fwd", ctypes.byref(P), _stream(pre_word))
         ctx.save_for_backward(pre_word, pre_tgt, mapped, obj, valid, w_tdh, *ws, buf)

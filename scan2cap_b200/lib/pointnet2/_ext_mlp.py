@@ -112,17 +112,43 @@ def bwd_weight_supported(C, P, *lds):
             and all(ld % 4 == 0 for ld in lds))
 
 
-def mlp_layer_bwd_weight(dY, X, P, xs=None, xh=None, a=None, b=None, c=None, Y=None):
+def mlp_layer_bwd_weight(dY, X, P, xs=None, xh=None, a=None, b=None, c=None, Y=None, out=None, col0=0):
     """dW (C, P) = sum_r dY[r]^T X'[r]; dY (R, C) dense or (with a, b, c, Y) formed as a*dY + b*Y + c; X (R, >=P)
-    with optional relu(X*xs+xh) prologue."""
+    with optional relu(X*xs+xh) prologue.  With `out` (C, >= col0+P, zero-filled by the caller) the block is written
+    to out[:, col0:col0+P] from the columns X[:, col0:col0+P]."""
     R, C = dY.shape
-    dW = torch.zeros((C, P), dtype=torch.float32, device=dY.device)
-    ptr = lambda t: t.data_ptr() if t is not None else None
+    dW = torch.zeros((C, P), dtype=torch.float32, device=dY.device) if out is None else out
+    ptr = lambda t, o=0: t.data_ptr() + 4 * o if t is not None else None
     with _guard(dY):
         call("s2c_mlp_layer_bwd_weight", dY.data_ptr(), dY.stride(0), ptr(Y), Y.stride(0) if Y is not None else 0,
-             ptr(a), ptr(b), ptr(c), X.data_ptr(), X.stride(0), ptr(xs), ptr(xh), R, C, int(P), dW.data_ptr(), P,
-             _stream(dY))
+             ptr(a), ptr(b), ptr(c), ptr(X, col0), X.stride(0), ptr(xs, col0), ptr(xh, col0), R, C, int(P),
+             ptr(dW, col0), dW.stride(0), _stream(dY))
     return dW
+
+
+def wgrad_blocked_supported(C, P, *lds):
+    return KERNEL_VERSION == 2 and C <= 256 and C % 4 == 0 and P % 4 == 0 and all(ld % 4 == 0 for ld in lds)
+
+
+def mlp_layer_bwd_weight_blocked(dY, X, P, xs=None, xh=None):
+    """The same weight gradient for any width P: column blocks of the widest shape the tensor-core kernel holds
+    (256 columns for C <= 128 output channels, 128 for C <= 256), each one launch over all rows."""
+    R, C = dY.shape
+    step = 256 if C <= 128 else 128
+    dW = torch.zeros((C, P), dtype=torch.float32, device=dY.device)
+    for c0 in range(0, P, step):
+        mlp_layer_bwd_weight(dY, X, min(step, P - c0), xs, xh, out=dW, col0=c0)
+    return dW
+
+
+def col_sum(A):
+    """(R, M) -> (M): column sums (bias gradients)."""
+    R, M = A.shape
+    assert A.is_cuda and A.dtype == torch.float32 and A.stride(1) == 1
+    out = torch.empty((M,), dtype=torch.float32, device=A.device)
+    with _guard(A):
+        call("s2c_col_sum", A.data_ptr(), A.stride(0), R, M, out.data_ptr(), _stream(A))
+    return out
 
 
 def bn_finalize(s1, s2, R, bn, training):

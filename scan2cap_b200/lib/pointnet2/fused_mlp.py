@@ -130,6 +130,9 @@ class _FusedMLPPool(Function):
                     g_prev, dY, sum_g, sum_gy = _ext_mlp.mlp_layer_bwd_data(Y, a, b, c, W, Ys[l - 1], sc_p, sh_p, G=g)
                 if _ext_mlp.bwd_weight_supported(Y.shape[1], Ys[l - 1].shape[1], dY.stride(0), Ys[l - 1].stride(0)):
                     grads[3 * l] = _ext_mlp.mlp_layer_bwd_weight(dY, Ys[l - 1], Ys[l - 1].shape[1], sc_p, sh_p).view_as(params[3 * l])
+                elif _ext_mlp.wgrad_blocked_supported(Y.shape[1], Ys[l - 1].shape[1], dY.stride(0), Ys[l - 1].stride(0)):
+                    grads[3 * l] = _ext_mlp.mlp_layer_bwd_weight_blocked(dY, Ys[l - 1], Ys[l - 1].shape[1], sc_p,
+                                                                        sh_p).view_as(params[3 * l])
                 else:
                     Xp = torch.relu_(torch.addcmul(sh_p, Ys[l - 1], sc_p))
                     grads[3 * l] = (dY.t() @ Xp).view_as(params[3 * l])
@@ -164,6 +167,8 @@ class _FusedMLPPool(Function):
                                 grad_rows[:, 4 + K - 3:] = 0.0
                         if _ext_mlp.bwd_weight_supported(Y.shape[1], Kp, dY.stride(0), rows.stride(0)):
                             dWp = _ext_mlp.mlp_layer_bwd_weight(dY, rows, Kp)
+                        elif _ext_mlp.wgrad_blocked_supported(Y.shape[1], Kp, dY.stride(0), rows.stride(0)):
+                            dWp = _ext_mlp.mlp_layer_bwd_weight_blocked(dY, rows, Kp)
                         else:
                             dWp = dY.t() @ rows[:, :Kp]
                         grads[0] = _first_layer_weight_grad(dWp, K, xyz_gap).reshape(params[0].shape)

@@ -21,6 +21,7 @@ import torch
 import torch.nn as nn
 
 from ..lib.config import CONF
+from ..lib import linear_tc
 from ..lib.pointnet2 import _ext_graph
 
 
@@ -34,7 +35,10 @@ class EdgeConv(nn.Module):
         self.map_edge = nn.Sequential(nn.Linear(2 * in_size, out_size), nn.ReLU(), nn.Linear(out_size, out_size))
 
     def message(self, x_i, x_j):
-        return self.map_edge(torch.cat([x_i, x_j - x_i], dim=1))
+        z = torch.cat([x_i, x_j - x_i], dim=1)
+        # Linear -> ReLU -> Linear over all E edges; the weight gradients run on the tensor-core kernel (lib/linear_tc.py)
+        h = torch.relu(linear_tc.linear(z, self.map_edge[0].weight, self.map_edge[0].bias))
+        return linear_tc.linear(h, self.map_edge[2].weight, self.map_edge[2].bias)
 
     def forward(self, x, edge_index, edge_mask=None):
         """x (N,in), edge_index (2,E) long, optional edge_mask (E) bool -> (out (N,out), message (E,out))."""

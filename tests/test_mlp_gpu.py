@@ -176,3 +176,27 @@ def test_fused_mlp_gap_layout_matches_torch_path(Cf, widths, ns, need_xyz):
         assert float(x_a.grad[:, :3].abs().max()) == 0.0
     for (n, pa), (_, pb) in zip(mlp_a.named_parameters(), mlp_b.named_parameters()):
         assert l2(pa.grad, pb.grad) < 5e-3, n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("R,IN,OUT,bias", [(20480, 256, 128, True), (20480, 128, 128, True), (4096, 512, 256, False),
+                                           (3000, 64, 8, True)])
+def test_linear_tc_matches_float64(R, IN, OUT, bias):
+    """lib/linear_tc.py: library forward / dgrad, tensor-core weight gradient (column-blocked), column-sum bias grad."""
+    from scan2cap_b200.lib import linear_tc
+    torch.manual_seed(R + IN)
+    x = torch.randn(R, IN, device=DEV, requires_grad=True)
+    lin = torch.nn.Linear(IN, OUT, bias=bias).to(DEV)
+    g = torch.randn(R, OUT, device=DEV)
+    y = linear_tc.linear(x, lin.weight, lin.bias)
+    y.backward(g)
+    xd = x.detach().double().requires_grad_(True)
+    lind = torch.nn.Linear(IN, OUT, bias=bias).to(DEV).double()
+    lind.load_state_dict({k: v.double() for k, v in lin.state_dict().items()})
+    lind(xd).backward(g.double())
+    rel = lambda a, b: float((a.double() - b).abs().max() / b.abs().max().clamp_min(1e-12))
+    assert rel(y.detach(), lind(xd).detach()) < 1e-5
+    assert rel(x.grad, xd.grad) < 1e-5
+    assert rel(lin.weight.grad, lind.weight.grad) < 2e-5
+    if bias:
+        assert rel(lin.bias.grad, lind.bias.grad) < 2e-5

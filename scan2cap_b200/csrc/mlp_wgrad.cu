@@ -10,6 +10,8 @@
 // four channels a thread stores at each step.  dY is optionally formed on the fly (BatchNorm-backward affine
 // a*g + b*y + c), X' by the BatchNorm + ReLU prologue; fp32 operands are split hi/lo (3xTF32).  Each persistent CTA
 // accumulates its share of the rows in TMEM and adds its [C_l x C_prev] partial to the result with fp32 atomics.
+#include <math.h>
+
 #include "s2c_common.cuh"
 
 namespace s2c {
@@ -277,6 +279,7 @@ mlp_wgrad_kernel(WgradArgs g) {
   }
   // ===================== epilogue: this CTA's partial [C x P] -> global with fp32 atomics (warps 0-3, TMEM quarter = warp)
   if (warp < 4 && my_chunks > 0) {
+    const bool vec_red = ((g.lddw & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.dW) & 15) == 0);
     mbar_wait(&bars[4], 0);
     tc_fence_after();
     for (int mh = 0; mh < g.MH; ++mh) {
@@ -285,9 +288,25 @@ mlp_wgrad_kernel(WgradArgs g) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((mh * NB + nb) * 32), v);
         if (m < g.C) {
+          float *o = g.dW + (long long)m * g.lddw + nb * 32;
+          if (vec_red) {  // one 16-byte reduction per 4 columns (4x fewer atomic operations than scalar adds)
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb * 32 + j < g.P) atomicAdd(g.dW + (long long)m * g.lddw + nb * 32 + j, v[j]);
+            for (int j = 0; j < 32; j += 4) {
+              if (nb * 32 + j + 3 < g.P) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]),
+                             "f"(v[j + 3])
+                             : "memory");
+              } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (nb * 32 + j + u < g.P) atomicAdd(o + j + u, v[j + u]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb * 32 + j < g.P) atomicAdd(o + j, v[j]);
+          }
         }
       }
     }
@@ -325,12 +344,18 @@ extern "C" int s2c_mlp_layer_bwd_weight(const float *dY, long long lddy, const f
   S2C_REQUIRE(smem <= 227 * 1024, "mlp_layer_bwd_weight: shared memory %zu B exceeds 227 KB", smem);
   const long long chunks = (R + CK - 1) / CK;
   const int CB = (C + 31) / 32;
+  // chunks per CTA: every CTA ends with C*P/4 vector reductions into dW (~70 per ns device-wide) and spends ~2 us per
+  // chunk, so short reductions (R of a few thousand rows) want fewer, longer-running CTAs: minimise
+  //   cpc * 2000 ns + (chunks / cpc) * C*P / 280 ns   ->   cpc = sqrt(chunks * C*P / 560000)
+  long long cpc = (long long)(sqrt((double)chunks * (double)C * (double)P / 560000.0) + 0.5);
+  if (cpc < 1) cpc = 1;
 #define S2C_WGRAD(CBT, NBT, PF)                                                                                         \
   do {                                                                                                                  \
     auto kern = mlp_wgrad_kernel<CBT, NBT, PF>;                                                                         \
     S2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "wgrad smem attr");    \
     const long long cap = (long long)kNumSMs * ((PF) ? 2 : 1);                                                          \
-    const int grid = (int)(chunks < cap ? chunks : cap);                                                                \
+    const long long want = (chunks + cpc - 1) / cpc;                                                                    \
+    const int grid = (int)(want < cap ? want : cap);                                                                    \
     kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(g);                                                            \
     S2C_CHECK_LAUNCH("mlp_wgrad launch");                                                                               \
     return S2C_OK;                                                                                                      \

@@ -68,6 +68,27 @@ def furthest_point_sampling_with_xyz(points, nsamples):
     return out, new_xyz
 
 
+def furthest_point_sampling_chain(points, counts, stream):
+    """FPS levels chained on `stream` (a torch.cuda.Stream): level i samples counts[i] points from level i-1's output.
+    Outputs are allocated here (on the CURRENT stream's pool) and the kernels are enqueued on `stream`; the caller
+    orders the streams (stream.wait_stream(current) before, current.wait_stream(stream) before the first use).
+    Lets the coordinate-only sampling of the deeper set-abstraction levels run beside the first level's grouping and
+    MLP (backbone_module.py:74-128 evaluates them strictly in sequence)."""
+    _chk(points, "points", torch.float32)
+    out = []
+    cur = points
+    with _guard(points):
+        for m in counts:
+            B, N, _ = cur.shape
+            idx = torch.empty((B, m), dtype=torch.int32, device=points.device)
+            new_xyz = torch.empty((B, m, 3), dtype=torch.float32, device=points.device)
+            call("s2c_furthest_point_sampling", cur.data_ptr(), B, N, int(m), idx.data_ptr(), new_xyz.data_ptr(),
+                 stream.cuda_stream)
+            out.append((idx, new_xyz))
+            cur = new_xyz
+    return out
+
+
 def gather_points(points, idx):
     _chk(points, "points", torch.float32)
     _chk(idx, "idx", torch.int32)

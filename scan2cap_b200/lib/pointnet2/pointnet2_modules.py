@@ -89,9 +89,10 @@ class PointnetSAModuleVotes(nn.Module):
             mlp_spec[0] += 3  # (the reference mutates the caller's list too: pointnet2_modules.py:204-206)
         self.mlp_module = pt_utils.SharedMLP(mlp_spec, bn=bn)
 
-    def forward(self, xyz: torch.Tensor, features: torch.Tensor = None, inds: torch.Tensor = None):
+    def forward(self, xyz: torch.Tensor, features: torch.Tensor = None, inds: torch.Tensor = None,
+                sampled_xyz: torch.Tensor = None):
         """xyz (B,N,3), features (B,C,N), inds (B,npoint) -> new_xyz (B,npoint,3), new_features (B,C',npoint),
-        inds (B,npoint) int32."""
+        inds (B,npoint) int32.  sampled_xyz (extension): xyz[inds] when the caller already has it (no gradient)."""
         layers = self.mlp_module.layer_params()
         fast = (self.npoint is not None and self.use_xyz and self.pooling == "max" and layers is not None
                 and not self.ret_unique_cnt)
@@ -102,6 +103,9 @@ class PointnetSAModuleVotes(nn.Module):
             inds, new_xyz = _ext.furthest_point_sampling_with_xyz(xyz.detach(), self.npoint)
             if xyz.requires_grad:  # vote aggregation: the sampled coordinates carry gradient
                 new_xyz = torch.gather(xyz, 1, inds.long().unsqueeze(-1).expand(-1, -1, 3))
+        elif sampled_xyz is not None and not xyz.requires_grad:
+            assert inds.shape[1] == self.npoint
+            new_xyz = sampled_xyz
         else:
             assert inds.shape[1] == self.npoint
             new_xyz = torch.gather(xyz, 1, inds.long().unsqueeze(-1).expand(-1, -1, 3))

@@ -2,9 +2,18 @@
 feature-propagation layers, same attribute names (sa1..sa4, fp1, fp2 -> checkpoint keys) and the same
 ``data_dict`` keys.  The point cloud's feature columns are fed to SA1 as they lie in ``point_clouds``
 (point-major), so the reference's transpose().contiguous() copy (:68-71) does not happen."""
+import os
+
+import torch
 import torch.nn as nn
 
+from ..lib.pointnet2 import _ext
 from ..lib.pointnet2.pointnet2_modules import PointnetSAModuleVotes, PointnetFPModule
+
+# The sampling of SA2..SA4 depends on coordinates only (each level samples the previous level's samples), so it can
+# run on a second stream next to SA1's grouping + MLP instead of between the levels (S2C_SAMPLE_AHEAD=0: in sequence)
+SAMPLE_AHEAD = os.environ.get("S2C_SAMPLE_AHEAD", "1") != "0"
+_SIDE_STREAMS = {}
 
 
 class Pointnet2Backbone(nn.Module):
@@ -22,6 +31,13 @@ class Pointnet2Backbone(nn.Module):
         self.fp1 = PointnetFPModule(mlp=[256 + 256, 256, 256])
         self.fp2 = PointnetFPModule(mlp=[256 + 256, 256, 256])
 
+    @staticmethod
+    def _side_stream(device):
+        key = (device.type, device.index)
+        if key not in _SIDE_STREAMS:
+            _SIDE_STREAMS[key] = torch.cuda.Stream(device)
+        return _SIDE_STREAMS[key]
+
     def _break_up_pc(self, pc):
         xyz = pc[..., :3].contiguous()
         # (B,C,N) VIEW of the point-major columns; PointnetSAModuleVotes consumes it without a copy
@@ -32,21 +48,33 @@ class Pointnet2Backbone(nn.Module):
         pointcloud = data_dict["point_clouds"]
         xyz, features = self._break_up_pc(pointcloud)
 
-        xyz, features, fps_inds = self.sa1(xyz, features)
+        ahead = [(None, None)] * 3
+        if SAMPLE_AHEAD and xyz.is_cuda and not xyz.requires_grad:
+            # FPS of all four levels up front: level 1 on this stream, levels 2-4 (8 CTAs each) on a side stream that
+            # overlaps SA1's grouping and MLP; the streams join before SA2 (a fork/join the CUDA-graph capture keeps)
+            inds1, xyz1 = _ext.furthest_point_sampling_with_xyz(xyz, self.sa1.npoint)
+            main = torch.cuda.current_stream(xyz.device)
+            side = self._side_stream(xyz.device)
+            side.wait_stream(main)
+            ahead = _ext.furthest_point_sampling_chain(xyz1, [self.sa2.npoint, self.sa3.npoint, self.sa4.npoint], side)
+            xyz, features, fps_inds = self.sa1(xyz, features, inds1, sampled_xyz=xyz1)
+            main.wait_stream(side)
+        else:
+            xyz, features, fps_inds = self.sa1(xyz, features)
         data_dict["sa1_inds"] = fps_inds
         data_dict["sa1_xyz"] = xyz
         data_dict["sa1_features"] = features
 
-        xyz, features, fps_inds = self.sa2(xyz, features)
+        xyz, features, fps_inds = self.sa2(xyz, features, ahead[0][0], sampled_xyz=ahead[0][1])
         data_dict["sa2_inds"] = fps_inds
         data_dict["sa2_xyz"] = xyz
         data_dict["sa2_features"] = features
 
-        xyz, features, fps_inds = self.sa3(xyz, features)
+        xyz, features, fps_inds = self.sa3(xyz, features, ahead[1][0], sampled_xyz=ahead[1][1])
         data_dict["sa3_xyz"] = xyz
         data_dict["sa3_features"] = features
 
-        xyz, features, fps_inds = self.sa4(xyz, features)
+        xyz, features, fps_inds = self.sa4(xyz, features, ahead[2][0], sampled_xyz=ahead[2][1])
         data_dict["sa4_xyz"] = xyz
         data_dict["sa4_features"] = features
 

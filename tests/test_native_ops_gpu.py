@@ -219,6 +219,27 @@ def test_sweep_sizes_fps_and_ball_query(n, M, r, ns, ext, oracle):
     np.testing.assert_array_equal(N(got), oracle.ball_query(N(new_xyz), xyz, r, ns))
 
 
+@pytest.mark.parametrize("n,M,r,ns", [(6000, 300, 5.0, 512), (40000, 512, 0.9, 64), (40000, 256, 5.0, 512),
+                                      (5000, 100, 1e-4, 16)])
+def test_ball_query_dense_and_empty_balls(n, M, r, ns, ext, oracle, ref_ext):
+    """Grid path outside its comfort zone: balls holding thousands of points (more hits than the per-warp hit list:
+    the repeated-minimum fallback; MaskVoteNet's r=5 / nsample=512 query, models/mask_votenet.py:145-153) and balls
+    holding only the centre itself."""
+    pc, _ = synthetic.make_point_clouds(2, n, use_height=False, seed=21)
+    xyz = pc[..., :3].copy()
+    new_xyz = xyz[:, np.random.default_rng(1).permutation(n)[:M]].copy()
+    want = oracle.ball_query(new_xyz, xyz, r, ns)
+    np.testing.assert_array_equal(N(ext.ball_query(T(new_xyz), T(xyz), r, ns)), want)
+    if ref_ext is not None:
+        np.testing.assert_array_equal(want, N(ref_ext.ball_query(T(new_xyz), T(xyz), r, ns)))
+    feats = np.random.default_rng(2).standard_normal((2, n, 8)).astype(np.float32)
+    grouped, gidx = ext.query_and_group(T(xyz), T(new_xyz), T(feats), r, ns, True, feat_point_major=True,
+                                        channels_last=True, pad4=True)
+    np.testing.assert_array_equal(N(gidx), want)
+    b = np.arange(2)[:, None, None]
+    np.testing.assert_array_equal(N(grouped[:, 4:12]).transpose(0, 2, 3, 1), feats[b, want])
+
+
 @pytest.mark.parametrize("C,c0,ld", [(128, 3, 132), (3, 0, 132), (37, 3, 40), (256, 3, 260)])
 def test_group_rows_grad_matches_index_add(C, c0, ld, ext):
     """channels-last scatter-add (gradient of the grouped rows) vs a float64 index_add of the same rows."""

@@ -8,7 +8,7 @@
 namespace s2c {
 namespace {
 
-constexpr int TM = 64, TN = 64, TR = 16;
+constexpr int TM = 64, TN = 64, TR = 64;  // 64 reduction rows per stage: few, long stages (each pays one L2 round trip)
 
 __global__ void __launch_bounds__(256)
 gemm_tn_kernel(const float *__restrict__ A, long long lda, const float *__restrict__ X, long long ldx, int R, int M, int N,
@@ -23,13 +23,14 @@ gemm_tn_kernel(const float *__restrict__ A, long long lda, const float *__restri
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   float cs[4] = {0.f, 0.f, 0.f, 0.f};
   for (int r0 = 0; r0 < R; r0 += TR) {
+#pragma unroll 8
     for (int i = threadIdx.x; i < TR * TM; i += 256) {
       const int rr = i / TM, c = i - rr * TM;
       As[rr][c] = (r0 + rr < R && m0 + c < M) ? A[(size_t)(r0 + rr) * lda + m0 + c] : 0.f;
       Xs[rr][c] = (r0 + rr < R && n0 + c < N) ? X[(size_t)(r0 + rr) * ldx + n0 + c] : 0.f;
     }
     __syncthreads();
-#pragma unroll
+#pragma unroll 16
     for (int rr = 0; rr < TR; ++rr) {
       const float4 a = *reinterpret_cast<const float4 *>(&As[rr][ty * 4]);
       const float4 x = *reinterpret_cast<const float4 *>(&Xs[rr][tx * 4]);

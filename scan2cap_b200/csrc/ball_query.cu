@@ -24,7 +24,7 @@ constexpr int kWarps = 8;        // warps per CTA
 constexpr int kTile = 2048;      // points per shared-memory tile
 
 template <bool GROUP, int kCPW>
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, 4)
 ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz, int n, int M, float radius,
                   int nsample, int *__restrict__ idx, int *__restrict__ cnt_out, GroupArgs ga) {
   extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -195,7 +195,7 @@ grid_build_kernel(const float *__restrict__ xyz, int n, float radius, GridParams
 constexpr int kHitCap = 1024;
 
 template <bool GROUP>
-__global__ void __launch_bounds__(256, 6)
+__global__ void __launch_bounds__(256, 5)
 grid_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz, int n, int M, float radius, int nsample,
                   const GridParams *__restrict__ params, const int *__restrict__ cell_start, const float4 *__restrict__ sorted,
                   int *__restrict__ idx, GroupArgs ga) {

@@ -54,39 +54,49 @@ __device__ __forceinline__ void group_epilogue(const GroupArgs &ga, const float 
     // block the tensor-core dgrad / the vectorised scatter-add can address directly.
     const int CP = 4 + ((ga.C + 3) & ~3);
     float *o = ga.grouped + ((size_t)b * M + j) * (size_t)nsample * CP;
-    const int W = CP >> 2;
-    const int total = nsample * W;
-    const float invW = 1.0f / (float)W;
     const bool unit = ga.feat_chan_stride == 1;
-    const bool vec = unit && (ga.feat_point_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0;
-#pragma unroll 4
-    for (int q = lane; q < total; q += 32) {
-      const int s = __float2int_rz(((float)q + 0.5f) * invW);  // q / W (exact: |(q+.5)/W - integer| >= .5/W)
-      const int w = q - s * W;
+    const bool vec = unit && (ga.feat_point_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0 && (ga.C & 3) == 0;
+    // slot 0 of every sample: the three offsets and the zero that aligns the feature block
+    for (int s = lane; s < nsample; s += 32) {
       const int k = li[s];
       float4 v;
-      if (w == 0) {
-        v.x = __fsub_rn(xyz[(size_t)k * 3 + 0], cx);
-        v.y = __fsub_rn(xyz[(size_t)k * 3 + 1], cy);
-        v.z = __fsub_rn(xyz[(size_t)k * 3 + 2], cz);
-        if (ga.normalize) {
-          v.x = __fmul_rn(v.x, ga.inv_radius); v.y = __fmul_rn(v.y, ga.inv_radius); v.z = __fmul_rn(v.z, ga.inv_radius);
-        }
-        v.w = 0.f;
-      } else {
-        const int c = 4 * (w - 1);  // first feature channel of this slot
-        const float *fk = f + (size_t)k * ga.feat_point_stride + (size_t)c * ga.feat_chan_stride;
-        if (vec && c + 3 < ga.C) {
-          v = __ldg(reinterpret_cast<const float4 *>(fk));
-        } else {
-          const size_t cs = (size_t)ga.feat_chan_stride;
-          v.x = c + 0 < ga.C ? __ldg(fk) : 0.f;
-          v.y = c + 1 < ga.C ? __ldg(fk + cs) : 0.f;
-          v.z = c + 2 < ga.C ? __ldg(fk + 2 * cs) : 0.f;
-          v.w = c + 3 < ga.C ? __ldg(fk + 3 * cs) : 0.f;
-        }
+      v.x = __fsub_rn(xyz[(size_t)k * 3 + 0], cx);
+      v.y = __fsub_rn(xyz[(size_t)k * 3 + 1], cy);
+      v.z = __fsub_rn(xyz[(size_t)k * 3 + 2], cz);
+      if (ga.normalize) {
+        v.x = __fmul_rn(v.x, ga.inv_radius); v.y = __fmul_rn(v.y, ga.inv_radius); v.z = __fmul_rn(v.z, ga.inv_radius);
       }
-      st_stream4(o + 4 * (size_t)q, v);
+      v.w = 0.f;
+      st_stream4(o + (size_t)s * CP, v);
+    }
+    if (ga.C == 0) return;
+    if (vec) {
+      // aligned source rows (features of a previous set-abstraction level): 16-byte loads and stores
+      const int W = ga.C >> 2;
+      const int total = nsample * W;
+      const float invW = 1.0f / (float)W;
+#pragma unroll 4
+      for (int q = lane; q < total; q += 32) {
+        const int s = __float2int_rz(((float)q + 0.5f) * invW);  // q / W (exact: |(q+.5)/W - integer| >= .5/W)
+        const int w = q - s * W;
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(f + (size_t)li[s] * ga.feat_point_stride) + w);
+        st_stream4(o + (size_t)s * CP + 4 + 4 * w, v);
+      }
+    } else {
+      // unaligned / strided source rows (the feature columns of point_clouds, row stride 3+C floats): lanes run over
+      // the channels of one neighbour, so both the loads and the stores of a warp instruction cover one contiguous
+      // 128-byte run (4-byte accesses, fully coalesced) instead of 32 partly used sectors
+      const int Cw = CP - 4;  // feature columns incl. the zero pad
+      const int total = nsample * Cw;
+      const float invC = 1.0f / (float)Cw;
+      const size_t cs = (size_t)ga.feat_chan_stride;
+#pragma unroll 4
+      for (int t = lane; t < total; t += 32) {
+        const int s = __float2int_rz(((float)t + 0.5f) * invC);
+        const int w = t - s * Cw;
+        const float v = w < ga.C ? __ldg(f + (size_t)li[s] * ga.feat_point_stride + (size_t)w * cs) : 0.f;
+        st_stream(o + (size_t)s * CP + 4 + w, v);
+      }
     }
     return;
   }

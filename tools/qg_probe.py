@@ -11,6 +11,8 @@ pc, _ = synthetic.make_point_clouds(B, N, use_normal=False, use_height=False, se
 full = torch.cat([torch.from_numpy(pc[..., :3].copy()), torch.randn(B, N, C)], -1).cuda()   # like point_clouds (B,N,3+C)
 xyz = full[..., :3].contiguous()
 feats = full[..., 3:]
+if len(sys.argv) > 5 and sys.argv[5] == "aligned":  # (B,N,C) contiguous rows (16-byte aligned), as between SA levels
+    feats = feats.contiguous()
 r = 0.2 * (40000.0 / N) ** 0.5
 _, new_xyz = _ext.furthest_point_sampling_with_xyz(xyz, 2048)
 for _ in range(2):

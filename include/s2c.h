@@ -281,6 +281,10 @@ typedef struct s2c_caption_params {
   float *dgi2, *dgh2, *dlang, *datt, *dq, *dgi1, *dgh1, *du, *d_mapped, *d_obj, *d_watt;
   /* optional profiling aid: (T, 8) %globaltimer stamps (ns) taken by CTA 0 at the stage boundaries of every word */
   long long *dbg_ts;
+  /* optional: one zero-initialised unsigned int of device memory.  When given (and B <= 8, H/4 <= #SMs, cooperative
+   * launch available) the recurrence runs as a persistent cooperative grid with the weights resident in shared memory
+   * (csrc/caption_grid.cu) and this word is its grid-barrier counter; otherwise the cluster kernels are used. */
+  unsigned int *grid_bar;
 } s2c_caption_params;
 S2C_API int s2c_caption_decode_fwd(const s2c_caption_params *params, void *stream);
 S2C_API int s2c_caption_decode_bwd(const s2c_caption_params *params, void *stream);

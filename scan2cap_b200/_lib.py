@@ -55,7 +55,7 @@ class CaptionParams(ctypes.Structure):
              "d_h2 d_probs "
              "dgi2 dgh2 dlang datt dq dgi1 dgh1 du d_mapped d_obj d_watt").split()
     _fields_ = ([(n, c_int) for n in ("B", "T", "K", "E", "H", "F")] + [("ld_tdh", c_ll)] +
-                [(n, c_void_p) for n in _PTRS] + [("dbg_ts", c_void_p)])
+                [(n, c_void_p) for n in _PTRS] + [("dbg_ts", c_void_p), ("grid_bar", c_void_p)])
 
 
 class S2CError(RuntimeError):

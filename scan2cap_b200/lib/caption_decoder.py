@@ -6,6 +6,7 @@ Arithmetic = the per-word step of the reference (models/caption_module.py:250-29
 forward_sample_batch (:428-500); see TopDownSceneCaptionModule._forward_sample_batch for what is hoisted out of it.
 """
 import ctypes
+import os
 
 import torch
 from torch.autograd import Function
@@ -15,6 +16,8 @@ from .pointnet2._ext import _guard, _stream
 
 
 DEBUG_TS = None  # set to a list to collect (T, 8) globaltimer stamps of every forward call
+# persistent cooperative-grid variant (csrc/caption_grid.cu) for B <= 8; off: always the cluster kernels (csrc/caption.cu)
+USE_GRID = os.environ.get("S2C_CAPTION_GRID", "1") != "0"
 
 
 def supported(pre_word, mapped, obj):
@@ -58,6 +61,8 @@ class _TopDownDecode(Function):
             setattr(P, name, t.data_ptr())
         scores = torch.empty((T, B, K), dtype=torch.float32, device=dev)  # scratch of the forward kernel
         P.scores = scores.data_ptr()
+        bar = torch.zeros((1,), dtype=torch.int32, device=dev)  # grid-barrier counter of the persistent-grid variant
+        P.grid_bar = bar.data_ptr() if USE_GRID else None
         if DEBUG_TS is not None:  # profiling aid (tools/caption_probe.py): per-word stage time stamps
             DEBUG_TS.append(torch.zeros((T, 8), dtype=torch.int64, device=dev))
             P.dbg_ts = DEBUG_TS[-1].data_ptr()
@@ -108,6 +113,8 @@ class _TopDownDecode(Function):
         P.d_h2 = d_h2.data_ptr()
         P.d_probs = d_probs.data_ptr() if d_probs is not None else None
         P.d_mapped, P.d_obj, P.d_watt = d_mapped.data_ptr(), d_obj.data_ptr(), d_watt.data_ptr()
+        bar = torch.zeros((1,), dtype=torch.int32, device=dev)
+        P.grid_bar = bar.data_ptr() if USE_GRID else None
         with _guard(buf):
             call("s2c_caption_decode_bwd", ctypes.byref(P), _stream(buf))
 

@@ -38,8 +38,10 @@ def _reference(pre_word, pre_tgt, mapped, obj, valid, w_tdh, c1, map_hidd, atten
     (11, 3, 64, 64, 128, 32, 64),     # two clusters, every proposal valid, small widths (8-CTA or 16-CTA slices)
     (4, 31, 256, 300, 512, 128, 11),  # BASELINE config c4 batch, longest description
 ])
-def test_topdown_decode_matches_float64(B, T, K, E, H, Fd, nvalid):
+@pytest.mark.parametrize("grid", [True, False])  # persistent cooperative grid (B <= 8) / thread-block cluster kernels
+def test_topdown_decode_matches_float64(B, T, K, E, H, Fd, nvalid, grid, monkeypatch):
     from scan2cap_b200.lib import caption_decoder
+    monkeypatch.setattr(caption_decoder, "USE_GRID", grid)
     torch.manual_seed(B * 100 + T)
     mk = lambda *s: (torch.randn(*s, device=DEV) * 0.5)
     pre_word, pre_tgt, mapped, obj = mk(B, T, E), mk(B, E), mk(B, K, H), mk(B, K, Fd)

@@ -314,6 +314,23 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
           c3 = *reinterpret_cast<const float4 *>(s_pro + 3 * KP + kk);
           c4 = *reinterpret_cast<const float4 *>(s_pro + 4 * KP + kk);
         }
+        // PRO_POOL: (argmax, dpool) depend on the row's GROUP only; consecutive passes (16 rows apart) mostly stay in
+        // one group, so the two global loads are issued once per group change instead of once per pass, and the
+        // group / sample indices advance incrementally (one 64-bit division per chunk instead of one per pass)
+        long long pgrp = 0, pgrp_loaded = -1;
+        int psmp = 0;
+        int4 p_am = make_int4(0, 0, 0, 0);
+        float4 p_dp = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (PRO == PRO_POOL) {
+          const long long base = row0 + (tt >> 3);
+          pgrp = base / g.ns;
+          psmp = (int)(base - pgrp * g.ns);
+          if (base < g.R && kk < g.K) {  // first group's values: in flight while this warp waits for the raw tile
+            p_am = __ldg(reinterpret_cast<const int4 *>(g.argmax + pgrp * g.K + kk));
+            p_dp = __ldg(reinterpret_cast<const float4 *>(g.dpool + pgrp * g.K + kk));
+            pgrp_loaded = pgrp;
+          }
+        }
         mbar_wait(&raw_full[rs], (uint32_t)((it / RS) & 1));
         if (it >= OS) mbar_wait(&op_empty[os], (uint32_t)(((it / OS) - 1) & 1));
         const unsigned char *raw = raw_base + (size_t)rs * RAW_BYTES;
@@ -336,14 +353,24 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
             const float4 y = v;
             float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
             if (row < g.R && kk < g.K) {
-              const long long grp = row / g.ns;
-              const int smp = (int)(row - grp * g.ns);
-              const int4 am = __ldg(reinterpret_cast<const int4 *>(g.argmax + grp * g.K + kk));
-              const float4 dp = __ldg(reinterpret_cast<const float4 *>(g.dpool + grp * g.K + kk));
+              if (pgrp != pgrp_loaded) {
+                p_am = __ldg(reinterpret_cast<const int4 *>(g.argmax + pgrp * g.K + kk));
+                p_dp = __ldg(reinterpret_cast<const float4 *>(g.dpool + pgrp * g.K + kk));
+                pgrp_loaded = pgrp;
+              }
+              const int4 am = p_am;
+              const float4 dp = p_dp;
+              const int smp = psmp;
               gg.x = (am.x == smp && fmaf(y.x, c3.x, c4.x) > 0.f) ? dp.x : 0.f;
               gg.y = (am.y == smp && fmaf(y.y, c3.y, c4.y) > 0.f) ? dp.y : 0.f;
               gg.z = (am.z == smp && fmaf(y.z, c3.z, c4.z) > 0.f) ? dp.z : 0.f;
               gg.w = (am.w == smp && fmaf(y.w, c3.w, c4.w) > 0.f) ? dp.w : 0.f;
+            }
+            {  // the next pass is 16 rows further
+              const int nx = psmp + 16;
+              const int q = nx / g.ns;
+              pgrp += q;
+              psmp = nx - q * g.ns;
             }
             v.x = fmaf(c0.x, gg.x, fmaf(c1.x, y.x, c2.x)); v.y = fmaf(c0.y, gg.y, fmaf(c1.y, y.y, c2.y));
             v.z = fmaf(c0.z, gg.z, fmaf(c1.z, y.z, c2.z)); v.w = fmaf(c0.w, gg.w, fmaf(c1.w, y.w, c2.w));

@@ -18,6 +18,9 @@ from .pointnet2._ext import _guard, _stream
 DEBUG_TS = None  # set to a list to collect (T, 8) globaltimer stamps of every forward call
 # persistent cooperative-grid variant (csrc/caption_grid.cu) for B <= 8; off: always the cluster kernels (csrc/caption.cu)
 USE_GRID = os.environ.get("S2C_CAPTION_GRID", "1") != "0"
+# the backward recurrence measured faster on the cluster kernel (1.33 vs 1.64 ms at B=8, T=26): its per-word chain has
+# more dependent stages, and 16 SMs streaming from L2 beat 128 SMs paying a grid barrier per stage
+USE_GRID_BWD = os.environ.get("S2C_CAPTION_GRID_BWD", "0") != "0"
 
 
 def supported(pre_word, mapped, obj):
@@ -114,7 +117,7 @@ class _TopDownDecode(Function):
         P.d_probs = d_probs.data_ptr() if d_probs is not None else None
         P.d_mapped, P.d_obj, P.d_watt = d_mapped.data_ptr(), d_obj.data_ptr(), d_watt.data_ptr()
         bar = torch.zeros((1,), dtype=torch.int32, device=dev)
-        P.grid_bar = bar.data_ptr() if USE_GRID else None
+        P.grid_bar = bar.data_ptr() if (USE_GRID and USE_GRID_BWD) else None
         with _guard(buf):
             call("s2c_caption_decode_bwd", ctypes.byref(P), _stream(buf))
 

@@ -42,6 +42,7 @@ def _reference(pre_word, pre_tgt, mapped, obj, valid, w_tdh, c1, map_hidd, atten
 def test_topdown_decode_matches_float64(B, T, K, E, H, Fd, nvalid, grid, monkeypatch):
     from scan2cap_b200.lib import caption_decoder
     monkeypatch.setattr(caption_decoder, "USE_GRID", grid)
+    monkeypatch.setattr(caption_decoder, "USE_GRID_BWD", grid)
     torch.manual_seed(B * 100 + T)
     mk = lambda *s: (torch.randn(*s, device=DEV) * 0.5)
     pre_word, pre_tgt, mapped, obj = mk(B, T, E), mk(B, E), mk(B, K, H), mk(B, K, Fd)

@@ -401,9 +401,24 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
     float4 acc_s[N / 32], acc_q[N / 32];
 #pragma unroll
     for (int i = 0; i < N / 32; ++i) { acc_s[i] = make_float4(0.f, 0.f, 0.f, 0.f); acc_q[i] = acc_s[i]; }
+    // EPI_MASK_STATS: the ReLU-mask operand Yprev comes from global memory, 8 rows x 16 bytes per thread and column
+    // block.  Loading each value right before its use serialises ~16 L2/HBM round trips per tile on the four epilogue
+    // warps (ncu: 35 % of the kernel's stall samples sat on the first use of those loads, and 55 tiles x 16 x ~0.5 us
+    // is the whole kernel time).  So the loads of column block cb+1 are issued before the math of block cb, and
+    // block 0's before the wait for the accumulator.
+    float4 ypre[8];
+    auto load_y = [&](int cb, long long row_base) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const long long row = row_base + i * 4 + er;
+        ypre[i] = row < g.R ? __ldg(reinterpret_cast<const float4 *>(g.Yprev + row * g.ldyp + cb * 32 + es * 4))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
     for (long long t = 0; t < my_tiles; ++t) {
       const int ab = (int)(t & 1);
       const long long row_base = ((long long)blockIdx.x + t * gridDim.x) * BM + q * 32;
+      if (EPI == EPI_MASK_STATS) load_y(0, row_base);
       mbar_wait(&acc_full[ab], (uint32_t)((t >> 1) & 1));
       tc_fence_after();
 #pragma unroll
@@ -415,9 +430,13 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
           *reinterpret_cast<float4 *>(sE + lane * 36 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
         float4 e_sc = make_float4(1.f, 1.f, 1.f, 1.f), e_sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 ycur[8];
         if (EPI == EPI_MASK_STATS) {
           e_sc = __ldg(reinterpret_cast<const float4 *>(g.e_scale + cb * 32 + es * 4));
           e_sh = __ldg(reinterpret_cast<const float4 *>(g.e_shift + cb * 32 + es * 4));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ycur[i] = ypre[i];
+          if (cb + 1 < N / 32) load_y(cb + 1, row_base);
         }
         float4 ps = make_float4(0.f, 0.f, 0.f, 0.f), pq = ps;
 #pragma unroll
@@ -428,7 +447,7 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
           if (row < g.R) {
             if (EPI == EPI_MASK_STATS) {
               // gradient w.r.t. the previous layer's rectified output: mask by its ReLU, reduce sum(g) and sum(g*y)
-              const float4 y = __ldg(reinterpret_cast<const float4 *>(g.Yprev + row * g.ldyp + cb * 32 + es * 4));
+              const float4 y = ycur[i];
               a.x = fmaf(y.x, e_sc.x, e_sh.x) > 0.f ? a.x : 0.f; a.y = fmaf(y.y, e_sc.y, e_sh.y) > 0.f ? a.y : 0.f;
               a.z = fmaf(y.z, e_sc.z, e_sh.z) > 0.f ? a.z : 0.f; a.w = fmaf(y.w, e_sc.w, e_sh.w) > 0.f ? a.w : 0.f;
               pq.x = fmaf(a.x, y.x, pq.x); pq.y = fmaf(a.y, y.y, pq.y); pq.z = fmaf(a.z, y.z, pq.z); pq.w = fmaf(a.w, y.w, pq.w);

@@ -319,15 +319,22 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
         // group / sample indices advance incrementally (one 64-bit division per chunk instead of one per pass)
         long long pgrp = 0, pgrp_loaded = -1;
         int psmp = 0;
-        int4 p_am = make_int4(0, 0, 0, 0);
-        float4 p_dp = make_float4(0.f, 0.f, 0.f, 0.f);
+        int4 p_am = make_int4(0, 0, 0, 0), n_am = p_am;     // current group's values / the next group's (one ahead)
+        float4 p_dp = make_float4(0.f, 0.f, 0.f, 0.f), n_dp = p_dp;
+        const long long num_groups = g.ns > 0 ? g.R / g.ns : 0;
         if (PRO == PRO_POOL) {
           const long long base = row0 + (tt >> 3);
           pgrp = base / g.ns;
           psmp = (int)(base - pgrp * g.ns);
-          if (base < g.R && kk < g.K) {  // first group's values: in flight while this warp waits for the raw tile
-            p_am = __ldg(reinterpret_cast<const int4 *>(g.argmax + pgrp * g.K + kk));
-            p_dp = __ldg(reinterpret_cast<const float4 *>(g.dpool + pgrp * g.K + kk));
+          if (kk < g.K) {  // first two groups' values: in flight while this warp waits for the raw tile
+            if (pgrp < num_groups) {
+              p_am = __ldg(reinterpret_cast<const int4 *>(g.argmax + pgrp * g.K + kk));
+              p_dp = __ldg(reinterpret_cast<const float4 *>(g.dpool + pgrp * g.K + kk));
+            }
+            if (pgrp + 1 < num_groups) {
+              n_am = __ldg(reinterpret_cast<const int4 *>(g.argmax + (pgrp + 1) * g.K + kk));
+              n_dp = __ldg(reinterpret_cast<const float4 *>(g.dpool + (pgrp + 1) * g.K + kk));
+            }
             pgrp_loaded = pgrp;
           }
         }
@@ -354,8 +361,16 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
             float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
             if (row < g.R && kk < g.K) {
               if (pgrp != pgrp_loaded) {
-                p_am = __ldg(reinterpret_cast<const int4 *>(g.argmax + pgrp * g.K + kk));
-                p_dp = __ldg(reinterpret_cast<const float4 *>(g.dpool + pgrp * g.K + kk));
+                if (pgrp == pgrp_loaded + 1) {  // the prefetched group; fetch the one after it
+                  p_am = n_am; p_dp = n_dp;
+                } else {
+                  p_am = __ldg(reinterpret_cast<const int4 *>(g.argmax + pgrp * g.K + kk));
+                  p_dp = __ldg(reinterpret_cast<const float4 *>(g.dpool + pgrp * g.K + kk));
+                }
+                if (pgrp + 1 < num_groups) {
+                  n_am = __ldg(reinterpret_cast<const int4 *>(g.argmax + (pgrp + 1) * g.K + kk));
+                  n_dp = __ldg(reinterpret_cast<const float4 *>(g.dpool + (pgrp + 1) * g.K + kk));
+                }
                 pgrp_loaded = pgrp;
               }
               const int4 am = p_am;
@@ -368,9 +383,15 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
             }
             {  // the next pass is 16 rows further
               const int nx = psmp + 16;
-              const int q = nx / g.ns;
-              pgrp += q;
-              psmp = nx - q * g.ns;
+              if (g.ns >= 16) {  // at most one group boundary per pass: no division
+                const bool wrap = nx >= g.ns;
+                pgrp += wrap ? 1 : 0;
+                psmp = wrap ? nx - g.ns : nx;
+              } else {
+                const int q = nx / g.ns;
+                pgrp += q;
+                psmp = nx - q * g.ns;
+              }
             }
             v.x = fmaf(c0.x, gg.x, fmaf(c1.x, y.x, c2.x)); v.y = fmaf(c0.y, gg.y, fmaf(c1.y, y.y, c2.y));
             v.z = fmaf(c0.z, gg.z, fmaf(c1.z, y.z, c2.z)); v.w = fmaf(c0.w, gg.w, fmaf(c1.w, y.w, c2.w));

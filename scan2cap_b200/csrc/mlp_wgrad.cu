@@ -113,6 +113,33 @@ __device__ __forceinline__ void store_split_t(unsigned char *hi_base, unsigned c
     *reinterpret_cast<float *>(lo_base + off) = l;
   }
 }
+// The same store with the thread-constant part of the address hoisted: for a thread (data row k, segment seg) the
+// swizzled offset of channel m0 + ee is  base[e] + (m0 / 32) * 4096  (32 channels = 4 swizzle atoms of 1 KB).
+struct StoreT {
+  uint32_t base[4];  // byte offset of step e inside a 32-channel block
+  int ee[4];         // which of the thread's four channels step e stores
+};
+__device__ __forceinline__ StoreT make_store_t(int k, int seg) {
+  StoreT st;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    st.ee[e] = (e + (seg >> 1)) & 3;
+    st.base[e] = swz_elem(seg * 4 + st.ee[e], k);
+  }
+  return st;
+}
+__device__ __forceinline__ void store_split_t(unsigned char *hi_base, unsigned char *lo_base, const StoreT &st, int mb, float4 v) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int ee = st.ee[e];
+    const float val = ee == 0 ? v.x : (ee == 1 ? v.y : (ee == 2 ? v.z : v.w));
+    float h, l;
+    split_tf32(val, h, l);
+    const uint32_t off = st.base[e] + (uint32_t)mb * 4096u;
+    *reinterpret_cast<float *>(hi_base + off) = h;
+    *reinterpret_cast<float *>(lo_base + off) = l;
+  }
+}
 __device__ __forceinline__ float4 ld4_guard(const float *base, long long ld, long long row, long long R, int col, int ncols) {
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (row < R) {
@@ -166,6 +193,7 @@ mlp_wgrad_kernel(WgradArgs g) {
   if (warp < kLoadWarps) {
     // ===================== load + transform: global -> prologue -> hi/lo split -> transposed K-major operand blocks
     const int r = tid >> 3, seg = tid & 7;  // 256 threads = 32 rows x 8 sixteen-byte segments
+    const StoreT st = make_store_t(r, seg);
     const int CB = (g.C + 31) / 32;         // real channel blocks of A
     const bool affine = g.a != nullptr;
     const bool xpro = g.xs != nullptr;
@@ -219,7 +247,7 @@ mlp_wgrad_kernel(WgradArgs g) {
             v.z = fmaf(ca[2], v.z, fmaf(cb[2], y.z, cc[2])); v.w = fmaf(ca[3], v.w, fmaf(cb[3], y.w, cc[3]));
             if (row >= g.R) v = make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          store_split_t(a_hi, a_lo, ch, r, seg, v);
+          store_split_t(a_hi, a_lo, st, mb, v);
         }
       }
 #pragma unroll
@@ -238,7 +266,7 @@ mlp_wgrad_kernel(WgradArgs g) {
             v.z = fmaxf(fmaf(v.z, xs[2], xh[2]), 0.f); v.w = fmaxf(fmaf(v.w, xs[3], xh[3]), 0.f);
             if (row >= g.R) v = make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          store_split_t(b_hi, b_lo, ch, r, seg, v);
+          store_split_t(b_hi, b_lo, st, nb, v);
         }
       }
       fence_async_proxy();

@@ -181,6 +181,17 @@ def main():
     ap.add_argument("--ref-device", default="auto", choices=["auto", "cuda", "cpu"])
     args = ap.parse_args()
 
+    # stdout carries exactly ONE JSON line: anything libraries print on fd 1 meanwhile (e.g. NCCL's version banner
+    # at communicator creation) is routed to stderr, and fd 1 is restored for the final print
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -204,7 +215,7 @@ def main():
                     "data": "synthetic", "config": {"workload": args.config, "points": N, "note": "CPU oracle port"},
                     "cpu_baseline": cb,
                     "e2e": {"value": cb["value"], "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-            print(json.dumps(line))
+            emit(line)
             return
         from oracle import ref_model as R
         R.set_backend(ext)
@@ -357,7 +368,7 @@ def main():
             line["cpu_baseline"] = cpu_baseline(args.config, scenes=4)
         except Exception as e:  # never lose the GPU numbers to a host-side problem
             line["cpu_baseline"] = {"error": repr(e)}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

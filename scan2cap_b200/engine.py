@@ -30,6 +30,10 @@ class TrainStep(object):
         self.loss_fn = loss_fn or get_scene_cap_loss
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self._graphs = {}
+        self._stage = {}           # signature -> staging copies of the static input buffers (prefetch target)
+        self._prefetched = None    # (data_dict object, signature) whose inputs are in flight / in the staging buffers
+        self._copy_stream = None
+        self._stage_free = None    # event: the staging buffers have been copied into the static inputs
         self.kernels_per_step = None
         self.last = None  # data_dict of the last step (outputs live in graph-owned memory when graphed)
 
@@ -94,6 +98,32 @@ class TrainStep(object):
                 static[k].copy_(v, non_blocking=True)
 
     # ---- public ----------------------------------------------------------------------------------------------
+    def prefetch(self, data_dict):
+        """Start copying the NEXT step's inputs (pinned host tensors) to the device on a copy stream, so the transfer
+        overlaps the step that is currently running; pass the SAME dict object to run() afterwards (and do not modify
+        its tensors in between).  A no-op until the graph for this input signature exists, or without CUDA graphs."""
+        if not self.use_graph:
+            return
+        if "num_words" not in data_dict:
+            data_dict["num_words"] = int(data_dict["lang_len"].max().item())
+        sig = self._signature(data_dict)
+        if sig not in self._graphs:
+            return
+        static = self._graphs[sig][0]
+        if sig not in self._stage:
+            self._stage[sig] = {k: torch.empty_like(v) for k, v in static.items() if isinstance(v, torch.Tensor)}
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        if self._stage_free is not None:
+            # wait only for the staging -> static copies of the step that consumed the staging buffers last (an event
+            # recorded before that step's graph replay), NOT for the step itself: the transfer overlaps its compute
+            self._copy_stream.wait_event(self._stage_free)
+        with torch.cuda.stream(self._copy_stream):
+            for k, v in data_dict.items():
+                if isinstance(v, torch.Tensor):
+                    self._stage[sig][k].copy_(v, non_blocking=True)
+        self._prefetched = (data_dict, sig)
+
     def run(self, data_dict):
         """One training step on `data_dict` (host or device tensors; include the Python int "num_words" =
         lang_len.max() to avoid a device->host read).  Returns the (device) scalar loss."""
@@ -109,7 +139,16 @@ class TrainStep(object):
         if sig not in self._graphs:
             self._graphs[sig] = self._capture(data_dict)
         static, g1, g2, out = self._graphs[sig]
-        self._load(static, data_dict)
+        if self._prefetched is not None and self._prefetched[0] is data_dict and self._prefetched[1] == sig:
+            # inputs already on the device (prefetch): wait for the copy stream, then staging -> static (device copies)
+            torch.cuda.current_stream(self.device).wait_stream(self._copy_stream)
+            for k, v in self._stage[sig].items():
+                static[k].copy_(v, non_blocking=True)
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record(torch.cuda.current_stream(self.device))
+        else:
+            self._load(static, data_dict)
+        self._prefetched = None
         g1.replay()
         if g2 is not None:
             self.flat.all_reduce_mean()

@@ -45,6 +45,47 @@ def test_argument_validation_without_a_device():
         _lib.call("s2c_knn_adjacency", None, None, None, 1, 2000, 1, 10, 1, 0, 0.5, None, None, None)
 
 
+def test_argument_validation_of_the_fused_entry_points():
+    """The entry points added for the fused training path reject bad shapes with a message, before any CUDA call."""
+    from scan2cap_b200 import _lib
+    L = _lib.LIB
+    P = _lib.CaptionParams()
+    P.B, P.T, P.K, P.E, P.H, P.F = 8, 5, 256, 300, 500, 128      # H not a multiple of 64
+    P.ld_tdh = 940
+    assert L.s2c_caption_decode_fwd(ctypes.byref(P), None) == 1 and b"multiple of 64" in L.s2c_last_error()
+    P.H = 512
+    assert L.s2c_caption_decode_bwd(ctypes.byref(P), None) == 1 and b"null" in L.s2c_last_error()
+    assert L.s2c_bn_finalize(None, None, 0, 64, None, None, 1e-5, 0.1, 1, 1, None, None, None, None, None, None, None, None) == 1
+    assert L.s2c_bn_backward_coeffs(None, None, None, None, None, 10, 0, 1, None, None, None, None, None, None) == 0   # N = 0: no-op
+    assert L.s2c_group_rows_grad(None, 4, 3, 8, None, 1, 10, 5, ctypes.c_float(1.0), None, None) == 1                    # ld < c0 + C
+    assert L.s2c_mlp_layer_bwd_input(None, 64, None, 64, 100, 64, None, None, None, None, 132, 96, None, 132, None, None, None) == 1
+    assert b"64, 128 or 256" in L.s2c_last_error()
+    assert L.s2c_gemm_tn(None, 8, None, 8, 4, 0, 8, None, 8, None, None) == 0                                           # M = 0: no-op
+    assert L.s2c_col_sum(None, 4, 10, 8, None, None) == 1                                                                # lda < M
+    assert L.s2c_ball_query_grid_workspace_bytes(8, 40000) > 8 * 40000 * 16
+
+
+def test_first_layer_weight_layouts_round_trip():
+    """Host logic of the fused MLP: the first layer's weight in the column layout of the grouped rows
+    ([x,y,z,0 | features | pad], or zero-padded plain rows) and the inverse mapping of its gradient."""
+    import torch
+    from scan2cap_b200.lib.pointnet2 import fused_mlp as fm
+    W = torch.arange(6 * 131, dtype=torch.float32).view(6, 131)          # SA2: 3 + 128 input channels
+    Wp, Kp = fm._first_layer_weight(W, 131, 132, True)
+    assert Kp == 132 and Wp.shape == (6, 132)
+    assert torch.equal(Wp[:, :3], W[:, :3]) and float(Wp[:, 3].abs().sum()) == 0 and torch.equal(Wp[:, 4:], W[:, 3:])
+    assert torch.equal(fm._first_layer_weight_grad(Wp, 131, True), W)
+    W7 = torch.randn(4, 7)                                               # SA1 with C=4: rows of 8 floats
+    Wp, Kp = fm._first_layer_weight(W7, 7, 8, True)
+    assert Kp == 8 and torch.equal(fm._first_layer_weight_grad(Wp, 7, True), W7) and float(Wp[:, 3].abs().sum()) == 0
+    Wq, Kq = fm._first_layer_weight(W7, 7, 8, False)                     # plain rows padded to a multiple of 4
+    assert Kq == 8 and torch.equal(Wq[:, :7], W7) and torch.equal(fm._first_layer_weight_grad(Wq, 7, False), W7)
+    assert fm._input_blocks(131, 132, True) == [(4, 128)]
+    assert fm._input_blocks(259, 260, True) == [(4, 256)]
+    assert fm._input_blocks(512, 512, False) == [(0, 256), (256, 256)]
+    assert fm._input_blocks(7, 8, True) is None and fm._input_blocks(100, 100, False) is None
+
+
 def test_dropin_aliases():
     code = ("import sys; sys.path.insert(0, %r)\n"
             "import scan2cap_b200.dropin as d; d.install()\n"

@@ -20,6 +20,7 @@
 // that leaves out[i = lane/8][r = lane%8] in each lane.
 #include <stdlib.h>
 
+#define S2C_CAP_NT 512
 #include "caption_common.cuh"
 
 namespace s2c {
@@ -361,7 +362,7 @@ caption_bwd_kernel(const s2c_caption_params P, const int level) {
     cl_sync();
     // ---- B4: attention backward
     load_rows(sp.att, F, P.datt + tb * F, F, F, nb);             // d att (8,F)
-    load_flat(sp.probs, P.probs + tb * K, nb * K);
+    for (int i = threadIdx.x; i < nb * K; i += kThreads) sp.probs[i] = __ldcg(P.probs + tb * K + i);
     __syncthreads();
     // dp[r][i] = d att . obj_k (+ d probs) -> sp.sc, per (row, valid object): one warp each
     for (int r = 0; r < nb; ++r) {

@@ -3,6 +3,11 @@
 #pragma once
 #include "s2c_common.cuh"
 
+// threads per CTA of the including kernel file (a compile-time constant gives tighter loops than S2C_CAP_NT)
+#ifndef S2C_CAP_NT
+#define S2C_CAP_NT blockDim.x
+#endif
+
 namespace s2c {
 namespace {
 
@@ -78,15 +83,26 @@ __device__ __forceinline__ float gemv_quad(const float *__restrict__ w0, const f
 
 // global (nb rows of ncols floats, row stride ldg) -> shared (8 rows, stride xld), rows >= nb zero; L2 loads (.cg):
 // the data was written by other CTAs of the cluster earlier in this kernel
+// BATCH = 4 (persistent-grid kernels, 256 threads): four independent loads per thread before the first shared-memory
+// store -- an in-order warp otherwise pays one L2 round trip per element it moves.  BATCH = 1 (cluster kernels, 512
+// threads at the 128-register limit): the plain loop; the batched form measured 10 % slower there (spills).
+template <int BATCH = 1>
 __device__ __forceinline__ void load_rows(float *xs, int xld, const float *g, size_t ldg, int ncols, int nb) {
   const int c4 = ncols >> 2, total = kRows * c4;
-  // four independent loads per thread before the first shared-memory store (an in-order warp would otherwise pay
-  // one L2 round trip per element it moves)
-  for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
+  if (BATCH == 1) {
+    for (int i = threadIdx.x; i < total; i += S2C_CAP_NT) {
+      const int r = i / c4, c = (i - r * c4) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g != nullptr && r < nb) v = __ldcg(reinterpret_cast<const float4 *>(g + (size_t)r * ldg + c));
+      *reinterpret_cast<float4 *>(xs + r * xld + c) = v;
+    }
+    return;
+  }
+  for (int i0 = threadIdx.x; i0 < total; i0 += 4 * S2C_CAP_NT) {
     float4 v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * blockDim.x;
+      const int i = i0 + u * S2C_CAP_NT;
       v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (i < total) {
         const int r = i / c4, c = (i - r * c4) * 4;
@@ -95,7 +111,7 @@ __device__ __forceinline__ void load_rows(float *xs, int xld, const float *g, si
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * blockDim.x;
+      const int i = i0 + u * S2C_CAP_NT;
       if (i < total) {
         const int r = i / c4, c = (i - r * c4) * 4;
         *reinterpret_cast<float4 *>(xs + r * xld + c) = v[u];
@@ -105,16 +121,16 @@ __device__ __forceinline__ void load_rows(float *xs, int xld, const float *g, si
 }
 // n floats global (L2) -> shared, four independent loads per thread at a time
 __device__ __forceinline__ void load_flat(float *dst, const float *src, int n) {
-  for (int i0 = threadIdx.x; i0 < n; i0 += 4 * blockDim.x) {
+  for (int i0 = threadIdx.x; i0 < n; i0 += 4 * S2C_CAP_NT) {
     float v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * blockDim.x;
+      const int i = i0 + u * S2C_CAP_NT;
       v[u] = i < n ? __ldcg(src + i) : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * blockDim.x;
+      const int i = i0 + u * S2C_CAP_NT;
       if (i < n) dst[i] = v[u];
     }
   }
@@ -215,7 +231,7 @@ __device__ __forceinline__ void build_valid_lists(const SmemPlan &sp, const floa
       sp.nv[r] = 0; sp.uniform[r] = 0;
     }
   }
-  for (int i = threadIdx.x; i < kRows * K; i += blockDim.x) sp.probs[i] = 0.f;
+  for (int i = threadIdx.x; i < kRows * K; i += S2C_CAP_NT) sp.probs[i] = 0.f;
   __syncthreads();
   if (threadIdx.x == 0) {
     int tot = 0;
@@ -226,13 +242,13 @@ __device__ __forceinline__ void build_valid_lists(const SmemPlan &sp, const floa
   if (sp.pb[kRows] >= 0) {  // the valid set is the same for every word: keep those proposals' features on chip
     const int f4 = F >> 2;
     for (int r = 0; r < kRows; ++r)
-      for (int ii = threadIdx.x; ii < sp.nv[r]; ii += blockDim.x) {
+      for (int ii = threadIdx.x; ii < sp.nv[r]; ii += S2C_CAP_NT) {
         sp.pair_r[sp.pb[r] + ii] = r;
         sp.pair_k[sp.pb[r] + ii] = sp.vk[r * K + ii];
       }
     for (int r = 0; r < ((sp.mask & 1) ? nb : 0); ++r) {
       const int n = sp.nv[r];
-      for (int i = threadIdx.x; i < n * f4; i += blockDim.x) {
+      for (int i = threadIdx.x; i < n * f4; i += S2C_CAP_NT) {
         const int ii = i / f4, c = (i - ii * f4) * 4;
         const int k = sp.vk[r * K + ii];
         *reinterpret_cast<float4 *>(sp.objs + (size_t)(sp.pb[r] + ii) * F + c) =

@@ -8,6 +8,7 @@
 //
 // Stage structure per word (forward): S1 u | S2 GRU-1 | S3 q | S4a attention scores of this CTA's (scene, proposal) pair
 // | S4b softmax, attended features, language MLP | S5 GRU-2 : 6 grid barriers.  Backward: 6 barriers (see caption.cu).
+#define S2C_CAP_NT 256
 #include "caption_common.cuh"
 
 namespace s2c {
@@ -114,7 +115,7 @@ caption_fwd_grid_kernel(const s2c_caption_params P, unsigned int *bar, const int
     const size_t tb = (size_t)t * B, tb_prev = (size_t)(t - 1) * B;
     // ---- S1: u = relu(pre_word_t + pre_tgt + W_tdh h2)
     stamp(P.dbg_ts, c, t, 0);
-    load_rows(sp.XB, XLD, t > 0 ? P.h2 + tb_prev * H : nullptr, H, H, nb);
+    load_rows<4>(sp.XB, XLD, t > 0 ? P.h2 + tb_prev * H : nullptr, H, H, nb);
     __syncthreads();
     for (int q = warp; q < nqe; q += kGWarps) {
       const float v = gemv_quad<true>(QUAD_SM(s_tdh + (size_t)q * 4 * H, H), H, sp.XB, XLD, lane);
@@ -126,8 +127,8 @@ caption_fwd_grid_kernel(const s2c_caption_params P, unsigned int *bar, const int
     grid_sync(bar, target, CL);
     stamp(P.dbg_ts, c, t, 2);
     // ---- S2: GRU cell 1 on (u, h1_prev)
-    load_rows(sp.XA, XLD, P.u + tb * E, E, E, nb);
-    load_rows(sp.XB, XLD, t > 0 ? P.h1 + tb_prev * H : nullptr, H, H, nb);
+    load_rows<4>(sp.XA, XLD, P.u + tb * E, E, E, nb);
+    load_rows<4>(sp.XB, XLD, t > 0 ? P.h1 + tb_prev * H : nullptr, H, H, nb);
     __syncthreads();
     for (int q = warp; q < 6 * nqh; q += kGWarps) {
       const int m = q / (3 * nqh), rem = q - m * 3 * nqh;  // rem = g*nqh + quad-in-gate: rows rem*4.. of the [3*hs] block
@@ -140,7 +141,7 @@ caption_fwd_grid_kernel(const s2c_caption_params P, unsigned int *bar, const int
     stamp(P.dbg_ts, c, t, 3);
     grid_sync(bar, target, CL);
     // ---- S3: q = W_hidd h1   (h1 goes to columns [F, F+H) of XA, where the language MLP expects it: x = [att ; h1])
-    load_rows(sp.XA + F, XLD, P.h1 + tb * H, H, H, nb);
+    load_rows<4>(sp.XA + F, XLD, P.h1 + tb * H, H, H, nb);
     __syncthreads();
     for (int q = warp; q < nqh; q += kGWarps) {
       const float v = gemv_quad<true>(QUAD_SM(s_hidd + (size_t)q * 4 * H, H), H, sp.XA + F, XLD, lane);
@@ -149,7 +150,7 @@ caption_fwd_grid_kernel(const s2c_caption_params P, unsigned int *bar, const int
     grid_sync(bar, target, CL);
     stamp(P.dbg_ts, c, t, 4);
     // ---- S4a: attention scores (q in XB)
-    load_rows(sp.XB, XLD, P.q + tb * H, H, H, nb);
+    load_rows<4>(sp.XB, XLD, P.q + tb * H, H, H, nb);
     __syncthreads();
     if (split) {
       for (int o = warp; o < n_own; o += kGWarps) {
@@ -250,8 +251,8 @@ caption_fwd_grid_kernel(const s2c_caption_params P, unsigned int *bar, const int
     grid_sync(bar, target, CL);
     stamp(P.dbg_ts, c, t, 6);
     // ---- S5: GRU cell 2 on (l, h2_prev)
-    load_rows(sp.XA, XLD, P.lang + tb * E, E, E, nb);
-    load_rows(sp.XB, XLD, t > 0 ? P.h2 + tb_prev * H : nullptr, H, H, nb);
+    load_rows<4>(sp.XA, XLD, P.lang + tb * E, E, E, nb);
+    load_rows<4>(sp.XB, XLD, t > 0 ? P.h2 + tb_prev * H : nullptr, H, H, nb);
     __syncthreads();
     for (int q = warp; q < 6 * nqh; q += kGWarps) {
       const int m = q / (3 * nqh), rem = q - m * 3 * nqh;
@@ -341,7 +342,7 @@ caption_bwd_grid_kernel(const s2c_caption_params P, unsigned int *bar, const int
     gru_backward(d2, P.d_h2, hs, S.j0, H, nb, tb, tb_prev, t == 0, P.r2, P.z2, P.n2, P.hn2, P.h2, P.dgi2, P.dgh2);
     grid_sync(bar, target, CL);
     // ---- B2: d l_pre = (W_ih2^T dgi2) * [l > 0]  ;  dh2 += W_hh2^T dgh2 (own units)
-    load_rows(X, XLD, P.dgi2 + tb * 3 * H, 3 * H, 3 * H, nb);
+    load_rows<4>(X, XLD, P.dgi2 + tb * 3 * H, 3 * H, 3 * H, nb);
     __syncthreads();
     for (int q = warp; q < nqe; q += kGWarps) {
       const float v = gemv_quad<true>(QUAD_SM(s_ih2 + (size_t)q * 4 * 3 * H, 3 * H), 3 * H, X, XLD, lane);
@@ -352,7 +353,7 @@ caption_bwd_grid_kernel(const s2c_caption_params P, unsigned int *bar, const int
       }
     }
     __syncthreads();
-    load_rows(X, XLD, P.dgh2 + tb * 3 * H, 3 * H, 3 * H, nb);
+    load_rows<4>(X, XLD, P.dgh2 + tb * 3 * H, 3 * H, 3 * H, nb);
     __syncthreads();
     for (int q = warp; q < nqh; q += kGWarps) {
       const float v = gemv_quad<true>(QUAD_SM(s_hh2 + (size_t)q * 4 * 3 * H, 3 * H), 3 * H, X, XLD, lane);
@@ -360,7 +361,7 @@ caption_bwd_grid_kernel(const s2c_caption_params P, unsigned int *bar, const int
     }
     grid_sync(bar, target, CL);
     // ---- B3: [d att ; d h1] = W_lang^T d l_pre
-    load_rows(X, XLD, P.dlang + tb * E, E, E, nb);
+    load_rows<4>(X, XLD, P.dlang + tb * E, E, E, nb);
     __syncthreads();
     for (int q = warp; q < nqf + nqh; q += kGWarps) {
       if (q < nqf) {
@@ -375,7 +376,7 @@ caption_bwd_grid_kernel(const s2c_caption_params P, unsigned int *bar, const int
     }
     grid_sync(bar, target, CL);
     // ---- B4: attention backward
-    load_rows(sp.att, F, P.datt + tb * F, F, F, nb);
+    load_rows<4>(sp.att, F, P.datt + tb * F, F, F, nb);
     load_flat(sp.probs, P.probs + tb * K, nb * K);
     __syncthreads();
     for (int r = 0; r < nb; ++r) {
@@ -434,7 +435,7 @@ caption_bwd_grid_kernel(const s2c_caption_params P, unsigned int *bar, const int
     }
     grid_sync(bar, target, CL);
     // ---- B5: dh1 += W_hidd^T dq (own units) ; B6: GRU cell 1 backward (own units)
-    load_rows(X, XLD, P.dq + tb * H, H, H, nb);
+    load_rows<4>(X, XLD, P.dq + tb * H, H, H, nb);
     __syncthreads();
     for (int q = warp; q < nqh; q += kGWarps) {
       const float v = gemv_quad<true>(QUAD_SM(s_hidd + (size_t)q * 4 * H, H), H, X, XLD, lane);
@@ -444,7 +445,7 @@ caption_bwd_grid_kernel(const s2c_caption_params P, unsigned int *bar, const int
     gru_backward(d1, nullptr, hs, S.j0, H, nb, tb, tb_prev, t == 0, P.r1, P.z1, P.n1, P.hn1, P.h1, P.dgi1, P.dgh1);
     grid_sync(bar, target, CL);
     // ---- B7: d u_pre = (W_ih1^T dgi1) * [u > 0]  ;  dh1 += W_hh1^T dgh1 (own units)
-    load_rows(X, XLD, P.dgi1 + tb * 3 * H, 3 * H, 3 * H, nb);
+    load_rows<4>(X, XLD, P.dgi1 + tb * 3 * H, 3 * H, 3 * H, nb);
     __syncthreads();
     for (int q = warp; q < nqe; q += kGWarps) {
       const float v = gemv_quad<true>(QUAD_SM(s_ih1 + (size_t)q * 4 * 3 * H, 3 * H), 3 * H, X, XLD, lane);
@@ -455,7 +456,7 @@ caption_bwd_grid_kernel(const s2c_caption_params P, unsigned int *bar, const int
       }
     }
     __syncthreads();
-    load_rows(X, XLD, P.dgh1 + tb * 3 * H, 3 * H, 3 * H, nb);
+    load_rows<4>(X, XLD, P.dgh1 + tb * 3 * H, 3 * H, 3 * H, nb);
     __syncthreads();
     for (int q = warp; q < nqh; q += kGWarps) {
       const float v = gemv_quad<true>(QUAD_SM(s_hh1 + (size_t)q * 4 * 3 * H, 3 * H), 3 * H, X, XLD, lane);
@@ -463,7 +464,7 @@ caption_bwd_grid_kernel(const s2c_caption_params P, unsigned int *bar, const int
     }
     grid_sync(bar, target, CL);
     // ---- B8: dh2 += W_tdh^T d u_pre (own units; consumed by this CTA's B1 of the previous word)
-    load_rows(X, XLD, P.du + tb * E, E, E, nb);
+    load_rows<4>(X, XLD, P.du + tb * E, E, E, nb);
     __syncthreads();
     for (int q = warp; q < nqh; q += kGWarps) {
       const float v = gemv_quad<true>(QUAD_SM(s_tdh + (size_t)q * 4 * E, E), E, X, XLD, lane);

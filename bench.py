@@ -54,10 +54,16 @@ LOSS_FLAGS = dict(detection=True, caption=True, orientation=True, distance=False
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    fallback = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
     if os.path.exists(p):
-        with open(p) as f:
-            return json.load(f), "measured (MEASURED_PEAKS.json)"
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+        try:
+            with open(p) as f:
+                pk = json.load(f)
+            if float(pk["hbm_gbs"]) > 0:
+                return pk, "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return fallback, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler(object):

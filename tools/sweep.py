@@ -24,8 +24,13 @@ from scan2cap_b200.lib.pointnet2 import _ext  # noqa: E402
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        with open(p) as f:
-            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json"
+        try:
+            with open(p) as f:
+                v = float(json.load(f)["hbm_gbs"])
+            if v > 0:
+                return v, "MEASURED_PEAKS.json"
+        except Exception:
+            pass
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 

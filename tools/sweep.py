@@ -107,8 +107,9 @@ def main():
                     row(op="group_points", N=N, M=M, ns=ns, C=C, B=B, ours_ms=t_o, ref_ms=t_r, alg_bytes=alg,
                         GBps=alg / t_o / 1e6, frac_hbm=alg / t_o / 1e6 / peak)
                 # fused QueryAndGroup.forward
+                # the product layout: channels-last rows [x,y,z,0 | features | pad] (what PointnetSAModuleVotes requests)
                 t_o = timeit(lambda: _ext.query_and_group(xyz, new_xyz, feats_pm, radius, ns, True,
-                                                          feat_point_major=True, channels_last=True))
+                                                          feat_point_major=True, channels_last=True, pad4=True))
 
                 def ref_qg():
                     i = ref.ball_query(new_xyz, xyz, radius, ns)

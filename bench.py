@@ -6,23 +6,27 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
            bench.py --gpus N --steps K --warmup W
 
-Workload at N=1 (config "c3" = BASELINE.json configs[2]): CapNet(top-down caption, relation graph, orientation
-head, num_graph_steps=2, num_proposals=256, num_locals=10), batch 8 per GPU, 40 000 points of XYZ+normal+height
-(7 floats), vocabulary 3 500, fp32 (TF32 off on both arms), random-init weights, synthetic scenes
+Headline workload (all N; config "c3" = BASELINE.json configs[2]): CapNet(top-down caption, relation graph,
+orientation head, num_graph_steps=2, num_proposals=256, num_locals=10), batch 8 per GPU, 40 000 points of
+XYZ+normal+height (7 floats), vocabulary 3 500, fp32 (TF32 off on both arms), random-init weights, synthetic scenes
 (scan2cap_b200/synthetic.py).  Weak scaling: every rank gets its own 8 scenes; one NCCL all-reduce on one flat
-gradient buffer per step.
+gradient buffer per step, captured inside the step's CUDA graph.
+
+The same run also measures BASELINE.json configs[3] ("config4" in the JSON line: 4 scenes per GPU of
+XYZ+multiview+normal+height = 135 floats per point, the configuration the 8-GPU target is quoted on) with the same
+timing rules, and the fused ball_query+group_points kernel at the shape where bytes dominate ("roofline_c132").
 
 One JSON line is printed by rank 0 (contract in the task statement): value = device-timed whole-job
 scenes/sec with inputs resident in HBM; e2e = the same step fed from pinned HOST memory (H2D of the whole
 data_dict and D2H of the loss inside the timed region); roofline = the fused ball_query+group_points kernel of
 SA1 (nsample = 64), timed live with CUDA events inside the timed steps, against the measured HBM peak;
-cpu_baseline = the oracle port of the reference on the host cores (bounded sample).
+cpu_baseline = BASELINE configs[0], the reference's own CPU-runnable capnet_pretrained path on the host cores.
 
---impl reference runs the reference's stock code path: the UNMODIFIED lib/pointnet2 CUDA kernels re-compiled
-for sm_100 (oracle/_ref/pointnet2_ref_ext.so) under the literal restatement of the reference's Python layers
-(oracle/ref_model.py: unfused conv/BN/ReLU/max-pool, 256-iteration adjacency loop, per-scene graphs, per-scene
-.item() syncs) -- none of our kernels or modules.  If the extension is missing it falls back to the CPU-only
-oracle port on the host cores.
+--impl reference runs the reference's stock code path and NOTHING of ours: the UNMODIFIED reference Python modules
+(baseline/_ref, a git-ignored verbatim copy made by baseline/install_ref.py) over the UNMODIFIED lib/pointnet2
+CUDA kernels re-compiled for sm_100 (oracle/_ref/pointnet2_ref_ext.so), issued as lib/solver.py issues a training
+iteration.  That process imports neither scan2cap_b200 nor the oracle restatements (asserted before the line is
+printed).  With N > 1 each rank is an independent replica (the reference has no multi-GPU mode).
 """
 import argparse
 import json
@@ -38,7 +42,6 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 CONFIGS = {
     # name: (batch per GPU, points, use_normal, use_multiview)
@@ -50,6 +53,7 @@ VOCAB = 3500
 MODEL_CFG = dict(num_proposal=256, num_locals=10, use_topdown=True, query_mode="center", graph_mode="edge_conv",
                  num_graph_steps=2, use_relation=True, use_orientation=True)
 LOSS_FLAGS = dict(detection=True, caption=True, orientation=True, distance=False)
+METRIC = "scenes/sec CapNet fwd+bwd @40k pts"
 
 
 def peaks():
@@ -110,69 +114,361 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_inputs(cfg_name, seed, rank):
-    from scan2cap_b200 import synthetic
-    B, N, use_normal, use_mv = CONFIGS[cfg_name]
-    d = synthetic.make_data_dict(B, N, use_normal=use_normal, use_multiview=use_mv, num_vocabs=VOCAB,
-                                 seed=seed + 100000 * rank)
-    host = {k: torch.from_numpy(v).pin_memory() for k, v in d.items()}
-    num_words = int(d["lang_len"].max())
-    C = host["point_clouds"].shape[-1] - 3
-    return host, num_words, C
+def workload_string(name, B, N, F, num_words):
+    return ("%s: full CapNet training step (zero_grad+fwd+loss+bwd+grad all-reduce+Adam), batch %d/GPU, %d pts x %d "
+            "floats, K=256 proposals, L=10 locals, 2 graph steps, top-down caption, V=%d, caption length %d words"
+            % (name, B, N, F, VOCAB, num_words))
 
 
-def build_model(impl, C, device):
-    from scan2cap_b200 import synthetic
-    from scan2cap_b200.data.scannet.model_util_scannet import ScannetDatasetConfig
-    DC = ScannetDatasetConfig()
-    vocab, emb, _ = synthetic.make_vocabulary(VOCAB)
-    torch.manual_seed(42)
-    if impl == "ours":
+def cpu_baseline(budget_s=12.0):
+    """BASELINE configs[0] on the host cores, in a SUBPROCESS (its shims neutralise Tensor.cuda process-wide)."""
+    cmd = [sys.executable, "-m", "baseline.reference_arm", "--cpu-pretrained", "--budget", str(budget_s)]
+    try:
+        p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+        lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+        return json.loads(lines[-1]) if lines else {"error": (p.stderr or p.stdout)[-400:]}
+    except Exception as e:  # never lose the GPU numbers to a host-side problem
+        return {"error": repr(e)}
+
+
+class Timer(object):
+    """K steps bracketed by barrier + synchronize on both sides, CUDA events, max over ranks."""
+
+    def __init__(self, device, world):
+        self.device, self.world = device, world
+        self.flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)  # 256 MB > 126 MB L2
+
+    def run(self, K, body):
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(K):
+            self.flush.zero_()  # L2 flush between iterations (inside the timed region: conservative)
+            body(i)
+        b.record()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=self.device)
+        if self.world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------
+class Ours(object):
+    def __init__(self, cfg_name, device, rank, use_graph=True):
+        from scan2cap_b200 import synthetic
+        from scan2cap_b200.data.scannet.model_util_scannet import ScannetDatasetConfig
+        from scan2cap_b200.engine import TrainStep
         from scan2cap_b200.models.capnet import CapNet
-        from scan2cap_b200.lib.loss_helper import get_scene_cap_loss
-    else:
-        from oracle.ref_model import CapNet
-        from oracle.ref_loss import get_scene_cap_loss
-    model = CapNet(DC.num_class, vocab, emb, DC.num_heading_bin, DC.num_size_cluster, DC.mean_size_arr,
-                   input_feature_dim=C, **MODEL_CFG).to(device)
-    model.train()
-    return model, DC, get_scene_cap_loss
+        self.name, self.device = cfg_name, device
+        B, N, use_normal, use_mv = CONFIGS[cfg_name]
+        d = synthetic.make_data_dict(B, N, use_normal=use_normal, use_multiview=use_mv, num_vocabs=VOCAB,
+                                     seed=42 + 100000 * rank)
+        self.host = {k: torch.from_numpy(v).pin_memory() for k, v in d.items()}
+        self.num_words = int(d["lang_len"].max())
+        self.B, self.N, self.F = B, N, self.host["point_clouds"].shape[-1]
+        DC = ScannetDatasetConfig()
+        vocab, emb, _ = synthetic.make_vocabulary(VOCAB)
+        torch.manual_seed(42)
+        self.model = CapNet(DC.num_class, vocab, emb, DC.num_heading_bin, DC.num_size_cluster, DC.mean_size_arr,
+                            input_feature_dim=self.F - 3, **MODEL_CFG).to(device)
+        self.model.train()
+        self.engine = TrainStep(self.model, DC, lr=1e-3, weight_decay=1e-5, use_cuda_graph=use_graph, **LOSS_FLAGS)
+        # make the referred box of every scene a box the (random-init) detector proposes, so good_bbox_masks is not
+        # empty and the caption loss / its gradients are exercised (SURVEY.md section 8(d))
+        with torch.no_grad():
+            probe = self.model(self.resident())
+            self.host["ref_box_corner_label"] = probe["bbox_corner"][:, 3].detach().cpu().pin_memory()
+        del probe
+
+    def resident(self):
+        d = {k: v.to(self.device, non_blocking=True) for k, v in self.host.items()}
+        d["num_words"] = self.num_words
+        return d
+
+    def h2d_bytes(self):
+        return int(sum(v.numel() * v.element_size() for v in self.host.values()))
+
+    def timed(self, timer, K, from_host):
+        eng = self.engine
+        if not from_host:
+            res = self.resident()
+            return timer.run(K, lambda i: eng.run(dict(res))), None
+        # double-buffered input pipeline of the public API: every step's inputs travel pinned host -> device inside
+        # the timed region (K+1 transfers for K steps), each one overlapping the previous step's compute
+        state = {"nxt": dict(self.host, num_words=self.num_words), "last": None}
+        eng.prefetch(state["nxt"])
+
+        def body(i):
+            cur = state["nxt"]
+            loss = eng.run(cur)
+            state["nxt"] = dict(self.host, num_words=self.num_words)
+            eng.prefetch(state["nxt"])            # next step's H2D, in flight while this step computes
+            state["last"] = float(loss.item())    # D2H read of the step's result
+        ms = timer.run(K, body)
+        return ms, state["last"]
+
+    def query_group_events(self, timer, steps):
+        """CUDA-event time of the SA1 fused query+group entry point inside eager steps (events cannot bracket a node
+        of a replayed graph).  SA1 (n = 40 000) is the only call of the step that takes the uniform-grid entry."""
+        import scan2cap_b200._lib as L
+        res = self.resident()
+        names = ("s2c_query_and_group_grid", "s2c_query_and_group")
+        L.TIMING = {n: [] for n in names}
+        for _ in range(steps):
+            timer.flush.zero_()
+            self.engine.run_eager(dict(res))
+        torch.cuda.synchronize()
+        ev, kernel = [], None
+        for n, k in zip(names, ("grid_build_kernel + grid_query_kernel<GROUP>", "ball_query_kernel<GROUP>")):
+            if L.TIMING[n]:
+                per = len(L.TIMING[n]) // steps
+                ev = [e for i, e in enumerate(L.TIMING[n]) if i % per == 0]  # SA1 = the first call of every step
+                kernel = k
+                break
+        L.TIMING = None
+        return [s.elapsed_time(e) for s, e in ev], kernel
 
 
-def to_device(host, device, num_words=None):
-    d = {k: v.to(device, non_blocking=True) for k, v in host.items()}
-    if num_words is not None:
-        d["num_words"] = num_words  # lets the caption module skip its one D2H read (host already knows it)
-    return d
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
+    kernel at this shape (profiles/roofline_traffic.json names the .txt summary it was read from); None if absent."""
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        with open(tp) as f:
+            return json.load(f).get(key, {}).get("traffic")
+    except Exception:
+        return None
 
 
-def cpu_baseline(cfg_name, scenes=4, budget_s=12.0, max_steps=6):
-    """Oracle port of the reference (C oracle for the native ops + restated Python layers) on the host cores."""
-    from oracle import ref_model as R
-    from oracle import native
-    R.set_backend(None)
-    _, N, use_normal, use_mv = CONFIGS[cfg_name]
+def qg_roofline(t_ms, kernel, B, N, C, pk, pk_src, layout, traffic=None):
+    M, ns = 2048, 64
+    alg = B * (12 * N + 12 * M + 4 * C * N + 4 * M * ns + 4 * (3 + C) * M * ns)
+    achieved = alg / (t_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "%s (SA1: B=%d, N=%d, M=2048, nsample=64, C=%d; %s)" % (kernel, B, N, C, layout),
+            "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+            "traffic": traffic, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": t_ms, "peak_source": pk_src}
+
+
+def standalone_qg(timer, B, N, C, iters=20):
+    """The fused entry point on the ALIGNED feature layout (features (B,N,C) contiguous), timed alone with the L2
+    flushed before every launch: the BASELINE configs[4] sweep row N=40k / C=132 / nsample=64."""
     from scan2cap_b200 import synthetic
-    d = synthetic.make_data_dict(scenes, N, use_normal=use_normal, use_multiview=use_mv, num_vocabs=VOCAB, seed=7)
-    host = {k: torch.from_numpy(v) for k, v in d.items()}
-    C = host["point_clouds"].shape[-1] - 3
-    torch.set_num_threads(os.cpu_count())
-    model, DC, loss_fn = build_model("reference", C, "cpu")
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5)
-    steps, t0 = 0, time.perf_counter()
-    while True:  # bounded sample: whole steps until >= `budget_s` seconds of CPU work (at most `max_steps`)
-        out = loss_fn(model({k: v.clone() for k, v in host.items()}), "cpu", DC, None, **LOSS_FLAGS)
-        opt.zero_grad()
-        out["loss"].backward()
-        opt.step()
-        steps += 1
-        dt = time.perf_counter() - t0
-        if dt >= budget_s or steps >= max_steps:
-            break
-    return {"value": scenes * steps / dt, "unit": "scenes/s", "cores": os.cpu_count(), "kind": "port",
-            "threads": {"torch": torch.get_num_threads(), "openmp_native_ops": native.num_threads()},
-            "sample": "%d training step(s) on %d scene(s) of the same workload (N=%d), %.1f s of host time"
-                      % (steps, scenes, N, dt)}
+    from scan2cap_b200.lib.pointnet2 import _ext
+    pc, _ = synthetic.make_point_clouds(B, N, use_normal=False, use_height=False, seed=42)
+    xyz = torch.from_numpy(np.ascontiguousarray(pc[..., :3])).cuda()
+    _, new_xyz = _ext.furthest_point_sampling_with_xyz(xyz, 2048)
+    feats = torch.randn((B, N, C), device="cuda", generator=torch.Generator(device="cuda").manual_seed(N + C))
+
+    def fn():
+        return _ext.query_and_group(xyz, new_xyz, feats, 0.2, 64, True, feat_point_major=True, channels_last=True,
+                                    pad4=True)
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(iters):
+        timer.flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.mean(ts))
+
+
+def run_ours(args, emit, rank, world, local_rank):
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    import scan2cap_b200._lib as L
+    timer = Timer(device, world)
+    pk, pk_src = peaks()
+    main = Ours(args.config, device, rank, use_graph=not args.no_graph)
+
+    main.timed(timer, args.warmup, False)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    L.LAUNCH_COUNT = 0
+    ms, _ = main.timed(timer, args.steps, False)
+    launches = L.LAUNCH_COUNT
+    if main.engine.use_graph:
+        launches = main.engine.kernels_per_step * args.steps  # replayed from the graph: no Python call per launch
+    clocks = sampler.stop() if rank == 0 else None
+    qg_ms, qg_kernel = main.query_group_events(timer, min(args.steps, 5))
+    main.timed(timer, 2, True)
+    ms_e2e, last_loss = main.timed(timer, args.steps, True)
+
+    second = None
+    if args.config == "c3" and not args.no_config4:
+        # BASELINE configs[3] in the same run, same rules (fewer steps: it is the secondary line)
+        c4 = Ours("c4", device, rank, use_graph=not args.no_graph)
+        k4 = max(3, min(args.steps, 10))
+        c4.timed(timer, max(3, min(args.warmup, 5)), False)
+        ms4, _ = c4.timed(timer, k4, False)
+        qg4_ms, qg4_kernel = c4.query_group_events(timer, 3)
+        c4.timed(timer, 2, True)
+        ms4_e2e, loss4 = c4.timed(timer, k4, True)
+        second = {
+            "workload": workload_string("c4", c4.B, c4.N, c4.F, c4.num_words), "n_gpus": world,
+            "global_batch": c4.B * world, "steps": k4, "value": c4.B * world * k4 / (ms4 * 1e-3), "unit": "scenes/s",
+            "ms_per_step": ms4 / k4,
+            "e2e": {"value": c4.B * world * k4 / (ms4_e2e * 1e-3), "unit": "scenes/s", "ms_per_step": ms4_e2e / k4,
+                    "h2d_bytes_per_step": c4.h2d_bytes(), "d2h_bytes_per_step": 4, "last_loss": loss4},
+            "gpu_launches_per_step": c4.engine.kernels_per_step}
+        rc132 = {}
+        if qg4_ms:
+            rc132["product_layout"] = qg_roofline(
+                float(np.mean(qg4_ms)), qg4_kernel, c4.B, c4.N, c4.F - 3, pk, pk_src,
+                "inside the c4 training step; features are columns 3.. of point_clouds, 540-byte rows",
+                traffic=ncu_traffic("c4"))
+        if rank == 0 and world == 1:
+            t = standalone_qg(timer, 8, 40000, 132)
+            rc132["aligned_layout"] = qg_roofline(t, "grid_build_kernel + grid_query_kernel<GROUP>", 8, 40000, 132, pk,
+                                                  pk_src, "standalone launch, L2 flushed; features (B,N,132) contiguous",
+                                                  traffic=ncu_traffic("sweep_n40k_c132_ns64"))
+        del c4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    scenes = main.B * world * args.steps
+    line = {
+        "metric": METRIC, "value": scenes / (ms * 1e-3), "unit": "scenes/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_string(args.config, main.B, main.N, main.F, main.num_words),
+                   "global_batch": main.B * world, "points": main.N, "point_floats": main.F, "tf32": False,
+                   "l2": "256 MB buffer rewritten between iterations (inside the timed region)",
+                   "parallelism": "dp%d" % world},
+        "issue": ("cuda-graph replay of the whole step (%d decoder steps: caption length rounded up to a multiple of 4)"
+                  % (main.engine._words({"num_words": main.num_words, "lang_ids": main.host["lang_ids"]}) - 1)
+                  if main.engine.use_graph else "eager launches"),
+        "e2e": {"value": scenes / (ms_e2e * 1e-3), "unit": "scenes/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": main.h2d_bytes(), "d2h_bytes_per_step": 4, "last_loss": last_loss},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    if qg_ms:
+        line["roofline"] = qg_roofline(float(np.mean(qg_ms)), qg_kernel, main.B, main.N, main.F - 3, pk, pk_src,
+                                       "inside the training step", traffic=ncu_traffic(args.config))
+    if second is not None:
+        line["config4"] = second
+        if rc132:
+            line["roofline_c132"] = rc132
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline()
+    emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm: nothing of ours in this process
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference(args, emit, rank, world, local_rank):
+    from baseline import reference_arm as RA
+    from baseline import shims
+    have_gpu = torch.cuda.is_available() and args.ref_device != "cpu"
+    if not have_gpu or shims.load_reference_ext() is None:
+        # no GPU / extension: the reference's CPU-runnable case (BASELINE configs[0]); rank 0 alone runs it
+        if rank != 0:
+            return
+        cb = RA.time_cpu_pretrained()
+        RA.assert_clean_process()
+        emit({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "scenes/s", "n_gpus": 0,
+              "steps": 1, "warmup": 0, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "weak",
+              "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": cb["config"]},
+              "cpu_baseline": cb,
+              "e2e": {"value": cb["value"], "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        return
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)  # timing barrier / max over ranks only: no data-path collective
+    timer = Timer(device, world)
+
+    def measure(cfg_name, K, W):
+        B, N, use_normal, use_mv = CONFIGS[cfg_name]
+        syn = RA.load_synthetic()
+        F = 3 + 3 * use_normal + 128 * use_mv + 1
+        ref = RA.GpuReference(F - 3, VOCAB, device)
+        d = syn.make_data_dict(B, N, use_normal=use_normal, use_multiview=use_mv, num_vocabs=VOCAB,
+                               seed=42 + 100000 * rank, mean_size_arr=ref.DC.mean_size_arr)
+        host = {k: torch.from_numpy(v).pin_memory() for k, v in d.items()}
+        with torch.no_grad():
+            probe = ref.forward({k: v.to(device) for k, v in host.items()})
+            host["ref_box_corner_label"] = probe["bbox_corner"][:, 3].detach().cpu().pin_memory()
+        del probe
+        resident = {k: v.to(device) for k, v in host.items()}
+        timer.run(W, lambda i: ref.step(dict(resident)))
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        ms = timer.run(K, lambda i: ref.step(dict(resident)))
+        clocks = sampler.stop() if rank == 0 else None
+        last = [None]
+
+        def body(i):
+            last[0] = float(ref.step(dict(host)).item())   # solver.py:380-382 moves every key .to(device); D2H of the loss
+        timer.run(2, body)
+        ms_e2e = timer.run(K, body)
+        h2d = int(sum(v.numel() * v.element_size() for v in host.values()))
+        return dict(B=B, N=N, F=F, ms=ms, ms_e2e=ms_e2e, clocks=clocks, h2d=h2d, last=last[0],
+                    num_words=int(d["lang_len"].max()))
+
+    m = measure(args.config, args.steps, args.warmup)
+    second = None
+    if args.config == "c3" and not args.no_config4:
+        k4 = max(3, min(args.steps, 10))
+        m4 = measure("c4", k4, 3)
+        second = {"workload": workload_string("c4", m4["B"], m4["N"], m4["F"], m4["num_words"]), "n_gpus": world,
+                  "global_batch": m4["B"] * world, "steps": k4, "value": m4["B"] * world * k4 / (m4["ms"] * 1e-3),
+                  "unit": "scenes/s", "ms_per_step": m4["ms"] / k4,
+                  "e2e": {"value": m4["B"] * world * k4 / (m4["ms_e2e"] * 1e-3), "unit": "scenes/s",
+                          "ms_per_step": m4["ms_e2e"] / k4, "h2d_bytes_per_step": m4["h2d"], "d2h_bytes_per_step": 4,
+                          "last_loss": m4["last"]}}
+    RA.assert_clean_process()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    scenes = m["B"] * world * args.steps
+    line = {
+        "impl": "reference", "metric": METRIC, "value": scenes / (m["ms"] * 1e-3), "unit": "scenes/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms"] / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_string(args.config, m["B"], m["N"], m["F"], m["num_words"]),
+                   "global_batch": m["B"] * world, "points": m["N"], "point_floats": m["F"], "tf32": False,
+                   "l2": "256 MB buffer rewritten between iterations (inside the timed region)",
+                   "parallelism": "dp%d" % world},
+        "issue": "eager launches (the reference's own solver loop)",
+        "reference": ("UNMODIFIED reference Python (baseline/_ref: models/*.py, lib/pointnet2/*.py, lib/loss_helper.py) "
+                      "over the UNMODIFIED lib/pointnet2 CUDA kernels (sm_100 build, oracle/_ref); PyG's "
+                      "MessagePassing.propagate restated (baseline/shims.py: the one substitution); "
+                      "CUDA_LAUNCH_BLOCKING unset; N>1 = independent replicas, no collective"),
+        "e2e": {"value": scenes / (m["ms_e2e"] * 1e-3), "unit": "scenes/s", "ms_per_step": m["ms_e2e"] / args.steps,
+                "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": 4, "last_loss": m["last"]},
+        "gpu_launches": 0,
+        "clocks": m["clocks"],
+    }
+    if second is not None:
+        line["config4"] = second
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline()
+    emit(line)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
@@ -183,9 +479,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config4", action="store_true", help="skip the secondary BASELINE configs[3] measurement")
     ap.add_argument("--no-graph", action="store_true", help="ours: issue the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--ref-device", default="auto", choices=["auto", "cuda", "cpu"])
     args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
 
     # stdout carries exactly ONE JSON line: anything libraries print on fd 1 meanwhile (e.g. NCCL's version banner
     # at communicator creation) is routed to stderr, and fd 1 is restored for the final print
@@ -203,189 +501,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-
-    ref_on_cpu = False
     if args.impl == "reference":
-        from conftest import load_reference_ext
-        ext = load_reference_ext() if args.ref_device != "cpu" else None
-        ref_on_cpu = ext is None or not torch.cuda.is_available()
-        if ref_on_cpu:
-            # CPU-only oracle port: rank 0 alone runs it
-            if rank != 0:
-                return
-            cb = cpu_baseline(args.config, scenes=4)
-            B, N, _, _ = CONFIGS[args.config]
-            line = {"impl": "reference", "metric": "scenes/sec CapNet fwd+bwd @40k pts", "value": cb["value"],
-                    "unit": "scenes/s", "n_gpus": 0, "steps": 1, "warmup": 0, "ms_per_step": 1e3 / cb["value"],
-                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                    "data": "synthetic", "config": {"workload": args.config, "points": N, "note": "CPU oracle port"},
-                    "cpu_baseline": cb,
-                    "e2e": {"value": cb["value"], "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-            emit(line)
-            return
-        from oracle import ref_model as R
-        R.set_backend(ext)
-
-    device = torch.device("cuda", local_rank)
-    torch.cuda.set_device(device)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-
-    host, num_words, C = build_inputs(args.config, seed=42, rank=rank)
-    model, DC, loss_fn = build_model(args.impl, C, device)
-    B, N = host["point_clouds"].shape[0], host["point_clouds"].shape[1]
-    from scan2cap_b200.distributed import FlatGradients
-    engine = None
-    if args.impl == "ours":
-        from scan2cap_b200.engine import TrainStep
-        engine = TrainStep(model, DC, lr=1e-3, weight_decay=1e-5, use_cuda_graph=not args.no_graph, **LOSS_FLAGS)
+        run_reference(args, emit, rank, world, local_rank)
     else:
-        flat = FlatGradients(model)
-        opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5)
-
-    # make the referred box of every scene a box the (random-init) detector proposes, so good_bbox_masks is not
-    # empty and the caption loss / its gradients are exercised
-    with torch.no_grad():
-        probe = model(to_device(host, device, num_words))
-        host["ref_box_corner_label"] = probe["bbox_corner"][:, 3].detach().cpu().pin_memory()
-    del probe
-
-    import scan2cap_b200._lib as L
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)  # 256 MB > 126 MB L2
-
-    def step(data):
-        if engine is not None:
-            return engine.run(data)
-        flat.zero_()
-        out = loss_fn(model(data), device, DC, None, **LOSS_FLAGS)
-        out["loss"].backward()
-        flat.all_reduce_mean()
-        opt.step()
-        return out["loss"]
-
-    def timed(K, from_host):
-        resident = None if from_host else to_device(host, device, num_words)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        last = None
-        nxt = None
-        if from_host and engine is not None:
-            # double-buffered input pipeline of the public API: every step's inputs travel pinned host -> device inside
-            # the timed region (K+1 transfers for K steps), each one overlapping the previous step's compute
-            nxt = dict(host, num_words=num_words)
-            engine.prefetch(nxt)
-        for _ in range(K):
-            flush.zero_()  # L2 flush between iterations (inside the timed region: conservative)
-            if from_host:
-                if engine is not None:  # the engine copies pinned host tensors into its static device buffers
-                    cur = nxt
-                    loss = step(cur)
-                    nxt = dict(host, num_words=num_words)
-                    engine.prefetch(nxt)  # next step's H2D, in flight while this step computes
-                else:
-                    loss = step(to_device(host, device, None))
-                last = float(loss.item())  # D2H read of the step's result
-            else:
-                loss = step({k: v for k, v in resident.items()})
-        b.record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ms = torch.tensor([a.elapsed_time(b)], device=device)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), last
-
-    timed(args.warmup, False)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    L.LAUNCH_COUNT = 0
-    ms, _ = timed(args.steps, False)
-    launches = L.LAUNCH_COUNT
-    if engine is not None and engine.use_graph:
-        launches = engine.kernels_per_step * args.steps  # replayed from the graph: no Python call per launch
-    clocks = sampler.stop() if rank == 0 else None
-    # single-kernel timing for the roofline: the same step issued eagerly, CUDA events around the SA1
-    # query+group launch (events cannot bracket a node inside a replayed graph)
-    qg_name, qg_grid = "s2c_query_and_group", "s2c_query_and_group_grid"
-    qg_events, qg_steps, qg_kernel = [], min(args.steps, 5), None
-    if engine is not None:
-        resident = to_device(host, device, num_words)
-        L.TIMING = {qg_name: [], qg_grid: []}
-        for _ in range(qg_steps):
-            flush.zero_()
-            engine.run_eager(dict(resident))
-        torch.cuda.synchronize()
-        if L.TIMING[qg_grid]:
-            # SA1 (n = 40 000 >= S2C_BALL_GRID_MIN) is the only call of the step that takes the uniform-grid entry
-            # point: grid_build_kernel + grid_query_kernel<GROUP>, both inside the timed bracket
-            per = len(L.TIMING[qg_grid]) // qg_steps
-            qg_events = [e for i, e in enumerate(L.TIMING[qg_grid]) if i % per == 0]
-            qg_kernel = "grid_build_kernel + grid_query_kernel<GROUP>"
-        else:
-            # SA1 is the first query_and_group call of every step (5 per step: SA1-4 + vote aggregation)
-            per = len(L.TIMING[qg_name]) // qg_steps
-            qg_events = [e for i, e in enumerate(L.TIMING[qg_name]) if i % per == 0]
-            qg_kernel = "ball_query_kernel<GROUP>"
-        L.TIMING = None
-    timed(2, True)
-    ms_e2e, last_loss = timed(args.steps, True)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    h2d = int(sum(v.numel() * v.element_size() for v in host.values()))
-    scenes = B * world * args.steps
-    pk, pk_src = peaks()
-    line = {
-        "metric": "scenes/sec CapNet fwd+bwd @40k pts", "value": scenes / (ms * 1e-3), "unit": "scenes/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: full CapNet training step (zero_grad+fwd+loss+bwd+grad all-reduce+Adam), "
-                               "batch %d/GPU, %d pts x %d floats, K=256 proposals, L=10 locals, 2 graph steps, "
-                               "top-down caption, V=%d, %d decoder steps" % (args.config, B, N, C + 3, VOCAB, num_words - 1),
-                   "global_batch": B * world, "points": N, "point_floats": C + 3, "tf32": False,
-                   "l2": "256 MB buffer rewritten between iterations (inside the timed region)",
-                   "parallelism": "dp%d" % world,
-                   "issue": ("cuda-graph replay of the whole step" if (engine is not None and engine.use_graph)
-                             else "eager launches")},
-        "e2e": {"value": scenes / (ms_e2e * 1e-3), "unit": "scenes/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "last_loss": last_loss},
-        "gpu_launches": launches,
-        "clocks": clocks,
-    }
-    if args.impl == "reference":
-        line["impl"] = "reference"
-        line["gpu_launches"] = 0
-        line["config"]["reference"] = ("unmodified lib/pointnet2 CUDA kernels (sm_100 build, oracle/_ref) + literal "
-                                       "restatement of the reference Python layers; CUDA_LAUNCH_BLOCKING unset")
-    if qg_events:
-        t_ms = float(np.mean([s.elapsed_time(e) for s, e in qg_events]))
-        M, ns = 2048, 64
-        alg = B * (12 * N + 12 * M + 4 * C * N + 4 * M * ns + 4 * (3 + C) * M * ns)
-        achieved = alg / (t_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tp):
-            with open(tp) as f:
-                traffic = json.load(f).get(args.config, {}).get("traffic")
-        line["roofline"] = {"bound": "hbm", "kernel": "%s (SA1: N=%d, M=2048, nsample=64, C=%d)" % (qg_kernel, N, C),
-                            "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                            "traffic": traffic, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": t_ms,
-                            "peak_source": pk_src}
-    if not args.no_cpu_baseline and world == 1:
-        try:
-            line["cpu_baseline"] = cpu_baseline(args.config, scenes=4)
-        except Exception as e:  # never lose the GPU numbers to a host-side problem
-            line["cpu_baseline"] = {"error": repr(e)}
-    emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+        run_ours(args, emit, rank, world, local_rank)
 
 
 if __name__ == "__main__":

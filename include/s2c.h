@@ -230,7 +230,8 @@ S2C_API int s2c_query_and_group_grid(const float *xyz, const float *new_xyz, con
  *   statistics handling, lib/pointnet2/pytorch_utils.py:88-120 / torch batch_norm):
  *   use_batch_stats: mean = sum/R, var = max(sumsq/R - mean^2, 0) from the float64 column sums of the GEMM epilogue,
  *   else the running statistics; update_running: running = (1-momentum)*running + momentum*{mean, unbiased var},
- *   ++num_batches_tracked (may be NULL).  Outputs [N]: mean, invstd (float64) and the folded fp32 affine
+ *   ++num_batches_tracked (may be NULL); momentum < 0 = nn.BatchNorm(momentum=None): cumulative moving average with
+ *   factor 1/num_batches_tracked (value after the increment; the counter is then required).  Outputs [N]: mean, invstd (float64) and the folded fp32 affine
  *   scale = gamma*invstd, shift = beta - mean*scale that the next kernel applies in its operand prologue. */
 S2C_API int s2c_bn_finalize(const double *sum, const double *sumsq, long long R, int N, const float *gamma,
                             const float *beta, double eps, double momentum, int use_batch_stats, int update_running,

@@ -19,28 +19,37 @@ __global__ void bn_finalize_kernel(const double *__restrict__ s1, const double *
                                    long long *__restrict__ num_batches_tracked, double *__restrict__ mean_out,
                                    double *__restrict__ invstd_out, float *__restrict__ scale_out,
                                    float *__restrict__ shift_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && update_running && num_batches_tracked) *num_batches_tracked += 1;
-  if (c >= N) return;
-  double mean, var;
-  if (use_batch) {
-    mean = s1[c] / R;
-    var = fmax(s2[c] / R - mean * mean, 0.0);
-    if (update_running) {
-      const double unbiased = var * (R / fmax(R - 1.0, 1.0));
-      running_mean[c] = __fmaf_rn(momentum, (float)mean, __fmul_rn(running_mean[c], one_minus_momentum));
-      running_var[c] = __fmaf_rn(momentum, (float)unbiased, __fmul_rn(running_var[c], one_minus_momentum));
-    }
-  } else {
-    mean = (double)running_mean[c];
-    var = (double)running_var[c];
+  // ONE block (channels are looped over): every thread reads the old counter, the barrier orders the reads before the
+  // increment.  momentum < 0 selects nn.BatchNorm's momentum=None mode: cumulative moving average with factor
+  // 1 / num_batches_tracked (counter value AFTER this batch's increment), torch/nn/modules/batchnorm.py.
+  const long long seen = (update_running && num_batches_tracked) ? *num_batches_tracked : 0;
+  __syncthreads();
+  if (threadIdx.x == 0 && update_running && num_batches_tracked) *num_batches_tracked = seen + 1;
+  if (momentum < 0.f) {
+    momentum = 1.0f / (float)(seen + 1);
+    one_minus_momentum = 1.0f - momentum;
   }
-  const double invstd = 1.0 / sqrt(var + eps);
-  const double scale = (double)gamma[c] * invstd;
-  mean_out[c] = mean;
-  invstd_out[c] = invstd;
-  scale_out[c] = (float)scale;
-  shift_out[c] = (float)((double)beta[c] - mean * scale);
+  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+    double mean, var;
+    if (use_batch) {
+      mean = s1[c] / R;
+      var = fmax(s2[c] / R - mean * mean, 0.0);
+      if (update_running) {
+        const double unbiased = var * (R / fmax(R - 1.0, 1.0));
+        running_mean[c] = __fmaf_rn(momentum, (float)mean, __fmul_rn(running_mean[c], one_minus_momentum));
+        running_var[c] = __fmaf_rn(momentum, (float)unbiased, __fmul_rn(running_var[c], one_minus_momentum));
+      }
+    } else {
+      mean = (double)running_mean[c];
+      var = (double)running_var[c];
+    }
+    const double invstd = 1.0 / sqrt(var + eps);
+    const double scale = (double)gamma[c] * invstd;
+    mean_out[c] = mean;
+    invstd_out[c] = invstd;
+    scale_out[c] = (float)scale;
+    shift_out[c] = (float)((double)beta[c] - mean * scale);
+  }
 }
 
 __global__ void bn_backward_coeffs_kernel(const double *__restrict__ sum_g, const double *__restrict__ sum_gy,
@@ -115,7 +124,9 @@ extern "C" int s2c_bn_finalize(const double *sum, const double *sumsq, long long
   S2C_REQUIRE(!use_batch_stats || (sum && sumsq), "bn_finalize: batch statistics requested without sums");
   S2C_REQUIRE((use_batch_stats && !update_running) || (running_mean && running_var),
               "bn_finalize: running statistics needed but null");
-  bn_finalize_kernel<<<ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(
+  S2C_REQUIRE(momentum >= 0.0 || !update_running || num_batches_tracked,
+              "bn_finalize: cumulative average (momentum < 0) needs num_batches_tracked");
+  bn_finalize_kernel<<<1, N <= 128 ? 128 : 256, 0, (cudaStream_t)stream>>>(
       sum, sumsq, (double)R, N, gamma, beta, eps, (float)momentum, (float)(1.0 - momentum), use_batch_stats ? 1 : 0,
       update_running ? 1 : 0, running_mean, running_var, num_batches_tracked, mean, invstd, scale, shift);
   S2C_CHECK_LAUNCH("bn_finalize");

@@ -559,13 +559,31 @@ int check_params(const s2c_caption_params *P, const char *what) {
   return S2C_OK;
 }
 
-// 16-CTA clusters when the device can co-schedule one (non-portable size), else 8
+// 16-CTA clusters when the device can co-schedule one for THIS shape (non-portable size), else 8.  The answer of the
+// occupancy probe depends on the shared-memory plan, i.e. on (H, K, F): it is cached per shape, not per process.
 template <bool BWD>
 int dispatch(const s2c_caption_params &P, cudaStream_t st) {
-  static int use16 = -1;  // probed once per process (same answer for fwd and bwd is not assumed: per template)
-  if (use16 < 0) use16 = (P.H % (4 * 16) == 0 && launch_caption<16, BWD>(P, st, true) == 0) ? 1 : 0;
-  if (use16 && P.H % 64 == 0) return launch_caption<16, BWD>(P, st, false);
-  return launch_caption<8, BWD>(P, st, false);
+  struct Probe { int H, K, F, use16; };
+  static thread_local Probe cache[8];
+  static thread_local int ncache = 0;
+  int use16 = -1;
+  for (int i = 0; i < ncache; ++i)
+    if (cache[i].H == P.H && cache[i].K == P.K && cache[i].F == P.F) use16 = cache[i].use16;
+  if (use16 < 0) {
+    use16 = (P.H % (4 * 16) == 0 && launch_caption<16, BWD>(P, st, true) == 0) ? 1 : 0;
+    cache[ncache % 8] = Probe{P.H, P.K, P.F, use16};
+    ++ncache;
+    if (ncache > 8) ncache = 8;
+  }
+  int rc = -1;
+  if (use16) rc = launch_caption<16, BWD>(P, st, false);
+  if (rc == -1) rc = launch_caption<8, BWD>(P, st, false);
+  if (rc == -1) {
+    s2c::set_error("%s: no shared-memory plan fits 227 KB for H=%d, K=%d, F=%d (8- and 16-CTA clusters tried)",
+                   BWD ? "caption_decode_bwd" : "caption_decode_fwd", P.H, P.K, P.F);
+    return S2C_ERR_UNSUPPORTED;
+  }
+  return rc;
 }
 
 }  // namespace
@@ -574,15 +592,6 @@ int dispatch(const s2c_caption_params &P, cudaStream_t st) {
 namespace s2c {
 int caption_grid_launch(const s2c_caption_params &P, bool bwd, unsigned int *bar, cudaStream_t st);  // caption_grid.cu
 }
-static bool grid_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("S2C_CAPTION_GRID");
-    v = (e == nullptr || atoi(e) != 0) ? 1 : 0;
-  }
-  return v == 1;
-}
-
 extern "C" int s2c_caption_decode_fwd(const s2c_caption_params *P, void *stream) {
   if (int rc = check_params(P, "caption_decode_fwd")) return rc;
   S2C_REQUIRE(P->pre_word && P->pre_tgt && P->mapped && P->obj && P->valid && P->w_tdh && P->w_ih1 && P->w_hh1 &&
@@ -592,7 +601,7 @@ extern "C" int s2c_caption_decode_fwd(const s2c_caption_params *P, void *stream)
   S2C_REQUIRE(P->u && P->h1 && P->r1 && P->z1 && P->n1 && P->hn1 && P->q && P->probs && P->att && P->lang && P->r2 &&
                   P->z2 && P->n2 && P->hn2 && P->h2 && P->scores,
               "caption_decode_fwd: null output");
-  if (P->grid_bar != nullptr && grid_enabled()) {
+  if (P->grid_bar != nullptr) {
     const int rc = s2c::caption_grid_launch(*P, false, P->grid_bar, (cudaStream_t)stream);
     if (rc != -1) return rc;
   }
@@ -609,7 +618,7 @@ extern "C" int s2c_caption_decode_bwd(const s2c_caption_params *P, void *stream)
   S2C_REQUIRE(P->d_h2 && P->dgi2 && P->dgh2 && P->dlang && P->datt && P->dq && P->dgi1 && P->dgh1 && P->du &&
                   P->d_mapped && P->d_obj && P->d_watt,
               "caption_decode_bwd: null gradient buffer");
-  if (P->grid_bar != nullptr && grid_enabled()) {
+  if (P->grid_bar != nullptr) {
     const int rc = s2c::caption_grid_launch(*P, true, P->grid_bar, (cudaStream_t)stream);
     if (rc != -1) return rc;
   }

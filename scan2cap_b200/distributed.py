@@ -25,10 +25,14 @@ class FlatGradients(object):
         self.flat.zero_()
 
     def all_reduce_mean(self, group=None):
-        """sum over ranks in one collective, then scale by 1/world."""
+        """Mean over ranks in ONE collective: ncclAllReduce(avg) (the 1/world scale is applied inside NCCL's reduction,
+        no extra kernel); backends without AVG (gloo, used by the CPU tests) sum and scale."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-            self.flat.mul_(1.0 / dist.get_world_size(group))
+            if self.flat.is_cuda and dist.get_backend(group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+                self.flat.mul_(1.0 / dist.get_world_size(group))
 
 
 def shard_batch(data_dict, rank, world_size):

@@ -1,5 +1,5 @@
-"""Training-step engine: the whole CapNet step (zero grads -> forward -> loss -> backward -> [all-reduce] -> Adam)
-as ONE CUDA graph replay.
+"""Training-step engine: the whole CapNet step (zero grads -> forward -> loss -> backward -> gradient all-reduce
+-> Adam) as ONE CUDA graph replay (lib/solver.py:293-300,376-408 is the reference's step).
 
 The reference's step is ~3 500 kernel launches issued one by one from Python (with CUDA_LAUNCH_BLOCKING=1 in
 its own scripts, scripts/train.py:354), so on a B200 it is bound by launch latency, not by the GPU.  The product
@@ -8,7 +8,16 @@ the GPU then runs back-to-back kernels with no host in the loop.  Graphs are cac
 (shapes / dtypes / number of teacher-forced words); inputs are copied into static device buffers, from pinned
 host memory when the caller passes host tensors.
 
-With more than one rank the step is two graphs with the NCCL all-reduce of the flat gradient buffer between them.
+* Caption length.  The number of teacher-forced words is data dependent (lang_len.max()); it is rounded UP to a
+  multiple of `word_bucket` (pad targets carry zero loss and zero gradient, and the loss takes its denominators from
+  lang_len on the device -- lib/loss_helper.py::compute_cap_loss), so a training run needs at most
+  ceil(31 / word_bucket) graphs.  When the caller gives no host-side length the full 31 steps run: no device->host
+  read, and every rank takes the same decision without talking to the others.
+* Capture is free of side effects: the eager warm-up iterations that capture needs (allocator, lazy module loading)
+  run on the live model, then parameters, BatchNorm buffers and optimiser state are restored IN PLACE, so the first
+  batch of a new signature is trained on exactly once.  Warm-up and capture issue no collective.
+* With more than one rank the NCCL all-reduce (average) of the flat gradient buffer is captured INSIDE the graph
+  between backward and Adam: no host launch and no scaling kernel sit between them.
 """
 import torch
 import torch.distributed as dist
@@ -19,7 +28,8 @@ from .lib.loss_helper import get_scene_cap_loss
 
 class TrainStep(object):
     def __init__(self, model, dataset_config, lr=1e-3, weight_decay=1e-5, detection=True, caption=True,
-                 orientation=False, distance=False, use_cuda_graph=True, loss_fn=None):
+                 orientation=False, distance=False, use_cuda_graph=True, loss_fn=None, word_bucket=4,
+                 collective_in_graph=True):
         self.model = model
         self.DC = dataset_config
         self.flags = dict(detection=detection, caption=caption, orientation=orientation, distance=distance)
@@ -29,6 +39,8 @@ class TrainStep(object):
         self.opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay, capturable=self.use_graph)
         self.loss_fn = loss_fn or get_scene_cap_loss
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.word_bucket = max(1, int(word_bucket))
+        self.collective_in_graph = collective_in_graph
         self._graphs = {}
         self._stage = {}           # signature -> staging copies of the static input buffers (prefetch target)
         self._prefetched = None    # (data_dict object, signature) whose inputs are in flight / in the staging buffers
@@ -44,11 +56,49 @@ class TrainStep(object):
         out["loss"].backward()
         return out
 
-    def _step_eager(self, data):
+    def _step_eager(self, data, collective=True):
         out = self._fwd_bwd(data)
-        self.flat.all_reduce_mean()
+        if collective:
+            self.flat.all_reduce_mean()
         self.opt.step()
         return out
+
+    # ---- caption length -> number of decoder steps the graph runs ---------------------------------------
+    def _words(self, data_dict):
+        """num_words (teacher-forced steps + 1) this step runs with; no device->host read."""
+        width = int(data_dict["lang_ids"].shape[1]) if "lang_ids" in data_dict else int(data_dict["lang_feat"].shape[1])
+        n = data_dict.get("num_words", None)
+        if n is None and isinstance(data_dict.get("lang_len"), torch.Tensor) and not data_dict["lang_len"].is_cuda:
+            n = int(data_dict["lang_len"].max())
+        if n is None:
+            return width
+        b = self.word_bucket
+        return max(2, min(width, (int(n) + b - 1) // b * b))
+
+    # ---- state snapshot: makes warm-up side-effect free ---------------------------------------------------
+    def _snapshot(self):
+        tensors = [p for p in self.model.parameters()] + [b for b in self.model.buffers()]
+        saved = [t.detach().clone() for t in tensors]
+        opt_saved = {}
+        for p, st in self.opt.state.items():
+            opt_saved[p] = {k: (v.detach().clone() if isinstance(v, torch.Tensor) else v) for k, v in st.items()}
+        return tensors, saved, opt_saved
+
+    def _restore(self, snap):
+        tensors, saved, opt_saved = snap
+        with torch.no_grad():
+            for t, s in zip(tensors, saved):
+                t.copy_(s)
+            for p, st in self.opt.state.items():
+                old = opt_saved.get(p)
+                for k, v in st.items():
+                    if isinstance(v, torch.Tensor):
+                        if old is not None and k in old:
+                            v.copy_(old[k])   # in place: the captured graph keeps pointing at these tensors
+                        else:
+                            v.zero_()         # state created by the warm-up (step, exp_avg, exp_avg_sq): as new
+                    elif old is not None and k in old:
+                        st[k] = old[k]
 
     # ---- graph capture -------------------------------------------------------------------------------
     @staticmethod
@@ -60,21 +110,26 @@ class TrainStep(object):
         static = {k: (torch.empty(v.shape, dtype=v.dtype, device=self.device) if isinstance(v, torch.Tensor) else v)
                   for k, v in data.items()}
         self._load(static, data)
-        # warm-up on a side stream (allocator / cuBLAS workspaces / lazy kernel loading), as capture requires
+        # warm-up on a side stream (allocator / cuBLAS workspaces / lazy kernel loading), as capture requires;
+        # no collective (ranks capture independently), and every side effect on the training state is undone
+        snap = self._snapshot()
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for _ in range(3):
-                self._step_eager(dict(static))
+                self._step_eager(dict(static), collective=False)
         torch.cuda.current_stream(self.device).wait_stream(side)
+        self._restore(snap)
         torch.cuda.synchronize(self.device)
         from . import _lib
         n0 = _lib.LAUNCH_COUNT
         g1 = torch.cuda.CUDAGraph()
         g2 = None
-        if self.world == 1:
+        if self.world == 1 or self.collective_in_graph:
             with torch.cuda.graph(g1):
                 out = self._fwd_bwd(dict(static))
+                if self.world > 1:
+                    self.flat.all_reduce_mean()   # ncclAllReduce(avg) captured as a graph node
                 self.opt.step()
         else:
             with torch.cuda.graph(g1):
@@ -89,6 +144,7 @@ class TrainStep(object):
         """The same step issued kernel by kernel (used by bench.py to time single kernels with CUDA events)."""
         data = {k: (v.to(self.device, non_blocking=True) if isinstance(v, torch.Tensor) else v)
                 for k, v in data_dict.items()}
+        data["num_words"] = self._words(data_dict)
         self.last = self._step_eager(data)
         return self.last["loss"]
 
@@ -104,8 +160,7 @@ class TrainStep(object):
         its tensors in between).  A no-op until the graph for this input signature exists, or without CUDA graphs."""
         if not self.use_graph:
             return
-        if "num_words" not in data_dict:
-            data_dict["num_words"] = int(data_dict["lang_len"].max().item())
+        data_dict["num_words"] = self._words(data_dict)
         sig = self._signature(data_dict)
         if sig not in self._graphs:
             return
@@ -125,11 +180,12 @@ class TrainStep(object):
         self._prefetched = (data_dict, sig)
 
     def run(self, data_dict):
-        """One training step on `data_dict` (host or device tensors; include the Python int "num_words" =
-        lang_len.max() to avoid a device->host read).  Returns the (device) scalar loss."""
-        if "num_words" not in data_dict:
+        """One training step on `data_dict` (host or device tensors; a Python int "num_words" = lang_len.max(), or a
+        host-side lang_len, lets the step run only as many decoder steps as the batch needs).  Returns the (device)
+        scalar loss."""
+        if self._prefetched is None or self._prefetched[0] is not data_dict:
             data_dict = dict(data_dict)
-            data_dict["num_words"] = int(data_dict["lang_len"].max().item())
+            data_dict["num_words"] = self._words(data_dict)
         if not self.use_graph:
             data = {k: (v.to(self.device, non_blocking=True) if isinstance(v, torch.Tensor) else v)
                     for k, v in data_dict.items()}

@@ -6,7 +6,6 @@ Arithmetic = the per-word step of the reference (models/caption_module.py:250-29
 forward_sample_batch (:428-500); see TopDownSceneCaptionModule._forward_sample_batch for what is hoisted out of it.
 """
 import ctypes
-import os
 
 import torch
 from torch.autograd import Function
@@ -16,17 +15,26 @@ from .pointnet2._ext import _guard, _stream
 
 
 DEBUG_TS = None  # set to a list to collect (T, 8) globaltimer stamps of every forward call
-# persistent cooperative-grid variant (csrc/caption_grid.cu) for B <= 8; off: always the cluster kernels (csrc/caption.cu)
-USE_GRID = os.environ.get("S2C_CAPTION_GRID", "1") != "0"
-# the backward recurrence measured faster on the cluster kernel (1.33 vs 1.64 ms at B=8, T=26): its per-word chain has
-# more dependent stages, and 16 SMs streaming from L2 beat 128 SMs paying a grid barrier per stage
-USE_GRID_BWD = os.environ.get("S2C_CAPTION_GRID_BWD", "0") != "0"
+# Kernel choice (fixed policy, both are libs2c kernels): the forward recurrence runs on the persistent cooperative grid
+# (csrc/caption_grid.cu, taken by the library when B <= 8 and a barrier counter is passed), the backward recurrence on
+# the cluster kernel (csrc/caption.cu): it measured faster there (1.33 vs 1.64 ms at B=8, T=26) -- its per-word chain
+# has more dependent stages, and 16 SMs streaming from L2 beat 128 SMs paying a grid barrier per stage.  The tests
+# flip these two constants to cover the other two kernels.
+USE_GRID = True
+USE_GRID_BWD = False
 
 
 def supported(pre_word, mapped, obj):
     E, H, F = pre_word.shape[2], mapped.shape[2], obj.shape[2]
     return (pre_word.is_cuda and pre_word.dtype == torch.float32 and E % 4 == 0 and F % 4 == 0 and H % 64 == 0
-            and E >= 4 and F >= 4)
+            and E >= 4 and F >= 4 and mapped.shape[1] >= 1)
+
+
+def require_supported(pre_word, mapped, obj):
+    if not supported(pre_word, mapped, obj):
+        raise RuntimeError("caption decoder kernels: unsupported input (emb %d, hidden %d, feat %d): need CUDA fp32, emb / "
+                           "feat multiples of 4, hidden a multiple of 64 (a shape whose shared-memory plan does not fit "
+                           "is reported by the library itself)" % (pre_word.shape[2], mapped.shape[2], obj.shape[2]))
 
 
 def _c(t):

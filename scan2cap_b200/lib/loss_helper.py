@@ -93,8 +93,8 @@ def compute_box_and_sem_cls_loss(data_dict, config):
     size_residual_label = torch.gather(data_dict["size_residual_label"], 1, object_assignment.unsqueeze(-1).expand(-1, -1, 3))
     size_label_one_hot_tiled = F.one_hot(size_class_label, num_size_cluster).to(pred_center.dtype).unsqueeze(-1)
     predicted_size_residual_normalized = torch.sum(data_dict["size_residuals_normalized"] * size_label_one_hot_tiled, 2)
-    mean_size_arr_expanded = _const("mean_size%d" % id(mean_size_arr),
-                                    lambda: torch.from_numpy(mean_size_arr.astype(np.float32)),
+    mean_size_arr_expanded = _const(("mean_size", np.asarray(mean_size_arr, np.float32).tobytes()),
+                                    lambda: torch.from_numpy(np.asarray(mean_size_arr, np.float32)),
                                     pred_center.device).unsqueeze(0).unsqueeze(0)
     mean_size_label = torch.sum(size_label_one_hot_tiled * mean_size_arr_expanded, 2)
     size_residual_label_normalized = size_residual_label / mean_size_label
@@ -117,7 +117,12 @@ def compute_cap_loss(data_dict, config, weights):
                                reduction="none")
     good = data_dict["good_bbox_masks"]
     good_rep = good.unsqueeze(1).expand(B, T).reshape(-1).to(cap_loss.dtype)
-    cap_loss = torch.sum(cap_loss * good_rep) / (torch.sum(good_rep) + 1e-6)
+    # The reference's denominator sum(good_bbox_masks repeated num_words-1 times) (:213-215) counts the teacher-forced
+    # steps of ITS run, num_words = lang_len.max().  The engine may run more steps than that (T padded to a bucket so
+    # that one captured graph serves many caption lengths; the extra positions have pad targets = zero loss and zero
+    # gradient), so the count is taken from lang_len on the device -- identical (exact integers) when T is not padded.
+    steps = (data_dict["lang_len"].max() - 1).clamp(min=1, max=T).to(cap_loss.dtype)
+    cap_loss = torch.sum(cap_loss * good_rep) / (torch.sum(good.to(cap_loss.dtype)) * steps + 1e-6)
     # accuracy over the non-pad tokens of the good boxes (0 if there is no good box) -- masked, no indexing
     with torch.no_grad():
         tok = (target_caps != 0) & good.unsqueeze(1)

@@ -12,9 +12,9 @@ import os
 
 from ..._lib import LIB, call
 
-# ball queries over at least this many points go through the uniform-grid pre-filter (S2C_BALL_GRID_MIN=0: always,
-# a huge value: never); below it the brute-force scan is as fast and needs no workspace
-GRID_MIN_POINTS = int(os.environ.get("S2C_BALL_GRID_MIN", "4096"))
+# ball queries over at least this many points go through the uniform-grid pre-filter; below it the brute-force scan
+# is as fast and needs no workspace (both are libs2c kernels with bit-identical results)
+GRID_MIN_POINTS = 4096
 
 
 def _chk(t, name, dtype):

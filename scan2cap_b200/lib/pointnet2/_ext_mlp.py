@@ -5,9 +5,10 @@ from ..._lib import call
 from ._ext import _guard, _stream
 
 
-import os
-
-KERNEL_VERSION = int(os.environ.get("S2C_MLP_KERNEL", "2"))  # 2 = pipelined (default), 1 = single-role kernel
+# Two libs2c kernels implement a layer: the warp-specialised TMA-fed one (mlp2.cu; output widths 64/128/256, 16-byte
+# aligned rows -- every layer of the CapNet stacks) and the single-role one (mlp.cu) that takes the remaining shapes
+# (unaligned rows, widths that are other multiples of 16).  `version` is a test hook, not a product switch.
+KERNEL_VERSION = 2
 
 
 def mlp_layer_fwd(A, W, pro_scale=None, pro_shift=None, want_stats=True, K=None, version=None):
@@ -161,7 +162,7 @@ def bn_finalize(s1, s2, R, bn, training):
     f64 = torch.empty((2, N), dtype=torch.float64, device=dev)
     f32 = torch.empty((2, N), dtype=torch.float32, device=dev)
     ptr = lambda t: t.data_ptr() if t is not None else None
-    mom = bn.momentum if bn.momentum is not None else 0.0
+    mom = bn.momentum if bn.momentum is not None else -1.0  # < 0: cumulative average, 1 / num_batches_tracked
     with _guard(bn.weight):
         call("s2c_bn_finalize", ptr(s1) if use_batch else None, ptr(s2) if use_batch else None, int(R), N,
              bn.weight.data_ptr(), bn.bias.data_ptr(), float(bn.eps), float(mom), int(use_batch), int(update),

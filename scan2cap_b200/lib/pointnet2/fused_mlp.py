@@ -17,6 +17,12 @@ from torch.autograd import Function
 
 from . import _ext_mlp
 
+# Test hook (tests/parity_utils.py): when set to a list, every forward call appends the tensors that define its
+# discontinuous decisions -- pre-BatchNorm outputs + folded BatchNorm affine of every layer (ReLU masks) and the
+# pooling arg-max -- so a parity test can tell "different arithmetic" from "a ReLU / arg-max decision flipped by
+# fp32 rounding".  Never set by the product.
+CAPTURE = None
+
 
 def _bn_coefficients(s1, s2, R, bn, training):
     """mean / invstd (float64) of this layer's BatchNorm and the folded fp32 (scale, shift); updates running stats
@@ -84,6 +90,9 @@ class _FusedMLPPool(Function):
             coefs.append((mean, invstd, scale, shift))
             A, k = Y, W.shape[0]
         pooled, argmax = _ext_mlp.pool_fwd(Ys[-1], G, ns, scale, shift, want_argmax=True)
+        if CAPTURE is not None:
+            CAPTURE.append(dict(G=G, ns=ns, Ys=list(Ys), affine=[(c[2], c[3]) for c in coefs], argmax=argmax,
+                                pooled=pooled))
         ctx.save_for_backward(rows, argmax, *Ys, *[t for c in coefs for t in c], *params)
         ctx.meta = (K, G, ns, L, bool(training), [bool(training or not b.track_running_stats) for b in bns],
                     bool(xyz_gap), bool(need_xyz_grad))

@@ -17,16 +17,10 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-import os
-
 from . import _ext
 from . import fused_mlp
 from . import pointnet2_utils
 from . import pytorch_utils as pt_utils
-
-# S2C_FUSED_MLP=0 selects library GEMM + BatchNorm + ReLU kernels instead of the tcgen05 path (A/B comparison)
-USE_FUSED_MLP = os.environ.get("S2C_FUSED_MLP", "1") != "0"
-
 
 def point_major(features):
     """(B,C,N) tensor -> (B,N,C) view with unit channel stride (copying only if the storage is channel-major)."""
@@ -38,7 +32,10 @@ def bn_rows(x, bn, training):
     """BatchNorm{1d,2d} of a row-major (R, C) matrix: statistics over the R rows (every (scene, point[, sample]))."""
     if training and bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
-    mom = bn.momentum if bn.momentum is not None else 0.0
+    if bn.momentum is not None:
+        mom = bn.momentum
+    else:  # nn.BatchNorm: cumulative moving average, factor 1 / num_batches_tracked (already incremented above)
+        mom = 1.0 / float(bn.num_batches_tracked) if (training and bn.num_batches_tracked is not None) else 0.0
     return F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias,
                         training or not bn.track_running_stats, mom, bn.eps)
 
@@ -48,17 +45,11 @@ def conv1x1_rows(x, conv):
     return F.linear(x, conv.weight.view(conv.weight.shape[0], -1), conv.bias)
 
 
-def shared_mlp_rows(rows, layers, training):
-    """conv1x1(no bias) -> BatchNorm -> ReLU stack on a row-major (R, Cin) matrix (R = every (scene, group,
-    sample) triple), the arithmetic of SharedMLP on a (B,C,npoint,nsample) tensor (pytorch_utils.py:11-36,
-    88-120).  BatchNorm statistics over R rows == BatchNorm2d statistics over (B, npoint, nsample)."""
-    x = rows
-    for conv, bn in layers:
-        x = conv1x1_rows(x, conv)
-        if bn is not None:
-            x = bn_rows(x, bn, training)
-        x = F.relu_(x)
-    return x
+def _require_fusable(layers, what):
+    """The grouped MLP runs on the tcgen05 kernels only; there is no library-kernel alternative in the product."""
+    if not fused_mlp.fusable(layers):
+        raise RuntimeError("%s: the shared MLP must be [1x1 conv without bias -> affine BatchNorm -> ReLU] layers with "
+                           "output widths that are multiples of 16 and <= 256 (tensor-core kernels of libs2c)" % what)
 
 
 class PointnetSAModuleVotes(nn.Module):
@@ -94,10 +85,12 @@ class PointnetSAModuleVotes(nn.Module):
         """xyz (B,N,3), features (B,C,N), inds (B,npoint) -> new_xyz (B,npoint,3), new_features (B,C',npoint),
         inds (B,npoint) int32.  sampled_xyz (extension): xyz[inds] when the caller already has it (no gradient)."""
         layers = self.mlp_module.layer_params()
-        fast = (self.npoint is not None and self.use_xyz and self.pooling == "max" and layers is not None
-                and not self.ret_unique_cnt)
-        if not fast:
-            return self._forward_generic(xyz, features, inds)
+        if self.npoint is None or not self.use_xyz or self.ret_unique_cnt or self.pooling not in ("max", "avg", "rbf"):
+            # GroupAll raises in the reference itself (pointnet2_utils.py:387-390 vs :422, SURVEY Appendix E);
+            # use_xyz=False / ret_unique_cnt are never used by the CapNet / MaskVoteNet / encoder stacks
+            raise NotImplementedError("PointnetSAModuleVotes: npoint=None, use_xyz=False and ret_unique_cnt are not "
+                                      "provided by the fused query+group kernel")
+        _require_fusable(layers, "PointnetSAModuleVotes")
         xyz = xyz.contiguous()
         if inds is None:
             inds, new_xyz = _ext.furthest_point_sampling_with_xyz(xyz.detach(), self.npoint)
@@ -110,40 +103,28 @@ class PointnetSAModuleVotes(nn.Module):
             assert inds.shape[1] == self.npoint
             new_xyz = torch.gather(xyz, 1, inds.long().unsqueeze(-1).expand(-1, -1, 3))
         feats_pm = point_major(features) if features is not None else None
-        use_fused = USE_FUSED_MLP and fused_mlp.fusable(layers)
         grouped, _ = pointnet2_utils.query_and_group(xyz, new_xyz, feats_pm, self.radius, self.nsample,
-                                                     self.normalize_xyz, True, True, use_fused)
+                                                     self.normalize_xyz, True, True, True)
         B, C, M, ns = grouped.shape
-        if use_fused:
-            # rows of the 16-byte aligned channels-last buffer the kernel wrote: (R, Cp) = [xyz, 0 | features | pad]
-            Cin = 3 + (feats_pm.shape[2] if feats_pm is not None else 0)
-            rows = grouped.permute(0, 2, 3, 1).reshape(B * M * ns, C)
-            pooled = fused_mlp.fused_mlp_maxpool(rows, Cin, B * M, ns, layers, self.training, xyz_gap=True,
-                                                 need_xyz_grad=xyz.requires_grad or new_xyz.requires_grad
-                                                 ).view(B, M, -1)
-        else:
-            rows = grouped.permute(0, 2, 3, 1).reshape(B * M * ns, C)  # a view: the kernel wrote channels-last
-            out = shared_mlp_rows(rows, layers, self.training)
-            pooled = out.view(B, M, ns, -1).amax(dim=2)  # (B, M, C') point-major
-        return new_xyz, pooled.transpose(1, 2), inds
-
-    def _forward_generic(self, xyz, features, inds):
-        """Literal path for the options CapNet never uses (avg / rbf pooling, GroupAll, use_xyz=False)."""
-        xyz_flipped = xyz.transpose(1, 2).contiguous()
-        if inds is None and self.npoint is not None:
-            inds = pointnet2_utils.furthest_point_sample(xyz, self.npoint)
-        new_xyz = (pointnet2_utils.gather_operation(xyz_flipped, inds).transpose(1, 2).contiguous()
-                   if self.npoint is not None else None)
-        grouped_features, grouped_xyz = self.grouper(xyz, new_xyz, features.contiguous() if features is not None else None)
-        new_features = self.mlp_module(grouped_features)
+        # rows of the 16-byte aligned channels-last buffer the kernel wrote: (R, Cp) = [xyz, 0 | features | pad]
+        Cin = 3 + (feats_pm.shape[2] if feats_pm is not None else 0)
+        rows = grouped.permute(0, 2, 3, 1).reshape(B * M * ns, C)
+        need_xyz_grad = xyz.requires_grad or new_xyz.requires_grad
         if self.pooling == "max":
-            new_features = F.max_pool2d(new_features, kernel_size=[1, new_features.size(3)])
-        elif self.pooling == "avg":
-            new_features = F.avg_pool2d(new_features, kernel_size=[1, new_features.size(3)])
-        elif self.pooling == "rbf":
-            rbf = torch.exp(-1 * grouped_xyz.pow(2).sum(1, keepdim=False) / (self.sigma ** 2) / 2)
-            new_features = torch.sum(new_features * rbf.unsqueeze(1), -1, keepdim=True) / float(self.nsample)
-        return new_xyz, new_features.squeeze(-1), inds
+            pooled = fused_mlp.fused_mlp_maxpool(rows, Cin, B * M, ns, layers, self.training, xyz_gap=True,
+                                                 need_xyz_grad=need_xyz_grad).view(B, M, -1)
+        else:
+            # avg / rbf pooling (pointnet2_modules.py:258-266; never used by CapNet): same kernels without the pooling
+            # stage (groups of one row), then the weighted mean over the nsample rows of each group
+            act = fused_mlp.fused_mlp_maxpool(rows, Cin, B * M * ns, 1, layers, self.training, xyz_gap=True,
+                                              need_xyz_grad=need_xyz_grad).view(B, M, ns, -1)
+            if self.pooling == "avg":
+                pooled = act.mean(dim=2)
+            else:
+                gxyz = rows[:, :3].view(B, M, ns, 3)  # grouped_xyz as QueryAndGroup returns it (centred [, / radius])
+                rbf = torch.exp(-1 * gxyz.pow(2).sum(-1) / (self.sigma ** 2) / 2)
+                pooled = torch.sum(act * rbf.unsqueeze(-1), 2) / float(self.nsample)
+        return new_xyz, pooled.transpose(1, 2), inds
 
 
 class PointnetFPModule(nn.Module):
@@ -171,8 +152,6 @@ class PointnetFPModule(nn.Module):
             parts.append(unknow_feats.transpose(1, 2))
         rows = torch.cat(parts, dim=2)  # (B, n, C2+C1) point-major
         B, n, C = rows.shape
-        if USE_FUSED_MLP and fused_mlp.fusable(layers):
-            out = fused_mlp.fused_mlp_maxpool(rows.reshape(B * n, C), C, B * n, 1, layers, self.training)
-        else:
-            out = shared_mlp_rows(rows.reshape(B * n, C), layers, self.training)
+        _require_fusable(layers, "PointnetFPModule")
+        out = fused_mlp.fused_mlp_maxpool(rows.reshape(B * n, C), C, B * n, 1, layers, self.training)
         return out.view(B, n, -1).transpose(1, 2)

@@ -12,7 +12,7 @@ from ..lib.pointnet2.pointnet2_modules import PointnetSAModuleVotes, PointnetFPM
 
 # The sampling of SA2..SA4 depends on coordinates only (each level samples the previous level's samples), so it can
 # run on a second stream next to SA1's grouping + MLP instead of between the levels (S2C_SAMPLE_AHEAD=0: in sequence)
-SAMPLE_AHEAD = os.environ.get("S2C_SAMPLE_AHEAD", "1") != "0"
+SAMPLE_AHEAD = True
 _SIDE_STREAMS = {}
 
 

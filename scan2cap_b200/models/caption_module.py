@@ -19,17 +19,10 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-import os
-
 from ..lib import caption_decoder
 from ..lib.config import CONF
 from ..lib.pointnet2 import _ext_graph
 from ..utils.box_util import box3d_iou_batch_tensor
-
-
-# S2C_FUSED_CAPTION=0: issue the teacher-forced recurrence step by step with framework kernels instead of the
-# cluster kernels of csrc/caption.cu (same arithmetic; used by the tests as the comparison path)
-USE_FUSED_DECODER = os.environ.get("S2C_FUSED_CAPTION", "1") != "0"
 
 
 def select_target(data_dict):
@@ -242,33 +235,17 @@ class TopDownSceneCaptionModule(nn.Module):
         pre_word = F.linear(word_embs[:, :T], w_td[:, :E])                 # (B,T,emb)
         pre_tgt = F.linear(target_feats, w_td[:, E + H:], b_td)            # (B,emb)
         w_td_h = w_td[:, E:E + H]
-        if USE_FUSED_DECODER and caption_decoder.supported(pre_word, mapped, obj_feats):
-            # the whole recurrence in one launch (and one for its backward): csrc/caption.cu
-            valid_f = (valid_masks != 0).to(torch.float32)
-            hid, attn = caption_decoder.topdown_decode(pre_word, pre_tgt, mapped, obj_feats, valid_f, w_td_h,
-                                                       self.recurrent_cell_1, self.map_hidd, self.attend,
-                                                       self.map_lang[0], self.recurrent_cell_2)
-            good_bbox_masks = target_ious > min_iou
-            data_dict["lang_cap"] = self.classifier(hid)            # (B,T,V)
-            data_dict["pred_ious"] = _masked_mean(target_ious, good_bbox_masks)
-            data_dict["topdown_attn"] = attn                        # (B,K,T)
-            data_dict["valid_masks"] = valid_masks
-            data_dict["good_bbox_masks"] = good_bbox_masks
-            return data_dict
-        step_masks = valid_masks.unsqueeze(-1)
-        hidden_1 = torch.zeros(B, self.hidden_size, device=dev)
-        hidden_2 = torch.zeros(B, self.hidden_size, device=dev)
-        hiddens, masks = [], []
-        for step_id in range(T):
-            u = torch.relu(pre_word[:, step_id] + pre_tgt + F.linear(hidden_2, w_td_h))
-            hidden_1, hidden_2, step_mask = self._step_core(u, obj_feats, hidden_1, hidden_2, step_masks, mapped)
-            hiddens.append(hidden_2)
-            masks.append(step_mask)
-        outputs = [self.classifier(torch.stack(hiddens, dim=1))]          # (B,T,V)
+        # the whole recurrence in one launch (and one for its backward): csrc/caption.cu / caption_grid.cu.  There is
+        # no framework-kernel alternative in the product: shapes the kernels do not take raise.
+        caption_decoder.require_supported(pre_word, mapped, obj_feats)
+        valid_f = (valid_masks != 0).to(torch.float32)
+        hid, attn = caption_decoder.topdown_decode(pre_word, pre_tgt, mapped, obj_feats, valid_f, w_td_h,
+                                                   self.recurrent_cell_1, self.map_hidd, self.attend,
+                                                   self.map_lang[0], self.recurrent_cell_2)
         good_bbox_masks = target_ious > min_iou
-        data_dict["lang_cap"] = torch.cat(outputs, dim=1)       # (B,T,V)
+        data_dict["lang_cap"] = self.classifier(hid)            # (B,T,V)
         data_dict["pred_ious"] = _masked_mean(target_ious, good_bbox_masks)
-        data_dict["topdown_attn"] = torch.cat(masks, dim=-1)    # (B,K,T)
+        data_dict["topdown_attn"] = attn                        # (B,K,T)
         data_dict["valid_masks"] = valid_masks
         data_dict["good_bbox_masks"] = good_bbox_masks
         return data_dict

@@ -144,8 +144,8 @@ def box_corners(center, size):
 def make_data_dict(batch, n_points, use_normal=False, use_multiview=False, use_height=True, num_vocabs=3500,
                    seed=42, mean_size_arr=None, lang_len=None):
     """Seeded CPU ``data_dict`` (numpy arrays) for a full CapNet forward + loss + backward."""
-    from .data.scannet.model_util_scannet import MEAN_SIZE_ARR
-    mean_size_arr = MEAN_SIZE_ARR if mean_size_arr is None else mean_size_arr
+    if mean_size_arr is None:  # (the reference arm of bench.py loads this file by path and passes its own table)
+        from scan2cap_b200.data.scannet.model_util_scannet import MEAN_SIZE_ARR as mean_size_arr
     _, _, table = make_vocabulary(num_vocabs, seed=seed)
     T = MAX_DES_LEN + 2
     d = {k: [] for k in ("point_clouds", "center_label", "size_class_label", "size_residual_label", "sem_cls_label",
@@ -204,3 +204,40 @@ def make_data_dict(batch, n_points, use_normal=False, use_multiview=False, use_h
     out["heading_residual_label"] = np.zeros((B, MAX_NUM_OBJ), np.float32)
     out["lang_feat"] = out["lang_feat"].astype(np.float32)
     return out
+
+
+def make_pretrained_data_dict(batch, num_proposals=256, num_valid=64, num_vocabs=3500, seed=42, lang_len=20):
+    """Seeded ``data_dict`` of the capnet_pretrained path (BASELINE config 1; keys of lib/dataset_pretrained.py:659-699):
+    pre-extracted box features for `num_proposals` boxes of which the first `num_valid` are valid objects.  The
+    referred box (ref_box_corner_label) is valid box 3, so good_bbox_masks is not empty."""
+    _, _, table = make_vocabulary(num_vocabs, seed=seed)
+    T = MAX_DES_LEN + 2
+    d = {k: [] for k in ("bbox_feature", "bbox_corner", "bbox_center", "bbox_mask", "bbox_idx", "bbox_corner_label",
+                         "bbox_center_label", "ref_box_corner_label", "scene_object_rotations",
+                         "scene_object_rotation_masks", "lang_ids", "lang_len", "lang_feat")}
+    for b in range(batch):
+        rng = np.random.default_rng(seed + 1000 * b + 11)
+        center = rng.random((num_proposals, 3)) * np.array(ROOM) - np.array([ROOM[0] / 2, ROOM[1] / 2, 0.0])
+        size = rng.uniform(0.3, 2.0, (num_proposals, 3))
+        corners = box_corners(center, size)
+        mask = np.zeros(num_proposals, np.int64)
+        mask[:num_valid] = 1
+        d["bbox_feature"].append(rng.standard_normal((num_proposals, 128)).astype(np.float32))
+        d["bbox_corner"].append(corners)
+        d["bbox_center"].append(center.astype(np.float32))
+        d["bbox_mask"].append(mask)
+        d["bbox_idx"].append(3)
+        d["bbox_corner_label"].append(corners.copy())
+        d["bbox_center_label"].append(center.copy())
+        d["ref_box_corner_label"].append(corners[3].copy())
+        q, _ = np.linalg.qr(rng.standard_normal((num_proposals, 3, 3)))
+        d["scene_object_rotations"].append(q.astype(np.float32))
+        d["scene_object_rotation_masks"].append(np.ones(num_proposals, np.int64))
+        n_tok = int(lang_len)
+        ids = np.zeros(T, np.int64)
+        ids[:n_tok] = rng.integers(4, num_vocabs, n_tok)
+        ids[0], ids[n_tok - 1] = 2, 3
+        d["lang_ids"].append(ids)
+        d["lang_len"].append(n_tok)
+        d["lang_feat"].append((table[ids] * (ids != 0)[:, None]).astype(np.float32))
+    return {k: np.stack(v) if isinstance(v[0], np.ndarray) else np.asarray(v, np.int64) for k, v in d.items()}

@@ -1,30 +1,39 @@
 """GPU parity of the product CapNet (scan2cap_b200, fused / batched / sync-free, libs2c kernels through the
 C ABI) against the oracle restatement of the reference (oracle/ref_model.py + ref_loss.py driving the
-reference's own CUDA kernels when oracle/_ref is present, else the C oracle), same weights, same inputs.
+reference's own CUDA kernels when oracle/_ref is present, else the C oracle), same weights, same inputs -- at the
+shapes the benchmark runs (BASELINE configs[2] "c3": B=8, N=40 000, 7 floats; configs[3] "c4": B=4, N=40 000, 135
+floats with the shipped XYZ_MULTIVIEW_NORMAL VoteNet checkpoint mounted as scripts/train.py:84-104 does) and at two
+small shapes.
 
 Bars (north_star): integer outputs (FPS indices, neighbour lists via the masks/adjacency, kNN edges) bit-exact;
-float features / logits within 1e-3 relative (measured against the tensor's max magnitude); gradients within
-1e-3 of the larger of the parameter's own gradient scale and 1e-3 x the model's largest gradient entry
-(biases in front of a BatchNorm have an analytically zero gradient)."""
+float features / logits / losses within 1e-3 relative (of the tensor's max magnitude); BatchNorm running statistics
+within 1e-3; gradients: relative L2 <= 1e-3 PER PARAMETER with the ReLU / max-pool decisions of the two sides
+compared and the groups whose decisions flipped excluded from both backward passes (tests/parity_utils.py; the
+flip count is printed).
+
+FPS on the VOTE coordinates is discontinuous in its float input: a 1e-6 difference in vote_xyz between two fp32
+evaluation orders can flip a pick and with it the whole proposal set.  When that happens the run is repeated with the
+product's vote-aggregation sampling forced to the oracle's picks (after checking that our FPS kernel reproduces those
+picks bit-exactly from the oracle's votes), and EVERYTHING is still compared end to end -- outputs, loss, every
+gradient.  Which branch each case took is recorded in BRANCHES (printed, and written to gpurun_out/) and
+test_parity_branches fails if more than two cases needed the forced branch."""
 import copy
+import json
+import os
+import warnings
 
 import numpy as np
 import pytest
 import torch
 
+import parity_utils as PU
 from scan2cap_b200 import synthetic
 from scan2cap_b200.data.scannet.model_util_scannet import ScannetDatasetConfig
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 RTOL = 1e-3
-# Gradients.  ReLU / max-pool / arg-max are discontinuous: the ~1e-6 forward differences between two fp32
-# evaluation orders flip a handful of decisions among ~10^6, and k flips among n routed entries change a
-# gradient tensor by about sqrt(k/n) in relative L2 (the same happens between an fp32 and an fp64 run of ONE
-# implementation, tools/diag_mlp.py / tools/diag_fused.py; with no flip every kernel is at 1e-6 of float64).
-# The whole-network check is therefore a coarse one (gross errors: missing terms, wrong routing); the tight
-# gradient checks are the per-kernel ones against float64 in tests/test_mlp_gpu.py and tests/test_native_ops_gpu.py.
-GRAD_TOL = 2e-2
+BRANCHES = {}
 
 INT_KEYS = ["sa1_inds", "sa2_inds", "fp2_inds", "aggregated_vote_inds", "bbox_mask", "bbox_sems", "num_edge_source",
             "num_edge_target", "good_bbox_masks", "object_assignment", "objectness_label"]
@@ -35,14 +44,14 @@ FLOAT_KEYS = ["sa1_features", "sa2_features", "sa3_features", "sa4_features", "f
               "edge_feature", "edge_orientations", "edge_distances", "lang_cap", "topdown_attn", "pred_ious", "loss",
               "vote_loss", "objectness_loss", "box_loss", "sem_cls_loss", "cap_loss", "ori_loss", "dist_loss", "cap_acc",
               "ori_acc", "obj_acc"]
+PRE_INT = ["sa1_inds", "sa2_inds", "fp2_inds"]
+PRE_EXACT = ["sa1_xyz", "sa2_xyz", "sa3_xyz", "sa4_xyz"]
+PRE_FLOAT = ["sa1_features", "sa2_features", "sa3_features", "sa4_features", "fp2_features", "vote_xyz", "vote_features"]
+
+_rel = PU.rel
 
 
-def _rel(a, b):
-    a, b = a.detach().double(), b.detach().double()
-    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
-
-
-def _models(query_mode, C, V, seed=0):
+def _models(query_mode, C, V, seed=0, checkpoint=None):
     from oracle import ref_model as R
     from scan2cap_b200.models.capnet import CapNet
     from conftest import load_reference_ext
@@ -54,22 +63,23 @@ def _models(query_mode, C, V, seed=0):
     torch.manual_seed(seed)
     ours = CapNet(DC.num_class, vocab, emb, DC.num_heading_bin, DC.num_size_cluster, DC.mean_size_arr, **cfg).to(DEV)
     ref = R.CapNet(DC.num_class, vocab, emb, DC.num_heading_bin, DC.num_size_cluster, DC.mean_size_arr, **cfg).to(DEV)
+    if checkpoint is not None:
+        # scripts/train.py:84-104: the pre-trained VoteNet (backbone, voting, proposal) is loaded with strict=False
+        # into a no_caption CapNet and mounted; here: its tensors are loaded straight into the full model
+        sd = torch.load(checkpoint, map_location=DEV)
+        missing, unexpected = ours.load_state_dict(sd, strict=False)
+        assert not unexpected and all(k.startswith(("graph.", "caption.")) for k in missing), (missing, unexpected)
     ref.load_state_dict(ours.state_dict(), strict=True)  # identical key set = the checkpoint contract
     return ours, ref, DC
 
 
-def _data(B, N, V, seed, use_normal=True):
-    d = synthetic.make_data_dict(B, N, use_normal=use_normal, num_vocabs=V, seed=seed)
+def _data(B, N, V, seed, use_normal=True, use_multiview=False):
+    d = synthetic.make_data_dict(B, N, use_normal=use_normal, use_multiview=use_multiview, num_vocabs=V, seed=seed)
     return {k: torch.from_numpy(v).to(DEV) for k, v in d.items()}
 
 
 def _clone(d):
     return {k: v.clone() for k, v in d.items()}
-
-
-PRE_INT = ["sa1_inds", "sa2_inds", "fp2_inds"]
-PRE_EXACT = ["sa1_xyz", "sa2_xyz", "sa3_xyz", "sa4_xyz"]
-PRE_FLOAT = ["sa1_features", "sa2_features", "sa3_features", "sa4_features", "fp2_features", "vote_xyz", "vote_features"]
 
 
 def _check_outputs(o, r, int_keys, exact_keys, float_keys):
@@ -83,87 +93,108 @@ def _check_outputs(o, r, int_keys, exact_keys, float_keys):
         worst[k] = _rel(o[k], r[k])
     bad = {k: v for k, v in worst.items() if not v < RTOL}
     assert not bad, "float outputs beyond %g: %s" % (RTOL, bad)
+    return max(worst.values())
 
 
-def _check_grads(ours, ref, prefixes=None):
-    """Every parameter's gradient deviates by less than GRAD_TOL x the norm of the WHOLE gradient, and the cosine
-    between the two flattened gradients exceeds 0.999.  (A per-parameter relative measure is meaningless for e.g. the
-    bias of SA4's last BatchNorm: it is a sum of +-1e3-sized terms that cancels to 0.5, so the 3e-3 relative noise
-    of its inputs is an O(1) relative change of the sum -- tools/diag_sa4_bias.py.)"""
-    go = {n: p.grad for n, p in ours.named_parameters() if p.grad is not None}
-    gr = {n: p.grad for n, p in ref.named_parameters() if p.grad is not None}
-    if prefixes is None:
-        assert set(go) == set(gr)
-    names = [n for n in gr if prefixes is None or n.startswith(prefixes)]
-    for n in names:
-        assert n in go, "no gradient for %s" % n
-    fo = torch.cat([go[n].double().flatten() for n in names])
-    fr = torch.cat([gr[n].double().flatten() for n in names])
-    total = float(fr.norm())
-    cos = float(torch.dot(fo, fr) / (fo.norm() * fr.norm()))
-    dev = {n: float((go[n].double() - gr[n].double()).norm()) / total for n in names}
-    worst = max(dev.values())
-    print("worst per-parameter gradient deviation / |grad|: %.2e, cosine of the full gradient: %.6f" % (worst, cos))
-    bad = {n: e for n, e in dev.items() if not e < GRAD_TOL}
-    assert not bad, "gradients beyond %g of the gradient norm: %s" % (GRAD_TOL, bad)
-    assert cos > 0.999
+CASES = {
+    # name: (query_mode, B, N, use_multiview, vocabulary, checkpoint, data seed)
+    "small_center": ("center", 2, 8000, False, 150, None, 11),
+    "small_corner": ("corner", 1, 20000, False, 150, None, 11),
+    "c3_B8_N40k_C4": ("center", 8, 40000, False, 3500, None, 42),
+    "c4_B4_N40k_C132_ckpt": ("center", 4, 40000, True, 3500, "PRETRAIN_VOTENET_XYZ_MULTIVIEW_NORMAL", 42),
+}
 
 
-@pytest.mark.parametrize("query_mode,B,N", [("center", 2, 8000), ("corner", 1, 20000)])
-def test_capnet_forward_backward_parity(query_mode, B, N):
+@pytest.mark.parametrize("case", list(CASES))
+def test_capnet_forward_backward_parity(case):
     from oracle import ref_loss as RL
     from scan2cap_b200.lib.loss_helper import get_scene_cap_loss
+    from scan2cap_b200.lib.pointnet2 import _ext
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    V = 150
-    ours, ref, DC = _models(query_mode, 4, V)
-    data = _data(B, N, V, seed=11)
+    query_mode, B, N, use_mv, V, ckpt, seed = CASES[case]
+    ckpt_path = None
+    if ckpt is not None:
+        ckpt_path = PU.checkpoint_path(ckpt)
+        if ckpt_path is None:
+            pytest.skip("shipped checkpoint %s not installed under baseline/_ref/pretrained" % ckpt)
+    C = 4 + (128 if use_mv else 0)
+    ours, ref, DC = _models(query_mode, C, V, checkpoint=ckpt_path)
+    data = _data(B, N, V, seed=seed, use_multiview=use_mv)
+    state = copy.deepcopy(ours.state_dict())
     with torch.no_grad():
-        state = copy.deepcopy(ours.state_dict())
         probe = ours(_clone(data))
-        ours.load_state_dict(state)  # undo the BatchNorm running-stat update of the probe
     data["ref_box_corner_label"] = probe["bbox_corner"][:, 7].clone()
     data["ref_box_corner_label"][-1] += 50.0  # last scene: no good box -> its caption loss is masked out
+    del probe
     ours.train(); ref.train()
     flags = (True, True, True, True)
-    state = copy.deepcopy(ours.state_dict())
-    o = get_scene_cap_loss(ours(_clone(data)), DEV, DC, None, *flags)
-    # The oracle runs with cuDNN disabled (ATen's native conv / batch-norm kernels): cuDNN's fp32 weight-gradient
-    # kernels for 1x1 convolutions over 10^5..10^6 positions deviate 3e-3..2e-2 from a float64 evaluation on
-    # B200 (tools/diag_mlp.py, profiles/r01_gradient_accuracy.txt) whereas the GEMM formulation is at 1e-6, so
-    # cuDNN's gradients cannot serve as the yardstick.  bench.py --impl reference keeps cuDNN on (stock path).
-    with torch.backends.cudnn.flags(enabled=False):
-        r = RL.get_scene_cap_loss(ref(_clone(data)), DEV, DC, None, *flags)
-        r["loss"].backward()
-    # ---- everything up to the votes: FPS / ball-query indices bit-exact, features within tolerance
-    _check_outputs(o, r, PRE_INT, PRE_EXACT, PRE_FLOAT)
-    if torch.equal(o["aggregated_vote_inds"], r["aggregated_vote_inds"]):
-        # same proposals selected: the whole step is comparable end to end
-        _check_outputs(o, r, INT_KEYS, EXACT_FLOAT_KEYS, FLOAT_KEYS)
+    with PU.DecisionTracker(ours, ref) as tracker:
+        # The oracle runs with cuDNN disabled (ATen's native conv / batch-norm kernels): cuDNN's fp32 weight-gradient
+        # kernels for 1x1 convolutions over 10^5..10^6 positions deviate 3e-3..2e-2 from a float64 evaluation on
+        # B200 (profiles/r01_gradient_accuracy.txt) whereas the GEMM formulation is at 1e-6, so cuDNN's gradients
+        # cannot serve as the yardstick.  bench.py --impl reference keeps cuDNN on (stock path).
+        with torch.backends.cudnn.flags(enabled=False):
+            r = RL.get_scene_cap_loss(ref(_clone(data)), DEV, DC, None, *flags)
+
+        def run_ours(forced_inds=None):
+            ours.load_state_dict(state)   # undo BatchNorm running-statistics updates of earlier forward passes
+            ours.zero_grad()
+            tracker.fused_mlp.CAPTURE = []
+            va = ours.proposal.vote_aggregation
+            if forced_inds is not None:
+                orig = va.forward
+                va.forward = lambda xyz, features=None, inds=None, sampled_xyz=None: orig(xyz, features, inds=forced_inds)
+            try:
+                return get_scene_cap_loss(ours(_clone(data)), DEV, DC, None, *flags)
+            finally:
+                if forced_inds is not None:
+                    del va.forward
+
+        o = run_ours()
+        # ---- everything up to the votes: FPS / ball-query indices bit-exact, features within tolerance
+        _check_outputs(o, r, PRE_INT, PRE_EXACT, PRE_FLOAT)
+        branch = "end-to-end"
+        if not torch.equal(o["aggregated_vote_inds"].long(), r["aggregated_vote_inds"].long()):
+            # our FPS kernel on the ORACLE's votes reproduces the oracle's picks: the flip came from input rounding
+            mine = _ext.furthest_point_sampling(r["vote_xyz"].detach().contiguous(), 256)
+            assert torch.equal(mine.long(), r["aggregated_vote_inds"].long()), "vote FPS differs on identical votes"
+            nflip = int((o["aggregated_vote_inds"].long() != r["aggregated_vote_inds"].long()).any(1).sum())
+            branch = "vote-FPS picks forced to the oracle's (%d of %d scenes flipped)" % (nflip, B)
+            o = run_ours(forced_inds=r["aggregated_vote_inds"].int().contiguous())
+            _check_outputs(o, r, PRE_INT, PRE_EXACT, PRE_FLOAT)
+        worst_out = _check_outputs(o, r, INT_KEYS, EXACT_FLOAT_KEYS, FLOAT_KEYS)
+        flipped = tracker.resolve()
         o["loss"].backward()
-        _check_grads(ours, ref)
-        rb = dict(ref.named_buffers())
-        for n1, b1 in ours.named_buffers():
-            if "running" in n1:
-                assert _rel(b1, rb[n1]) < RTOL, n1
-    else:
-        # FPS on the VOTE coordinates is discontinuous in its input: a 1e-6 difference in vote_xyz between two
-        # fp32 evaluation orders can flip a pick and with it the whole proposal set.  Compare the rest of the
-        # network from identical votes instead (the oracle's), stage-isolated.
-        print("vote-FPS pick flipped by fp32 rounding; comparing proposal/graph/caption from the oracle's votes")
-        ours.load_state_dict(state)
-        ours.zero_grad()
-        d = ours.backbone_net(_clone(data))
-        d["seed_inds"], d["seed_xyz"], d["seed_features"] = d["fp2_inds"], d["fp2_xyz"], d["fp2_features"]
-        d["vote_xyz"], d["vote_features"] = r["vote_xyz"].detach(), r["vote_features"].detach()
-        d = ours.proposal(d["vote_xyz"], d["vote_features"], d)
-        d = ours.caption(ours.graph(d), True, False)
-        o2 = get_scene_cap_loss(d, DEV, DC, None, *flags)
-        post_int = [k for k in INT_KEYS if k not in PRE_INT]
-        post_float = [k for k in FLOAT_KEYS if k not in PRE_FLOAT and k not in ("loss", "vote_loss")]
-        _check_outputs(o2, r, post_int, ["adjacent_mat", "edge_index", "valid_masks"], post_float)
-        o2["loss"].backward()
-        _check_grads(ours, ref, prefixes=("proposal.proposal", "graph.", "caption."))
+        with torch.backends.cudnn.flags(enabled=False):
+            r["loss"].backward()
+    worst_grad = PU.check_grads_per_parameter(ours, ref, label="[%s] " % case)
+    rb = dict(ref.named_buffers())
+    for n1, b1 in ours.named_buffers():
+        if "running" in n1:
+            assert _rel(b1, rb[n1]) < RTOL, n1
+    BRANCHES[case] = {"branch": branch, "flipped_groups": tracker.report(), "worst_output_rel": worst_out,
+                      "worst_param_grad_rel_l2": worst_grad}
+    msg = "parity[%s]: %s; decision flips excluded: %s (total %d); worst output %.2e, worst parameter gradient %.2e" % (
+        case, branch, tracker.report(), flipped, worst_out, worst_grad)
+    print(msg)
+    warnings.warn(msg)   # shows up in the pytest summary of a green run (the driver's log)
+
+
+def test_parity_branches():
+    """Record which branch every parity case took; more than two forced-pick cases would mean the end-to-end
+    comparison is the exception rather than the rule."""
+    if not BRANCHES:
+        pytest.skip("no parity case ran in this session")
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_branches.json"), "w") as f:
+            json.dump(BRANCHES, f, indent=1)
+    except OSError:
+        pass
+    forced = [c for c, v in BRANCHES.items() if v["branch"] != "end-to-end"]
+    assert len(forced) <= 2, "vote-FPS picks had to be forced in %s" % forced
 
 
 def test_capnet_eval_decode_parity():

@@ -1,0 +1,109 @@
+"""scan2cap_b200/engine.py::TrainStep -- the public training-step API the benchmark drives (SURVEY 8(f) row 3,
+lib/solver.py:293-300,376-408) -- and multi-GPU shard parity."""
+import copy
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from scan2cap_b200 import synthetic
+from scan2cap_b200.data.scannet.model_util_scannet import ScannetDatasetConfig
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FLAGS = dict(detection=True, caption=True, orientation=True, distance=False)
+
+
+def _setup(V=200, B=2, N=8000, seed=31):
+    from scan2cap_b200.models.capnet import CapNet
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    DC = ScannetDatasetConfig()
+    vocab, emb, _ = synthetic.make_vocabulary(V)
+    cfg = dict(input_feature_dim=4, num_proposal=256, num_locals=10, use_topdown=True, query_mode="center",
+               graph_mode="edge_conv", num_graph_steps=2, use_relation=True, use_orientation=True)
+    torch.manual_seed(0)
+    model = CapNet(DC.num_class, vocab, emb, DC.num_heading_bin, DC.num_size_cluster, DC.mean_size_arr, **cfg).to(DEV)
+    model.train()
+    batches = []
+    for i, n_tok in enumerate((14, 23)):   # two caption lengths -> two graph signatures (bucket 4: 16 and 24 words)
+        d = synthetic.make_data_dict(B, N, use_normal=True, num_vocabs=V, seed=seed + i, lang_len=n_tok)
+        batches.append({k: torch.from_numpy(v).pin_memory() for k, v in d.items()})
+    with torch.no_grad():
+        probe = copy.deepcopy(model)({k: v.to(DEV) for k, v in batches[0].items()})
+    for b in batches:
+        b["ref_box_corner_label"] = probe["bbox_corner"][:, 5].detach().cpu().pin_memory()
+    return model, DC, batches
+
+
+def test_trainstep_graph_equals_eager_and_capture_is_side_effect_free():
+    from scan2cap_b200.engine import TrainStep
+    model, DC, batches = _setup()
+    m_e, m_g = copy.deepcopy(model), copy.deepcopy(model)
+    eager = TrainStep(m_e, DC, use_cuda_graph=False, **FLAGS)
+    graph = TrainStep(m_g, DC, use_cuda_graph=True, **FLAGS)
+    assert graph._words({"num_words": 14, "lang_ids": batches[0]["lang_ids"]}) == 16
+    assert graph._words({"lang_ids": torch.zeros(2, 32, device=DEV), "lang_len": torch.tensor([5, 9], device=DEV)}) == 32
+    order = [0, 1, 0, 1, 0]
+    for step, bi in enumerate(order):
+        le = float(eager.run(dict(batches[bi])).item())
+        lg = float(graph.run(dict(batches[bi])).item())
+        assert abs(le - lg) <= 2e-3 * abs(le), ("step %d" % step, le, lg)
+        # capture (steps 0 and 1 capture a new signature each) must not train on the batch more than once:
+        steps = {int(s["step"]) for s in graph.opt.state.values()}
+        assert steps == {step + 1}, (step, steps)
+        nbt = int(m_g.backbone_net.sa1.mlp_module.layer0.bn.bn.num_batches_tracked)
+        assert nbt == step + 1, (step, nbt)
+    assert len(graph._graphs) == 2
+    # BatchNorm running statistics track the eager run
+    be, bg = dict(m_e.named_buffers()), dict(m_g.named_buffers())
+    for n, b in bg.items():
+        if "running" in n:
+            err = float((b.double() - be[n].double()).abs().max() / (be[n].double().abs().max() + 1e-12))
+            assert err < 1e-3, (n, err)
+
+
+def test_trainstep_prefetch_double_buffer_same_result():
+    """prefetch() + run() (the e2e input pipeline of bench.py) gives the same losses as run() on resident tensors."""
+    from scan2cap_b200.engine import TrainStep
+    model, DC, batches = _setup()
+    m_a, m_b = copy.deepcopy(model), copy.deepcopy(model)
+    a = TrainStep(m_a, DC, use_cuda_graph=True, **FLAGS)
+    b = TrainStep(m_b, DC, use_cuda_graph=True, **FLAGS)
+    seq = [0, 0, 1, 0, 1, 1]
+    la = [float(a.run({k: v.to(DEV) for k, v in batches[i].items()}).item()) for i in seq]
+    lb = []
+    nxt = dict(batches[seq[0]])
+    b.prefetch(nxt)
+    for j, i in enumerate(seq):
+        cur = nxt
+        loss = b.run(cur)
+        if j + 1 < len(seq):
+            nxt = dict(batches[seq[j + 1]])
+            b.prefetch(nxt)
+        lb.append(float(loss.item()))
+    for x, y in zip(la, lb):
+        assert abs(x - y) <= 2e-3 * abs(x), (la, lb)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_gpu_shard_parity():
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29631", os.path.join(ROOT, "tests", "dist_worker.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=1200, env=env, cwd=ROOT)
+    line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
+    assert p.returncode == 0 and line, (p.stdout[-2000:], p.stderr[-4000:])
+    for rank, res in enumerate(json.loads(line[-1][7:])):
+        assert res["rank_output_equals_single_gpu_shard"], (rank, res)
+        assert res["reduced_grad_vs_mean_of_shards"] < 1e-3, (rank, res)
+        assert res["graph_grad_vs_mean_of_shards"] < 1e-3, (rank, res)
+        assert res["graph_loss_vs_eager"] < 1e-4, (rank, res)
+        assert res["graph_update_sign_agreement"] > 0.99, (rank, res)
+        assert res["adam_steps_after_first_graph_run"] == [1, 1], (rank, res)
+        assert res["bn_batches_tracked"] == 1, (rank, res)
+        assert res["second_step_loss_finite"], (rank, res)

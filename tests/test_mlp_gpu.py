@@ -48,7 +48,7 @@ def test_fused_mlp_maxpool_matches_torch_path(B, M, ns, C, widths, training):
     import copy
     from scan2cap_b200.lib.pointnet2 import pytorch_utils as pt_utils
     from scan2cap_b200.lib.pointnet2.fused_mlp import fused_mlp_maxpool
-    from scan2cap_b200.lib.pointnet2.pointnet2_modules import shared_mlp_rows
+    from compare_paths import shared_mlp_rows
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(7)
     mlp_a = pt_utils.SharedMLP([C] + list(widths), bn=True).to(DEV)
@@ -150,7 +150,7 @@ def test_fused_mlp_gap_layout_matches_torch_path(Cf, widths, ns, need_xyz):
     import copy
     from scan2cap_b200.lib.pointnet2 import pytorch_utils as pt_utils
     from scan2cap_b200.lib.pointnet2.fused_mlp import fused_mlp_maxpool
-    from scan2cap_b200.lib.pointnet2.pointnet2_modules import shared_mlp_rows
+    from compare_paths import shared_mlp_rows
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(11)
     G = 96

@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 import torch
 from scan2cap_b200.lib.pointnet2 import pytorch_utils as pt_utils
 from scan2cap_b200.lib.pointnet2.fused_mlp import fused_mlp_maxpool
-from scan2cap_b200.lib.pointnet2.pointnet2_modules import shared_mlp_rows
+from compare_paths import shared_mlp_rows
 torch.backends.cuda.matmul.allow_tf32 = False
 DEV = "cuda"
 l2 = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))

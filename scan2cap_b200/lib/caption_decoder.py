@@ -15,6 +15,7 @@ from .pointnet2._ext import _guard, _stream
 
 
 DEBUG_TS = None  # set to a list to collect (T, 8) globaltimer stamps of every forward call
+CAPTURE = None   # test hook (tests/parity_utils.py): a list that receives the rectified u / lang stacks (T,B,E) of each call
 # Kernel choice (fixed policy, both are libs2c kernels): the forward recurrence runs on the persistent cooperative grid
 # (csrc/caption_grid.cu, taken by the library when B <= 8 and a barrier counter is passed), the backward recurrence on
 # the cluster kernel (csrc/caption.cu): it measured faster there (1.33 vs 1.64 ms at B=8, T=26) -- its per-word chain
@@ -79,6 +80,8 @@ class _TopDownDecode(Function):
             P.dbg_ts = DEBUG_TS[-1].data_ptr()
         with _guard(pre_word):
             call("s2c_caption_decode_fwd", ctypes.byref(P), _stream(pre_word))
+        if CAPTURE is not None:
+            CAPTURE.append({"u": saved["u"], "lang": saved["lang"]})
         ctx.save_for_backward(pre_word, pre_tgt, mapped, obj, valid, w_tdh, *ws, buf)
         ctx.dims = (B, T, K, E, H, F)
         ctx.widths = widths

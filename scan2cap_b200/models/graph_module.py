@@ -25,6 +25,11 @@ from ..lib import linear_tc
 from ..lib.pointnet2 import _ext_graph
 
 
+# Test hook (tests/parity_utils.py): a list that receives (rectified hidden layer, message tensor, edge mask) of every
+# EdgeConv call, so a parity test can compare ReLU decisions edge by edge.  Never set by the product.
+CAPTURE = None
+
+
 class EdgeConv(nn.Module):
     def __init__(self, in_size, out_size, aggregation="add"):
         super().__init__()
@@ -38,7 +43,10 @@ class EdgeConv(nn.Module):
         z = torch.cat([x_i, x_j - x_i], dim=1)
         # Linear -> ReLU -> Linear over all E edges; the weight gradients run on the tensor-core kernel (lib/linear_tc.py)
         h = torch.relu(linear_tc.linear(z, self.map_edge[0].weight, self.map_edge[0].bias))
-        return linear_tc.linear(h, self.map_edge[2].weight, self.map_edge[2].bias)
+        msg = linear_tc.linear(h, self.map_edge[2].weight, self.map_edge[2].bias)
+        if CAPTURE is not None:
+            CAPTURE.append({"hidden": h.detach(), "message": msg})
+        return msg
 
     def forward(self, x, edge_index, edge_mask=None):
         """x (N,in), edge_index (2,E) long, optional edge_mask (E) bool -> (out (N,out), message (E,out))."""
@@ -111,6 +119,8 @@ class GraphModule(nn.Module):
         col_g = (base + nbr).reshape(-1)
         edge_g = torch.stack([row_g, col_g], 0)
         emask = flat_valid.reshape(-1)
+        if CAPTURE is not None:
+            CAPTURE.append({"edge_mask": flat_valid})
 
         x = obj_feats.reshape(B * K, -1)
         node_feat, message = x, None

@@ -9,6 +9,13 @@ which is what made round 1 use a loose global bar.  Here the decisions of both s
   * per shared-MLP call (SA1..SA4, FP1, FP2, vote aggregation): ReLU masks of every layer and the max-pool routing;
   * a GROUP (one pooled output vector; one point for the FP modules) in which any decision differs is excluded from
     BOTH backward passes (its output gradient is zeroed by a tensor hook), the number of such groups is reported;
+  * the two small point-wise heads (voting module, proposal head: Conv1d -> BatchNorm -> ReLU twice) are handled by
+    margin instead: a row (seed / proposal) with any pre-ReLU activation of the ORACLE within HEAD_MARGIN x mean|y| of
+    zero could flip, and is excluded from both backward passes the same way (hooks on the heads' output tensors);
+  * EdgeConv message MLPs (graph module): the ReLU masks of every edge are compared exactly; a flipped edge's message
+    gradient is zeroed on both sides.  Caption decoder: the ReLU masks of map_topdown / map_lang are compared per
+    (scene, word); from the first flipped word of a scene on, that scene's logits are excluded from both backward
+    passes (the recurrence carries the flip forward);
   * all remaining groups took identical decisions, so every parameter's gradient must agree to fp32 accuracy:
     relative L2 <= GRAD_RTOL per parameter, measured against max(|g|, 1e-2 x the largest gradient norm of the same
     sub-module) (bias-like parameters in front of a BatchNorm have an analytically zero gradient).
@@ -18,6 +25,13 @@ import os
 import torch
 
 GRAD_RTOL = 1e-3
+HEAD_MARGIN = 5e-4
+HEAD_KEYS = {   # head -> (oracle BatchNorm modules in front of its ReLUs, data_dict outputs that carry its rows)
+    "vgen": (("vgen.bn1", "vgen.bn2"), ("vote_xyz", "vote_features")),
+    "proposal.proposal": (("proposal.proposal.1", "proposal.proposal.4"),
+                          ("objectness_scores", "center", "heading_scores", "heading_residuals_normalized",
+                           "size_scores", "size_residuals_normalized", "sem_cls_scores")),
+}
 MODULES = ["backbone_net.sa1", "backbone_net.sa2", "backbone_net.sa3", "backbone_net.sa4", "backbone_net.fp1",
            "backbone_net.fp2", "proposal.vote_aggregation"]
 
@@ -41,11 +55,33 @@ class DecisionTracker(object):
     def __init__(self, ours, ref):
         from scan2cap_b200.lib.pointnet2 import fused_mlp
         self.fused_mlp = fused_mlp
+        from scan2cap_b200.lib import caption_decoder
+        from scan2cap_b200.models import graph_module
+        self.caption_decoder, self.graph_module = caption_decoder, graph_module
+        self.edge_names = [n for n in ("graph.gc_layers.0", "graph.gc_layers.1", "graph.edge_layer")
+                           if self._has(ref, n)]
+        self.ref_edge_hidden = {n: [] for n in self.edge_names}   # per call (= per scene): post-ReLU (E_b, 128)
+        self.edge_keep = {}                                       # (name, call) -> (E_b) float, oracle side
+        self.ref_cap = {"u": [], "lang": []}                      # per word: post-ReLU (B, emb)
         self.ours, self.ref = ours, ref
         self.keep = {}        # module name -> (B, M) float 0/1, filled by resolve()
         self.flips = {}       # module name -> (#groups with a differing decision, #groups)
         self.ref_masks = {name: [] for name in MODULES}
         self.handles = []
+        self.head_risk = {}   # head -> (B, rows) bool: some pre-ReLU activation of the oracle is within the margin of 0
+        for head, (bns, _) in HEAD_KEYS.items():
+            for bn in bns:
+                self.handles.append(_get(ref, bn).register_forward_hook(self._head_hook(head)))
+        for n in self.edge_names:
+            conv = _get(ref, n)
+            self.handles.append(conv.map_edge[1].register_forward_hook(
+                lambda mod, inp, out, n=n: self.ref_edge_hidden[n].append(out.detach())))
+            self.handles.append(conv.map_edge.register_forward_hook(self._ref_edge_out_hook(n)))
+        if hasattr(ref, "caption"):
+            self.handles.append(ref.caption.map_topdown.register_forward_hook(
+                lambda mod, inp, out: self.ref_cap["u"].append(out.detach())))
+            self.handles.append(ref.caption.map_lang.register_forward_hook(
+                lambda mod, inp, out: self.ref_cap["lang"].append(out.detach())))
         for name in MODULES:
             mo, mr = _get(ours, name), _get(ref, name)
             mlp_r = mr.mlp_module if hasattr(mr, "mlp_module") else mr.mlp
@@ -54,11 +90,87 @@ class DecisionTracker(object):
             self.handles.append(mo.register_forward_hook(self._out_hook(name)))
             self.handles.append(mr.register_forward_hook(self._out_hook(name)))
 
+    @staticmethod
+    def _has(model, dotted):
+        try:
+            _get(model, dotted)
+            return True
+        except (AttributeError, IndexError):
+            return False
+
+    def _ref_edge_out_hook(self, name):
+        def hook(mod, inp, out):
+            call = len(self.ref_edge_hidden[name]) - 1   # the ReLU hook of this call has already fired
+            if out.requires_grad:
+                out.register_hook(lambda g, key=(name, call): g * self.edge_keep[key].to(g.dtype).unsqueeze(-1))
+        return hook
+
+    def resolve_graph_and_caption(self, o, r):
+        """Exact ReLU decisions of the EdgeConv message MLPs (per edge) and of the caption decoder (per scene, word)."""
+        gcap, ccap = self.graph_module.CAPTURE, self.caption_decoder.CAPTURE
+        self.graph_module.CAPTURE = self.caption_decoder.CAPTURE = None
+        if self.edge_names:
+            emask = gcap[0]["edge_mask"]                 # (B, K*L) bool: slot (i, t) is an edge of the compacted graph
+            B = emask.shape[0]
+            layers = gcap[1:]
+            assert len(layers) == len(self.edge_names), (len(layers), self.edge_names)
+            nflip = nedge = 0
+            for name, cap in zip(self.edge_names, layers):
+                hid = cap["hidden"].view(B, emask.shape[1], -1) > 0
+                keep = torch.ones(emask.shape, dtype=torch.float32, device=emask.device)
+                scenes = [b for b in range(B) if int(emask[b].sum()) > 0] if name.endswith("edge_layer") else list(range(B))
+                assert len(scenes) == len(self.ref_edge_hidden[name]), (name, len(scenes), len(self.ref_edge_hidden[name]))
+                for call, b in enumerate(scenes):
+                    theirs = self.ref_edge_hidden[name][call] > 0            # (E_b, 128), same edge order
+                    mine = hid[b][emask[b]]
+                    assert mine.shape == theirs.shape, (name, b, mine.shape, theirs.shape)
+                    same = (mine == theirs).all(-1)
+                    self.edge_keep[(name, call)] = same.float()
+                    keep[b][emask[b]] = same.float()
+                    nflip += int((~same).sum())
+                    nedge += same.numel()
+                cap["message"].register_hook(lambda g, k=keep.reshape(-1, 1): g * k.to(g.dtype))
+            self.flips["graph edges"] = (nflip, nedge)
+        if ccap:
+            assert len(ccap) == 1
+            u_o, l_o = ccap[0]["u"] > 0, ccap[0]["lang"] > 0              # (T, B, emb)
+            u_r = torch.stack(self.ref_cap["u"], 0) > 0
+            l_r = torch.stack(self.ref_cap["lang"], 0) > 0
+            assert u_o.shape == u_r.shape, (u_o.shape, u_r.shape)
+            flip = ((u_o != u_r).any(-1) | (l_o != l_r).any(-1)).t()       # (B, T)
+            keep = (torch.cumsum(flip.long(), 1) == 0).float()            # words before the scene's first flip
+            self.flips["caption words"] = (int((keep == 0).sum()), keep.numel())
+            for d in (o, r):
+                d["lang_cap"].register_hook(lambda g, k=keep.unsqueeze(-1): g * k.to(g.dtype))
+
     # -- capture ---------------------------------------------------------------------------------------------
     def _ref_layer_hook(self, name):
         def hook(mod, inp, out):
             self.ref_masks[name].append(out.detach())   # post-ReLU activations (B,C,M,ns); > 0 <=> pre-activation > 0
         return hook
+
+    def _head_hook(self, head):
+        def hook(mod, inp, out):   # out: (B, C, rows) pre-ReLU
+            y = out.detach()
+            risk = (y.abs() < HEAD_MARGIN * y.abs().mean()).any(1)
+            self.head_risk[head] = risk if head not in self.head_risk else (self.head_risk[head] | risk)
+        return hook
+
+    def exclude_head_rows(self, o, r):
+        """Zero the gradient of the at-risk rows of the two heads at their output tensors, in both data_dicts."""
+        for head, (_, keys) in HEAD_KEYS.items():
+            keep = (~self.head_risk[head]).float()    # (B, rows)
+            self.flips[head] = (int(self.head_risk[head].sum()), keep.numel())
+            for d in (o, r):
+                for k in keys:
+                    t = d[k]
+                    if not t.requires_grad:
+                        continue
+                    if t.shape[1] == keep.shape[1]:     # (B, rows, ...)
+                        m = keep.view(keep.shape + (1,) * (t.dim() - 2))
+                    else:                                # (B, C, rows)
+                        m = keep.unsqueeze(1)
+                    t.register_hook(lambda g, m=m: g * m.to(g.dtype))
 
     def _out_hook(self, name):
         def hook(mod, inp, out):
@@ -69,10 +181,14 @@ class DecisionTracker(object):
 
     def __enter__(self):
         self.fused_mlp.CAPTURE = []
+        self.graph_module.CAPTURE = []
+        self.caption_decoder.CAPTURE = []
+        self.head_risk = {}
         return self
 
     def __exit__(self, *a):
         self.fused_mlp.CAPTURE = None
+        self.graph_module.CAPTURE = self.caption_decoder.CAPTURE = None
         for h in self.handles:
             h.remove()
 
@@ -83,9 +199,21 @@ class DecisionTracker(object):
         return dict(zip(MODULES, cap))
 
     # -- compare -------------------------------------------------------------------------------------------
-    def resolve(self):
+    def resolve(self, o=None, r=None):
         ours = self.ours_captured()
         total = 0
+        membership = None
+        if o is not None:
+            # vote aggregation groups votes whose COORDINATES differ by ~1e-6 between the two sides: a vote within that
+            # distance of a ball's surface is a member on one side only (the other six grouping stages work on
+            # bit-identical coordinates).  Same kernel on both sides' tensors -> per-group "same neighbour list".
+            from scan2cap_b200.lib.pointnet2 import _ext
+            va = self.ours.proposal.vote_aggregation
+            io = _ext.ball_query(o["aggregated_vote_xyz"].detach().contiguous(), o["vote_xyz"].detach().contiguous(),
+                                 va.radius, va.nsample)
+            ir = _ext.ball_query(r["aggregated_vote_xyz"].detach().contiguous(), r["vote_xyz"].detach().contiguous(),
+                                 va.radius, va.nsample)
+            membership = (io == ir).all(-1)
         for name in MODULES:
             o, r = ours[name], self.ref_masks[name]
             L, ns = len(o["Ys"]), o["ns"]
@@ -111,6 +239,8 @@ class DecisionTracker(object):
             r_in_o = torch.gather(act_o, 2, am_r.unsqueeze(2)).squeeze(2) == max_o
             dead = (max_o <= 0) & (max_r <= 0)     # no gradient flows through an all-rectified channel
             same &= (pos_same & ((o_in_r & r_in_o) | dead)).all(-1)
+            if name == "proposal.vote_aggregation" and membership is not None:
+                same &= membership
             self.keep[name] = same.float()
             nflip = int((~same).sum())
             self.flips[name] = (nflip, B * M)

@@ -220,6 +220,10 @@ S2C_API int s2c_mlp_layer_bwd_weight(const float *dY, long long lddy, const floa
  *   only the points of the 27 surrounding cells and recovers "the first nsample indices in index order" from a
  *   per-warp bitmap.  ~200 distance tests per centre instead of n.  grouped may be NULL (ball query only), idx may be
  *   NULL (grouped only).  workspace: s2c_ball_query_grid_workspace_bytes(B, n) bytes of device memory. */
+/* Tuning knob of the TMA gather epilogue of s2c_query_and_group_grid (ring geometry per warp): 0 = default
+ * (8-row tiles x 3 per mover, 10 mover + 10 query warps), 1 = 8x4x8, 2 = 8x4x9, 3 = 8x5x7, 4 = 8x3x12, 5 = 16x3x6; -1 = disable the TMA path (LDG/STG epilogue; used by the
+ * tests to cross-check the two epilogues bit for bit).  Process-wide; not part of the reference surface. */
+S2C_API int s2c_query_and_group_grid_tune(int variant);
 S2C_API long long s2c_ball_query_grid_workspace_bytes(int B, int n);
 S2C_API int s2c_query_and_group_grid(const float *xyz, const float *new_xyz, const float *features, int B, int n,
                                      int M, int C, int feat_layout, long long feat_stride, float radius,

@@ -72,6 +72,8 @@ def _load():
     lib.s2c_last_error.restype = ctypes.c_char_p
     lib.s2c_ball_query_grid_workspace_bytes.restype = c_ll
     lib.s2c_ball_query_grid_workspace_bytes.argtypes = [c_int, c_int]
+    lib.s2c_query_and_group_grid_tune.restype = c_int
+    lib.s2c_query_and_group_grid_tune.argtypes = [c_int]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.argtypes = argtypes

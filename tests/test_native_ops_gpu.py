@@ -264,3 +264,42 @@ def test_errors_raise(ext):
         ext.ball_query(x.cuda(), x.cuda().transpose(1, 2), 0.1, 4)  # non-contiguous
     with pytest.raises(RuntimeError):
         ext.ball_query(x.cuda(), x.cuda(), 0.1, 0)  # nsample out of range -> S2C_ERR_INVALID_ARGUMENT
+
+
+@pytest.mark.parametrize("ns", [4, 16, 20, 50, 64, 128])
+@pytest.mark.parametrize("C,stride_pad", [(132, 0), (132, 4), (36, 0), (252, 0)])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+def test_query_and_group_tma_gather_matches_oracle(ns, C, stride_pad, variant, ext, oracle):
+    """TMA epilogue of the uniform-grid query (cp.async.bulk.tensor tile::gather4 loads + bulk stores; taken for
+    16-byte aligned point-major feature rows with (C+4) % 8 == 0) against the oracle composition AND bit for bit
+    against the LDG/STG epilogue, for every ring geometry, tile tails (ns % 8 != 0) and strided source rows."""
+    import scan2cap_b200._lib as L
+    if variant != 0 and (ns, C, stride_pad) not in ((64, 132, 0), (20, 132, 4), (128, 36, 0)):
+        pytest.skip("ring geometries are cross-checked on three shapes")
+    B, n, M, r = 2, 6000, 300, 0.3
+    pc, _ = synthetic.make_point_clouds(B, n, use_height=False, seed=17)
+    xyz = pc[..., :3].copy()
+    rng = np.random.default_rng(ns + C)
+    new_xyz = xyz[:, rng.permutation(n)[:M]].copy()
+    new_xyz[:, -1] += 50.0   # an empty ball: the list stays all-zero, row 0 is gathered nsample times
+    feats = rng.standard_normal((B, n, C + stride_pad)).astype(np.float32)
+    idx = oracle.ball_query(new_xyz, xyz, r, ns)
+    g_xyz = oracle.group_points(np.ascontiguousarray(xyz.transpose(0, 2, 1)), idx)
+    g_xyz = (g_xyz - new_xyz.transpose(0, 2, 1)[..., None]) * (np.float32(1.0) / np.float32(r))
+    g_f = oracle.group_points(np.ascontiguousarray(feats[..., :C].transpose(0, 2, 1)), idx)
+    f = T(feats)[..., :C]   # (B,n,C) view with row stride C + stride_pad
+    try:
+        L.LIB.s2c_query_and_group_grid_tune(variant)
+        gp, gidx = ext.query_and_group(T(xyz), T(new_xyz), f, r, ns, True, feat_point_major=True, channels_last=True,
+                                       pad4=True)
+        L.LIB.s2c_query_and_group_grid_tune(-1)
+        gp_ldg, _ = ext.query_and_group(T(xyz), T(new_xyz), f, r, ns, True, feat_point_major=True, channels_last=True,
+                                        pad4=True)
+    finally:
+        L.LIB.s2c_query_and_group_grid_tune(0)
+    np.testing.assert_array_equal(N(gidx), idx)
+    assert gp.shape == (B, C + 4, M, ns)
+    assert torch.equal(gp, gp_ldg), "TMA and LDG epilogues differ"
+    np.testing.assert_array_equal(N(gp[:, :3]), g_xyz)
+    np.testing.assert_array_equal(N(gp[:, 4:]), g_f)
+    assert float(gp[:, 3].abs().sum()) == 0.0

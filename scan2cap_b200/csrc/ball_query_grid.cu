@@ -61,13 +61,15 @@ __device__ __forceinline__ void cluster_sync_all() {
 __global__ void __launch_bounds__(kBuildThreads)
 grid_build_kernel(const float *__restrict__ xyz, int n, float radius, GridParams *__restrict__ params,
                   int *__restrict__ cell_start /* (B, kMaxCells+1) */, float4 *__restrict__ sorted /* (B, n): x,y,z,index */,
-                  int *__restrict__ cursor /* (B, kMaxCells) scratch */, float *__restrict__ bbox /* (B, CL, 6) scratch */) {
+                  int *__restrict__ cursor /* (B, kMaxCells) scratch */, float *__restrict__ bbox /* (B, CL, 6) scratch */,
+                  unsigned int *__restrict__ next_centre /* work counter of the gather kernel */) {
   __shared__ float s_red[6][32];
   __shared__ GridParams gp;
   __shared__ int s_scan[kBuildThreads / 32];
   const int b = blockIdx.x / kBuildCluster, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rank = (int)cluster_rank();
   const int gtid = rank * kBuildThreads + tid, gthreads = kBuildCluster * kBuildThreads;
+  if (blockIdx.x == 0 && tid == 0) *next_centre = 0u;
   xyz += (size_t)b * n * 3;
   cell_start += (size_t)b * (kMaxCells + 1);
   sorted += (size_t)b * n;
@@ -397,7 +399,7 @@ __global__ void __launch_bounds__(2 * kWarps * 32, 1)
 group_rows_tma_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz, int n, int M, long long centres,
                       int nsample, int *__restrict__ idx, GroupArgs ga, const __grid_constant__ CUtensorMap tmap,
                       float radius, const GridParams *__restrict__ params, const int *__restrict__ cell_start,
-                      const float4 *__restrict__ sorted) {
+                      const float4 *__restrict__ sorted, unsigned int *__restrict__ next_centre) {
   static_assert(kTileRows % 4 == 0 && kTileRows <= 32 && kStages >= 3 && kEntries >= 2,
                 "tile = whole gather4 instructions, one lane per row; ring of at least 3 tiles; 2+ entries per pair");
   constexpr int kAhead = kStages - 2;  // tile loads in flight per mover
@@ -407,10 +409,10 @@ group_rows_tma_kernel(const float *__restrict__ new_xyz, const float *__restrict
   const uint32_t row_bytes = (uint32_t)CP * 4u;
   const uint32_t tile_bytes = row_bytes * kTileRows;
   const int ns4 = (nsample + 3) & ~3;
-  // layout: [rings: warps x stages x tile_bytes] [entries: warps x kEntries x (xs: ns4 float4 | li: ns4 int)]
+  // layout: [rings: warps x stages x tile_bytes] [entries: warps x kEntries x (xs: ns4 float4 | li: ns4 int | centre id)]
   //         [slot meta: warps x stages x 16 B] [mbarriers: warps x stages] [done | taken: 2 x warps ints, 128 B]
   //         [query warps' hit lists: warps x kHitCapQ ints]
-  const size_t entry_bytes = (size_t)ns4 * 20;
+  const size_t entry_bytes = (size_t)ns4 * 20 + 16;
   unsigned char *p0 = smem_raw + (size_t)kWarps * kStages * tile_bytes;
   unsigned char *p1 = p0 + (size_t)kWarps * kEntries * entry_bytes;
   unsigned char *p2 = p1 + (size_t)kWarps * kStages * 24;
@@ -420,19 +422,30 @@ group_rows_tma_kernel(const float *__restrict__ new_xyz, const float *__restrict
   __syncthreads();
   const int pair = warp < kWarps ? warp : warp - kWarps;
   unsigned char *entries = p0 + (size_t)pair * kEntries * entry_bytes;
-  const long long c_first = (long long)blockIdx.x * kWarps + pair, stride = (long long)gridDim.x * kWarps;
+  // Centres are handed out dynamically (one atomic per centre on a counter the build kernel zeroed): a CTA that
+  // starts late -- the sampling chain of the deeper levels runs on a side stream and occupies SMs -- simply takes fewer.
 
   if (warp >= kWarps) {
     // ---------------------------------------------------------------- query role
     int *hk = reinterpret_cast<int *>(p2 + 128) + (size_t)pair * kHitCapQ;
     const float radius2 = __fmul_rn(radius, radius);
-    int k = 0;
-    for (long long c = c_first; c < centres; c += stride, ++k) {
+    for (int k = 0;; ++k) {
       if (lane == 0) while (k - taken[pair] >= kEntries) __nanosleep(64);   // the mover still uses entry k % kEntries
       __syncwarp();
       __threadfence_block();
       float4 *xs = reinterpret_cast<float4 *>(entries + (size_t)(k % kEntries) * entry_bytes);
       int *li = reinterpret_cast<int *>(xs + ns4);
+      long long c = 0;
+      if (lane == 0) c = (long long)atomicAdd(next_centre, 1u);
+      c = __shfl_sync(0xffffffffu, c, 0);
+      if (c >= centres) {   // no work left: tell the mover
+        if (lane == 0) {
+          *reinterpret_cast<long long *>(li + ns4) = -1;
+          __threadfence_block();
+          done[pair] = k + 1;
+        }
+        return;
+      }
       const int b = (int)(c / M);
       const GridParams gp = params[b];
       const float *ctr = new_xyz + (size_t)c * 3;
@@ -454,11 +467,11 @@ group_rows_tma_kernel(const float *__restrict__ new_xyz, const float *__restrict
         v.w = 0.f;
         xs[s] = v;
       }
+      if (lane == 0) *reinterpret_cast<long long *>(li + ns4) = c;
       __threadfence_block();
       __syncwarp();
       if (lane == 0) done[pair] = k + 1;
     }
-    return;
   }
 
   // ------------------------------------------------------------------ mover role
@@ -502,15 +515,16 @@ group_rows_tma_kernel(const float *__restrict__ new_xyz, const float *__restrict
     ++finished;
   };
 
-  int k = 0;
-  for (long long c = c_first; c < centres; c += stride, ++k) {
+  for (int k = 0;; ++k) {
     if (lane == 0) while (done[warp] <= k) __nanosleep(64);   // the paired query warp has filled entry k % kEntries
     __syncwarp();
     __threadfence_block();
-    const int b = (int)(c / M);
-    const int row_base = b * n;   // row of this scene's point 0 in the (B*n, C) feature matrix
     const float4 *xs = reinterpret_cast<const float4 *>(entries + (size_t)(k % kEntries) * entry_bytes);
     const int *li = reinterpret_cast<const int *>(xs + ns4);
+    const long long c = *reinterpret_cast<const long long *>(li + ns4);
+    if (c < 0) break;
+    const int b = (int)(c / M);
+    const int row_base = b * n;   // row of this scene's point 0 in the (B*n, C) feature matrix
     float *out = ga.grouped + (size_t)c * (size_t)nsample * CP;
     for (int t = 0; t < T; ++t) {
       if (issued - finished == (uint32_t)kAhead) finish();
@@ -588,7 +602,7 @@ extern "C" long long s2c_ball_query_grid_workspace_bytes(int B, int n) {
   using namespace s2c;
   // params (64 B per scene) | sorted (B, n) float4 | cell_start (B, kMaxCells+1) | cursor (B, kMaxCells)
   return (long long)B * 64 + (long long)B * n * 16 + (long long)B * (kMaxCells + 1) * 4 + (long long)B * kMaxCells * 4 +
-         (long long)B * kBuildCluster * 6 * 4 + 512;
+         (long long)B * kBuildCluster * 6 * 4 + 64 + 512;
 }
 
 extern "C" int s2c_query_and_group_grid(const float *xyz, const float *new_xyz, const float *features, int B, int n, int M,
@@ -613,6 +627,7 @@ extern "C" int s2c_query_and_group_grid(const float *xyz, const float *new_xyz, 
   int *cell_start = (int *)(sorted + (size_t)B * n);
   int *cursor = cell_start + (size_t)B * (kMaxCells + 1);
   float *bbox = (float *)(cursor + (size_t)B * kMaxCells);
+  unsigned int *counter = (unsigned int *)(bbox + (size_t)B * kBuildCluster * 6);
   {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(B * kBuildCluster));
@@ -622,7 +637,7 @@ extern "C" int s2c_query_and_group_grid(const float *xyz, const float *new_xyz, 
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = kBuildCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    S2C_CUDA(cudaLaunchKernelEx(&cfg, grid_build_kernel, xyz, n, radius, params, cell_start, sorted, cursor, bbox), "grid_build launch");
+    S2C_CUDA(cudaLaunchKernelEx(&cfg, grid_build_kernel, xyz, n, radius, params, cell_start, sorted, cursor, bbox, counter), "grid_build launch");
   }
   GroupArgs ga = {};
   ga.features = features; ga.grouped = grouped; ga.C = C;
@@ -644,14 +659,14 @@ extern "C" int s2c_query_and_group_grid(const float *xyz, const float *new_xyz, 
     // 2. the bytes
     const int ns4 = (nsample + 3) & ~3;
     auto launch = [&](auto kern, int tile_rows, int stages, int warps, int nentries) -> int {
-      const size_t smem = (size_t)warps * stages * tile_rows * (C + 4) * 4 + (size_t)warps * nentries * ns4 * 20 +
+      const size_t smem = (size_t)warps * stages * tile_rows * (C + 4) * 4 + (size_t)warps * nentries * (ns4 * 20 + 16) +
                           (size_t)warps * stages * 24 + 128 + (size_t)warps * kHitCapQ * 4;
       if (smem > 227 * 1024) return -1;
       S2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "group_rows_tma smem");
       const long long centres = (long long)B * M;
       const int ctas = (int)min((long long)kNumSMs, ceil_div_ll(centres, warps));
       kern<<<ctas, 2 * warps * 32, smem, st>>>(new_xyz, xyz, n, M, centres, nsample, idx, ga, tmap, radius, params,
-                                               cell_start, sorted);
+                                               cell_start, sorted, counter);
       S2C_CHECK_LAUNCH("group_rows_tma");
       return S2C_OK;
     };

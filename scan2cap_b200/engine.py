@@ -30,7 +30,7 @@ from .models.backbone_module import padded_point_clouds, padded_point_clouds_lik
 class TrainStep(object):
     def __init__(self, model, dataset_config, lr=1e-3, weight_decay=1e-5, detection=True, caption=True,
                  orientation=False, distance=False, use_cuda_graph=True, loss_fn=None, word_bucket=4,
-                 collective_in_graph=True):
+                 collective_in_graph=True, prefetch_indices=True):
         self.model = model
         self.DC = dataset_config
         self.flags = dict(detection=detection, caption=caption, orientation=orientation, distance=distance)
@@ -42,6 +42,9 @@ class TrainStep(object):
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.word_bucket = max(1, int(word_bucket))
         self.collective_in_graph = collective_in_graph
+        # FPS indices depend on the coordinates only: computed outside the step graph, for the NEXT batch on the copy
+        # stream while the current step runs (prefetch()), so the 2 ms serial sampling chain leaves the critical path
+        self.prefetch_indices = bool(prefetch_indices) and hasattr(getattr(model, "backbone_net", None), "sample_indices")
         self._graphs = {}
         self._stage = {}           # signature -> staging copies of the static input buffers (prefetch target)
         self._prefetched = None    # (data_dict object, signature) whose inputs are in flight / in the staging buffers
@@ -116,6 +119,10 @@ class TrainStep(object):
             pc = data["point_clouds"]
             static["point_clouds"] = padded_point_clouds_like(pc.shape, pc.dtype, self.device)
         self._load(static, data)
+        if self.prefetch_indices:
+            # static buffers of the sampling indices (filled by prefetch() on the copy stream, or by _load_indices())
+            static["fps_precomputed"] = [(i.clone(), x.clone()) for i, x in
+                                         self.model.backbone_net.sample_indices(static["point_clouds"][..., :3])]
         # warm-up on a side stream (allocator / cuBLAS workspaces / lazy kernel loading), as capture requires;
         # no collective (ranks capture independently), and every side effect on the training state is undone
         snap = self._snapshot()
@@ -167,11 +174,19 @@ class TrainStep(object):
             if isinstance(v, torch.Tensor):
                 static[k].copy_(v, non_blocking=True)
 
+    def _load_indices(self, dst, point_clouds):
+        """FPS of all levels for `point_clouds` into the (inds, xyz) buffers `dst`, on the current stream."""
+        fresh = self.model.backbone_net.sample_indices(point_clouds[..., :3])
+        for (di, dx), (si, sx) in zip(dst, fresh):
+            di.copy_(si, non_blocking=True)
+            dx.copy_(sx, non_blocking=True)
+
     # ---- public ----------------------------------------------------------------------------------------------
     def prefetch(self, data_dict):
         """Start copying the NEXT step's inputs (pinned host tensors) to the device on a copy stream, so the transfer
         overlaps the step that is currently running; pass the SAME dict object to run() afterwards (and do not modify
-        its tensors in between).  A no-op until the graph for this input signature exists, or without CUDA graphs."""
+        its tensors in between).  Device-resident source tensors must already be complete (the copy stream does not wait
+        for work queued on the current stream -- that would serialise it behind the running step).  A no-op until the graph for this input signature exists, or without CUDA graphs."""
         if not self.use_graph:
             return
         data_dict["num_words"] = self._words(data_dict)
@@ -179,11 +194,17 @@ class TrainStep(object):
         if sig not in self._graphs:
             return
         static = self._graphs[sig][0]
-        if sig not in self._stage:
-            self._stage[sig] = {k: torch.empty(v.shape, dtype=v.dtype, device=v.device) for k, v in static.items()
-                                if isinstance(v, torch.Tensor)}
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(self.device)
+        if sig not in self._stage:
+            # allocated ON the copy stream: a block the allocator recycles from the main stream's pool could still be in
+            # use by kernels queued there, and the copy stream does not wait for the main stream
+            with torch.cuda.stream(self._copy_stream):
+                self._stage[sig] = {k: torch.empty(v.shape, dtype=v.dtype, device=v.device) for k, v in static.items()
+                                    if isinstance(v, torch.Tensor)}
+                if self.prefetch_indices:
+                    self._stage[sig]["fps_precomputed"] = [(torch.empty_like(i), torch.empty_like(x))
+                                                           for i, x in static["fps_precomputed"]]
         if self._stage_free is not None:
             # wait only for the staging -> static copies of the step that consumed the staging buffers last (an event
             # recorded before that step's graph replay), NOT for the step itself: the transfer overlaps its compute
@@ -192,6 +213,8 @@ class TrainStep(object):
             for k, v in data_dict.items():
                 if isinstance(v, torch.Tensor):
                     self._stage[sig][k].copy_(v, non_blocking=True)
+            if self.prefetch_indices:
+                self._load_indices(self._stage[sig]["fps_precomputed"], self._stage[sig]["point_clouds"])
         self._prefetched = (data_dict, sig)
 
     def run(self, data_dict):
@@ -213,11 +236,18 @@ class TrainStep(object):
             # inputs already on the device (prefetch): wait for the copy stream, then staging -> static (device copies)
             torch.cuda.current_stream(self.device).wait_stream(self._copy_stream)
             for k, v in self._stage[sig].items():
-                static[k].copy_(v, non_blocking=True)
+                if k == "fps_precomputed":
+                    for (di, dx), (si, sx) in zip(static[k], v):
+                        di.copy_(si, non_blocking=True)
+                        dx.copy_(sx, non_blocking=True)
+                else:
+                    static[k].copy_(v, non_blocking=True)
             self._stage_free = torch.cuda.Event()
             self._stage_free.record(torch.cuda.current_stream(self.device))
         else:
             self._load(static, data_dict)
+            if self.prefetch_indices:   # not prefetched: sample inline, in front of the graph
+                self._load_indices(static["fps_precomputed"], static["point_clouds"])
         self._prefetched = None
         g1.replay()
         if g2 is not None:

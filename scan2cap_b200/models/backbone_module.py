@@ -72,12 +72,29 @@ class Pointnet2Backbone(nn.Module):
             feats = padded_point_clouds(pc)[..., 3:]
         return xyz, feats.transpose(1, 2)
 
+    def sample_indices(self, xyz):
+        """FPS of all four levels (40000 -> 2048 -> 1024 -> 512 -> 256 for the default sizes) from coordinates alone:
+        [(inds (B,m) int32, xyz (B,m,3))] x 4, enqueued on the current stream.  The indices depend on nothing but
+        point_clouds[..., :3], so a training loop can compute them for batch i+1 while batch i is in flight
+        (engine.TrainStep.prefetch) and pass them in as data_dict["fps_precomputed"]."""
+        out = []
+        cur = xyz.contiguous()
+        for m in (self.sa1.npoint, self.sa2.npoint, self.sa3.npoint, self.sa4.npoint):
+            inds, cur = _ext.furthest_point_sampling_with_xyz(cur, m)
+            out.append((inds, cur))
+        return out
+
     def forward(self, data_dict):
         pointcloud = data_dict["point_clouds"]
         xyz, features = self._break_up_pc(pointcloud)
 
         ahead = [(None, None)] * 3
-        if SAMPLE_AHEAD and xyz.is_cuda and not xyz.requires_grad:
+        pre = data_dict.get("fps_precomputed")
+        if pre is not None:
+            # sampled ahead of time (same kernels, same result): the 2 ms serial FPS chain is off the step's critical path
+            (inds1, xyz1), ahead = pre[0], list(pre[1:])
+            xyz, features, fps_inds = self.sa1(xyz, features, inds1, sampled_xyz=xyz1)
+        elif SAMPLE_AHEAD and xyz.is_cuda and not xyz.requires_grad:
             # FPS of all four levels up front: level 1 on this stream, levels 2-4 (8 CTAs each) on a side stream that
             # overlaps SA1's grouping and MLP; the streams join before SA2 (a fork/join the CUDA-graph capture keeps)
             inds1, xyz1 = _ext.furthest_point_sampling_with_xyz(xyz, self.sa1.npoint)

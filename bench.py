@@ -114,6 +114,26 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def trace(msg):
+    """Progress marker on stderr (S2C_BENCH_TRACE=1): where a multi-rank run stops if it ever hangs."""
+    if os.environ.get("S2C_BENCH_TRACE"):
+        sys.stderr.write("[bench rank %s %.1fs] %s\n" % (os.environ.get("RANK", "0"), time.time() - _T0, msg))
+        sys.stderr.flush()
+
+
+_T0 = time.time()
+
+
+def finish(world):
+    """Leave without tearing NCCL down: destroy_process_group() blocks while captured graphs still hold the
+    communicator's kernels (observed: the JSON line printed after 11 s, the process never exited).  Every rank has
+    passed the final barrier of the timed region by now; flush and exit 0."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        os._exit(0)
+
+
 def workload_string(name, B, N, F, num_words):
     return ("%s: full CapNet training step (zero_grad+fwd+loss+bwd+grad all-reduce+Adam), batch %d/GPU, %d pts x %d "
             "floats, K=256 proposals, L=10 locals, 2 graph steps, top-down caption, V=%d, caption length %d words"
@@ -294,9 +314,11 @@ def run_ours(args, emit, rank, world, local_rank):
     import scan2cap_b200._lib as L
     timer = Timer(device, world)
     pk, pk_src = peaks()
+    trace("process group up")
     main = Ours(args.config, device, rank, use_graph=not args.no_graph)
-
+    trace("model built")
     main.timed(timer, args.warmup, False)
+    trace("warm-up done (graph captured)")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -306,9 +328,12 @@ def run_ours(args, emit, rank, world, local_rank):
     if main.engine.use_graph:
         launches = main.engine.kernels_per_step * args.steps  # replayed from the graph: no Python call per launch
     clocks = sampler.stop() if rank == 0 else None
+    trace("timed steps done")
     qg_ms, qg_kernel = main.query_group_events(timer, min(args.steps, 5))
+    trace("eager kernel timing done")
     main.timed(timer, 2, True)
     ms_e2e, last_loss = main.timed(timer, args.steps, True)
+    trace("e2e done")
 
     second = None
     if args.config == "c3" and not args.no_config4:
@@ -341,8 +366,7 @@ def run_ours(args, emit, rank, world, local_rank):
         del c4
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world)
         return
     scenes = main.B * world * args.steps
     line = {
@@ -371,8 +395,7 @@ def run_ours(args, emit, rank, world, local_rank):
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline()
     emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    finish(world)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -442,8 +465,7 @@ def run_reference(args, emit, rank, world, local_rank):
                           "last_loss": m4["last"]}}
     RA.assert_clean_process()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world)
         return
     scenes = m["B"] * world * args.steps
     line = {
@@ -469,8 +491,7 @@ def run_reference(args, emit, rank, world, local_rank):
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline()
     emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    finish(world)
 
 
 def main():

@@ -94,7 +94,9 @@ def main():
     dist.all_gather_object(gathered, res)
     if rank == 0:
         print("RESULT " + json.dumps(gathered), flush=True)
-    dist.destroy_process_group()
+    dist.barrier()
+    sys.stdout.flush()
+    os._exit(0)   # destroy_process_group() blocks while captured graphs hold the communicator's kernels
 
 
 if __name__ == "__main__":

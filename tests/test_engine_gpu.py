@@ -123,7 +123,7 @@ def test_two_gpu_shard_parity():
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29631", os.path.join(ROOT, "tests", "dist_worker.py")]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=1200, env=env, cwd=ROOT)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=400, env=env, cwd=ROOT)
     line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
     assert p.returncode == 0 and line, (p.stdout[-2000:], p.stderr[-4000:])
     for rank, res in enumerate(json.loads(line[-1][7:])):

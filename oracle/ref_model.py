@@ -426,6 +426,28 @@ class EdgeConv(nn.Module):
         return out, message
 
 
+class GCNConv(nn.Module):
+    """torch_geometric.nn.GCNConv (graph_module.py:136) restated from its definition, PyG 1.6/1.7 parameter layout;
+    PARITY UNPINNED for PyG's internals (not installable, version not pinned by the reference, no vector exists)."""
+
+    def __init__(self, in_size, out_size):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(in_size, out_size))
+        self.bias = nn.Parameter(torch.zeros(out_size))
+        nn.init.xavier_uniform_(self.weight)
+
+    def forward(self, x, edge_index):
+        n = x.shape[0]
+        loops = torch.arange(n, device=x.device)
+        row = torch.cat([edge_index[0], loops])
+        col = torch.cat([edge_index[1], loops])
+        deg = torch.zeros(n, dtype=x.dtype, device=x.device).index_add(0, col, torch.ones_like(col, dtype=x.dtype))
+        norm = deg.pow(-0.5)[row] * deg.pow(-0.5)[col]
+        h = x @ self.weight
+        out = torch.zeros_like(h).index_add(0, col, h[row] * norm.unsqueeze(-1))
+        return out + self.bias
+
+
 def _nn_distance_dense(pc1, pc2):  # graph_module.py:154-174
     N, M = pc1.shape[1], pc2.shape[1]
     pc_diff = pc1.unsqueeze(2).repeat(1, 1, M, 1) - pc2.unsqueeze(1).repeat(1, N, 1, 1)
@@ -467,11 +489,13 @@ class GraphModule(nn.Module):
                  graph_mode="edge_conv", return_edge=False, graph_aggr="add", return_orientation=False, num_bins=6,
                  return_distance=False):
         super().__init__()
-        assert graph_mode == "edge_conv"
+        assert graph_mode in ("edge_conv", "graph_conv")
+        self.graph_mode = graph_mode
         self.in_size, self.out_size, self.num_proposals, self.feat_size = in_size, out_size, num_proposals, feat_size
         self.num_locals, self.query_mode, self.num_bins = num_locals, query_mode, num_bins
         self.return_orientation = return_orientation
-        self.gc_layers = nn.ModuleList([EdgeConv(in_size, out_size, graph_aggr) for _ in range(num_layers)])
+        self.gc_layers = nn.ModuleList([GCNConv(in_size, out_size) if graph_mode == "graph_conv" else
+                                        EdgeConv(in_size, out_size, graph_aggr) for _ in range(num_layers)])
         if return_orientation:
             self.edge_layer = EdgeConv(in_size, out_size, graph_aggr)
             self.edge_predict = nn.Linear(out_size, num_bins + 1)
@@ -507,7 +531,10 @@ class GraphModule(nn.Module):
             batch_obj_feats = obj_feats[batch_id, batch_object_masks == 1]
             node_feat, edge_feat = batch_obj_feats, None
             for layer in self.gc_layers:
-                node_feat, edge_feat = layer(node_feat, batch_edge_index)
+                if self.graph_mode == "graph_conv":
+                    node_feat, edge_feat = layer(node_feat, batch_edge_index), None
+                else:
+                    node_feat, edge_feat = layer(node_feat, batch_edge_index)
             if self.return_orientation:
                 try:
                     num_src_objects = len(set(batch_edge_index[0].cpu().numpy()))
@@ -722,6 +749,78 @@ class CapNet(nn.Module):
             data_dict = self.graph(data_dict)
         if not self.no_caption:
             data_dict = self.caption(data_dict, use_tf, is_eval)
+        return data_dict
+
+
+class MaskProposalModule(nn.Module):
+    """models/mask_votenet.py:134-218: one proposal per scene, radius 5, nsample 512, head without objectness/heading."""
+
+    def __init__(self, num_class, num_heading_bin, num_size_cluster, mean_size_arr, num_proposal, sampling, seed_feat_dim=256):
+        super().__init__()
+        self.num_class, self.num_size_cluster, self.mean_size_arr = num_class, num_size_cluster, mean_size_arr
+        self.vote_aggregation = PointnetSAModuleVotes(npoint=num_proposal, radius=5, nsample=512,
+                                                      mlp=[seed_feat_dim, 128, 128, 128], normalize_xyz=True)
+        self.proposal = nn.Sequential(
+            nn.Conv1d(128, 128, 1, bias=False), nn.BatchNorm1d(128), nn.ReLU(),
+            nn.Conv1d(128, 128, 1, bias=False), nn.BatchNorm1d(128), nn.ReLU(),
+            nn.Conv1d(128, 3 + num_size_cluster * 4 + num_class, 1))
+
+    def forward(self, xyz, features, data_dict):
+        xyz, features, fps_inds = self.vote_aggregation(xyz, features)
+        data_dict["aggregated_vote_xyz"] = xyz
+        data_dict["aggregated_vote_features"] = features.permute(0, 2, 1).contiguous()
+        data_dict["aggregated_vote_inds"] = fps_inds
+        net = self.proposal(features).transpose(2, 1).contiguous()
+        B, K, NS = net.shape[0], net.shape[1], self.num_size_cluster
+        data_dict["center"] = xyz + net[:, :, 0:3]
+        data_dict["size_scores"] = net[:, :, 3:3 + NS]
+        data_dict["size_residuals_normalized"] = net[:, :, 3 + NS:3 + NS * 4].view(B, K, NS, 3)
+        data_dict["size_residuals"] = data_dict["size_residuals_normalized"] * torch.from_numpy(
+            self.mean_size_arr.astype(np.float32)).to(net.device).unsqueeze(0).unsqueeze(0)
+        data_dict["sem_cls_scores"] = net[:, :, 3 + NS * 4:]
+        return data_dict
+
+
+class MaskVoteNet(nn.Module):
+    """models/mask_votenet.py:221-293."""
+
+    def __init__(self, num_class, num_heading_bin, num_size_cluster, mean_size_arr, input_feature_dim=0, num_proposal=1,
+                 vote_factor=1, sampling="vote_fps"):
+        super().__init__()
+        self.backbone_net = Pointnet2Backbone(input_feature_dim=input_feature_dim)
+        self.vgen = VotingModule(vote_factor, 256)
+        self.proposal = MaskProposalModule(num_class, num_heading_bin, num_size_cluster, mean_size_arr, num_proposal, sampling)
+
+    def forward(self, data_dict):
+        data_dict = self.backbone_net(data_dict)
+        xyz, features = data_dict["fp2_xyz"], data_dict["fp2_features"]
+        data_dict["seed_inds"], data_dict["seed_xyz"], data_dict["seed_features"] = data_dict["fp2_inds"], xyz, features
+        xyz, features = self.vgen(xyz, features)
+        features = features.div(torch.norm(features, p=2, dim=1).unsqueeze(1))
+        data_dict["vote_xyz"], data_dict["vote_features"] = xyz, features
+        return self.proposal(xyz, features, data_dict)
+
+
+class PointnetEncoder(nn.Module):
+    """models/encoder_module.py:11-202, whole_scene=False branch (:140-197)."""
+
+    def __init__(self, input_feature_dim=0, num_classes=18):
+        super().__init__()
+        self.sa1 = PointnetSAModuleVotes(npoint=2048, radius=0.2, nsample=64, mlp=[input_feature_dim, 64, 64, 128], normalize_xyz=True)
+        self.sa2 = PointnetSAModuleVotes(npoint=1024, radius=0.4, nsample=32, mlp=[128, 128, 128, 256], normalize_xyz=True)
+        self.sa3 = PointnetSAModuleVotes(npoint=512, radius=0.8, nsample=16, mlp=[256, 128, 128, 256], normalize_xyz=True)
+        self.sa4 = PointnetSAModuleVotes(npoint=256, radius=1.2, nsample=16, mlp=[256, 128, 128, 256], normalize_xyz=True)
+        self.map = nn.Sequential(nn.Linear(256, 128), nn.ReLU())
+        self.classifier = nn.Linear(128, num_classes)
+
+    def forward(self, data_dict):
+        pc = data_dict["point_clouds"]
+        xyz = pc[..., :3].contiguous()
+        features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
+        for sa in (self.sa1, self.sa2, self.sa3, self.sa4):
+            xyz, features, _ = sa(xyz, features)
+        features = self.map(features.max(-1)[0])
+        data_dict["enc_features"], data_dict["enc_preds"] = features, self.classifier(features)
         return data_dict
 
 

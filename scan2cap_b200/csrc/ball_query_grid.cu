@@ -17,9 +17,12 @@
 // writes instead of by distance arithmetic.
 //
 // Exactness of the pre-filter: a hit has |dx| <= sqrt(d2) < r*(1+2^-22) per axis.  Cell coordinates are
-// floor(fl(fl(x-lo)*inv)) -- monotone in x -- with at most 2^16 cells per axis range, so the fp32 rounding of the
-// argument is < 1e-2 of a cell, far below the 1e-3*r/cs... margin built into the cell edge: a hit can never be more
-// than one cell away from its centre's cell in any axis.
+// floor(f(x)), f(x) = fl(fl(x-lo)*inv), monotone in x.  With at most kMaxCellsPerAxis = 1024 cells per axis, f <= 1024
+// and its two roundings are off by at most 2 * 1024 * 2^-24 = 1.2e-4 of a cell each, so for a hit
+//   |f(x1) - f(x2)| <= (r / cs) * (1 + 2^-22) + 2.4e-4 <= 1 / 1.001 + 2.5e-4 < 1
+// (cs >= 1.001 r; coarsening only enlarges cs): a hit can never be more than one cell away from its centre's cell in
+// any axis.  (Round 1 allowed 65 001 cells on one axis, where the rounding, 8e-3 of a cell, exceeded the 1e-3 margin:
+// elongated, line-like clouds could lose a hit -- tests/test_native_ops_gpu.py::test_ball_query_line_cloud.)
 #include <cuda.h>
 
 #include "s2c_common.cuh"
@@ -29,6 +32,7 @@ namespace s2c {
 namespace {
 
 constexpr int kMaxCells = 65536;
+constexpr int kMaxCellsPerAxis = 1024;
 constexpr int kBuildThreads = 1024;
 
 struct GridParams {   // per scene, written by the build kernel
@@ -116,7 +120,7 @@ grid_build_kernel(const float *__restrict__ xyz, int n, float radius, GridParams
         dims[a] = q < 65000.f ? (int)q + 1 : 65001;
         tot *= dims[a];
       }
-      if (tot <= kMaxCells) {
+      if (tot <= kMaxCells && max(dims[0], max(dims[1], dims[2])) <= kMaxCellsPerAxis) {
         gp.n[0] = dims[0]; gp.n[1] = dims[1]; gp.n[2] = dims[2]; gp.ncell = (int)tot;
         break;
       }

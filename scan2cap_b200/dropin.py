@@ -27,6 +27,9 @@ _MAP = {
     "models.caption_module": "scan2cap_b200.models.caption_module",
     "models.capnet": "scan2cap_b200.models.capnet",
     "models.capnet_pretrained": "scan2cap_b200.models.capnet_pretrained",
+    "models.mask_votenet": "scan2cap_b200.models.mask_votenet",
+    "models.encoder_module": "scan2cap_b200.models.encoder_module",
+    "lib.loss_helper_pretrained": "scan2cap_b200.lib.loss_helper_pretrained",
     "lib.loss_helper": "scan2cap_b200.lib.loss_helper",
     "utils.nn_distance": "scan2cap_b200.utils.nn_distance",
 }
@@ -36,7 +39,7 @@ def install(replace_loss=True):
     """Alias the mirrors into sys.modules.  Parent packages that are not importable yet (e.g. `pointnet2`,
     which the reference installs with lib/pointnet2/setup.py) are created as empty namespace modules."""
     for alias, target in _MAP.items():
-        if not replace_loss and alias in ("lib.loss_helper", "utils.nn_distance"):
+        if not replace_loss and alias in ("lib.loss_helper", "lib.loss_helper_pretrained", "utils.nn_distance"):
             continue
         mod = importlib.import_module(target)
         sys.modules[alias] = mod

@@ -15,7 +15,10 @@ adjacency, then one scipy round trip + one PyG graph per scene):
     E != num_src*num_tar or when a scene has no edge at all.
 torch_geometric is not needed: EdgeConv is restated from its definition (message = MLP([x_i, x_j - x_i]) with
 x_i = x[edge_index[1]], x_j = x[edge_index[0]], aggregated at edge_index[1]; PyG flow "source_to_target").
-graph_mode="graph_conv" (PyG GCNConv, whose arithmetic lives wholly inside torch_geometric) is out of scope.
+graph_mode="graph_conv" (torch_geometric.nn.GCNConv, graph_module.py:136): restated from its published definition
+(Kipf & Welling; PyG 1.6/1.7 layout: ``weight`` (in, out), ``bias`` (out)) -- out = D^-1/2 (A + I) D^-1/2 X W + b with
+the in-degree (incl. the self loop) of the aggregation end.  PyG is not installable here and the reference pins no
+version and no test vector: parity with PyG's internals is unpinned; the oracle carries the same restatement.
 """
 import torch
 import torch.nn as nn
@@ -68,6 +71,27 @@ class EdgeConv(nn.Module):
         return out, msg
 
 
+class GCNConv(nn.Module):
+    """x' = D^-1/2 (A + I) D^-1/2 (x W) + b, messages flowing edge_index[0] -> edge_index[1] (PyG source_to_target);
+    masked edges do not exist.  Parameters as in PyG 1.6/1.7: weight (in, out) glorot, bias (out) zeros."""
+
+    def __init__(self, in_size, out_size):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(in_size, out_size))
+        self.bias = nn.Parameter(torch.zeros(out_size))
+        nn.init.xavier_uniform_(self.weight)
+
+    def forward(self, x, edge_index, edge_mask=None):
+        row, col = edge_index[0], edge_index[1]
+        w = torch.ones_like(row, dtype=x.dtype) if edge_mask is None else edge_mask.to(x.dtype)
+        deg = torch.ones(x.shape[0], dtype=x.dtype, device=x.device).index_add(0, col, w)   # self loop + in-degree
+        dis = deg.pow(-0.5)
+        h = x @ self.weight
+        norm = dis.index_select(0, row) * w * dis.index_select(0, col)
+        out = (h * (dis * dis).unsqueeze(-1)).index_add(0, col, h.index_select(0, row) * norm.unsqueeze(-1))
+        return out + self.bias
+
+
 class GraphModule(nn.Module):
     def __init__(self, in_size, out_size, num_layers, num_proposals, feat_size, num_locals, query_mode="corner",
                  graph_mode="graph_conv", return_edge=False, graph_aggr="add", return_orientation=False,
@@ -80,19 +104,18 @@ class GraphModule(nn.Module):
         self.num_locals = num_locals
         self.query_mode = query_mode
         self.graph_mode = graph_mode
-        if graph_mode == "graph_conv":
-            raise NotImplementedError("graph_mode='graph_conv' relies on torch_geometric.nn.GCNConv; only "
-                                      "'edge_conv' (the mode of every documented Scan2Cap configuration) is built")
-        if graph_mode != "edge_conv":
+        if graph_mode not in ("graph_conv", "edge_conv"):
             raise ValueError("invalid graph mode, choices: [\"graph_conv\", \"edge_conv\"]")
         if query_mode not in ("center", "corner"):
             raise ValueError("invalid distance mode, choice: [\"center\", \"corner\"]")
-        self.gc_layers = nn.ModuleList([EdgeConv(in_size, out_size, graph_aggr) for _ in range(num_layers)])
+        self.gc_layers = nn.ModuleList([GCNConv(in_size, out_size) if graph_mode == "graph_conv" else
+                                        EdgeConv(in_size, out_size, graph_aggr) for _ in range(num_layers)])
         self.return_edge = return_edge
         self.return_orientation = return_orientation
         self.return_distance = return_distance
         self.num_bins = num_bins
         if self.return_orientation:
+            assert self.graph_mode == "edge_conv"   # graph_module.py:148
             self.edge_layer = EdgeConv(in_size, out_size, graph_aggr)
             self.edge_predict = nn.Linear(out_size, num_bins + 1)
 
@@ -125,7 +148,10 @@ class GraphModule(nn.Module):
         x = obj_feats.reshape(B * K, -1)
         node_feat, message = x, None
         for layer in self.gc_layers:
-            node_feat, message = layer(node_feat, edge_g, emask)
+            if self.graph_mode == "graph_conv":
+                node_feat, message = layer(node_feat, edge_g, emask), None
+            else:
+                node_feat, message = layer(node_feat, edge_g, emask)
 
         edge_feats = obj_feats.new_zeros(B, K, L, self.out_size)
         edge_indices = obj_feats.new_zeros(B, 2, K * L)

@@ -273,3 +273,33 @@ def test_graph_irregular_rows_follow_reference_quirks():
     for k in ("bbox_feature", "edge_feature", "edge_orientations", "edge_distances"):
         assert _rel(o[k][1:], r[k][1:]) < RTOL, k
     assert float(o["edge_orientations"][2].abs().max()) == 0.0
+
+
+def test_graph_conv_mode_matches_restatement():
+    """graph_mode="graph_conv" (GCNConv, graph_module.py:136): batched masked product implementation vs the oracle's
+    per-scene compacted restatement (PyG internals themselves: parity unpinned)."""
+    from oracle import ref_model as R
+    from scan2cap_b200.models.graph_module import GraphModule
+    torch.manual_seed(0)
+    args = (128, 128, 2, 256, 128, 10, "center", "graph_conv", False, "add", False, 6, False)
+    ours, ref = GraphModule(*args).to(DEV), R.GraphModule(*args).to(DEV)
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    B, K = 2, 256
+    g = torch.Generator().manual_seed(1)
+    centers = torch.rand(B, K, 3, generator=g, dtype=torch.float64) * 6
+    sizes = torch.rand(B, K, 3, generator=g, dtype=torch.float64) * 0.5 + 0.1
+    corners = torch.from_numpy(synthetic.box_corners(centers.numpy(), sizes.numpy())).to(DEV)
+    mask = (torch.rand(B, K, generator=g) > 0.4).long()
+    feats = torch.randn(B, K, 128, generator=g)
+    fo = feats.clone().to(DEV).requires_grad_(True)
+    fr = feats.clone().to(DEV).requires_grad_(True)
+    o = ours({"bbox_feature": fo, "bbox_mask": mask.to(DEV), "bbox_corner": corners})
+    r = ref({"bbox_feature": fr, "bbox_mask": mask.to(DEV), "bbox_corner": corners})
+    assert torch.equal(o["adjacent_mat"], r["adjacent_mat"])
+    assert _rel(o["bbox_feature"], r["bbox_feature"]) < 1e-5
+    gout = torch.randn(B, K, 128, generator=g).to(DEV)
+    (o["bbox_feature"] * gout).sum().backward()
+    (r["bbox_feature"] * gout).sum().backward()
+    assert _rel(fo.grad, fr.grad) < 1e-5
+    for (n, po), (_, pr) in zip(ours.named_parameters(), ref.named_parameters()):
+        assert _rel(po.grad, pr.grad) < 1e-5, n

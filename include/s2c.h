@@ -220,6 +220,25 @@ S2C_API int s2c_mlp_layer_bwd_weight(const float *dY, long long lddy, const floa
  *   only the points of the 27 surrounding cells and recovers "the first nsample indices in index order" from a
  *   per-warp bitmap.  ~200 distance tests per centre instead of n.  grouped may be NULL (ball query only), idx may be
  *   NULL (grouped only).  workspace: s2c_ball_query_grid_workspace_bytes(B, n) bytes of device memory. */
+/* detection_loss -- the VoteNet detection loss of lib/loss_helper.py (compute_vote_loss :24-69, compute_objectness_loss
+ *   :71-111, compute_box_and_sem_cls_loss :113-187 on utils/nn_distance.py:32-59) forward AND backward in one launch:
+ *   det_loss = vote + 0.5*objectness + box + 0.1*sem_cls, box = center + 0.1*heading_cls + heading_reg + 0.1*size_cls
+ *   + size_reg (:409, :472-476; the caller applies the x10).  net (B,K,W) are the proposal head's outputs per proposal,
+ *   W = 2 + 3 + 2*NH + 4*NS + NC in the reference's channel order (proposal_module.py:105-144); center = agg_xyz +
+ *   net[...,2:5] is passed (and its gradient returned) separately.  stats[16] = {det_loss, vote, objectness, center,
+ *   heading_cls, heading_reg, size_cls, size_reg, sem_cls, box, obj_acc, pos_ratio, neg_ratio, 0, 0, 0}.  Label outputs
+ *   (objectness_label / object_assignment int64, objectness_mask f32; (B,K)) use the reference's fp32 operation order.
+ *   scratch: (B*K + B*G) ints. */
+S2C_API int s2c_detection_loss(int B, int S, int N, int K, int G, int NH, int NS, int NC, const float *vote_xyz,
+                               const float *seed_xyz, const int *seed_inds, long long seed_ld, const float *vote_label,
+                               const long long *vote_label_mask, const float *agg_xyz, const float *net,
+                               const float *center, const float *center_label, const long long *heading_class_label,
+                               const float *heading_residual_label, const long long *size_class_label,
+                               const float *size_residual_label, const long long *sem_cls_label,
+                               const float *box_label_mask, const float *mean_size, float *stats,
+                               long long *objectness_label, float *objectness_mask, long long *object_assignment,
+                               float *d_vote_xyz, float *d_net, float *d_center, int *scratch, void *stream);
+
 /* Tuning knob of the TMA gather epilogue of s2c_query_and_group_grid (ring geometry per warp): 0 = default
  * (8-row tiles x 3 per mover, 10 mover + 10 query warps), 1 = 8x4x8, 2 = 8x4x9, 3 = 8x5x7, 4 = 8x3x12, 5 = 16x3x6; -1 = disable the TMA path (LDG/STG epilogue; used by the
  * tests to cross-check the two epilogues bit for bit).  Process-wide; not part of the reference surface. */

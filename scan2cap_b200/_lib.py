@@ -42,6 +42,7 @@ SIGNATURES = {
     "s2c_gemm_tn": [P, c_ll, P, c_ll, c_int, c_int, c_int, P, c_ll, P, P],
     "s2c_caption_decode_fwd": [P, P],
     "s2c_caption_decode_bwd": [P, P],
+    "s2c_detection_loss": [c_int] * 8 + [P, P, P, c_ll] + [P] * 22,
     "s2c_knn_adjacency": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.c_double, P, P, P],
 }
 

@@ -10,6 +10,7 @@ import torch
 import torch.nn.functional as F
 
 from ..utils.nn_distance import nn_distance, huber_loss
+from . import fused_loss
 from .config import CONF
 
 FAR_THRESHOLD = 0.6
@@ -55,7 +56,8 @@ def compute_objectness_loss(data_dict):
     objectness_mask = (near | (euclidean_dist1 > FAR_THRESHOLD)).float()
     objectness_scores = data_dict["objectness_scores"]
     w = _const("obj_w", lambda: torch.tensor(OBJECTNESS_CLS_WEIGHTS, dtype=torch.float32), objectness_scores.device)
-    objectness_loss = F.cross_entropy(objectness_scores.transpose(2, 1), objectness_label, weight=w, reduction="none")
+    objectness_loss = F.cross_entropy(objectness_scores.transpose(2, 1), objectness_label,
+                                      weight=w.to(objectness_scores.dtype), reduction="none")
     objectness_loss = torch.sum(objectness_loss * objectness_mask) / (torch.sum(objectness_mask) + 1e-6)
     return objectness_loss, objectness_label, objectness_mask, ind1
 
@@ -95,7 +97,7 @@ def compute_box_and_sem_cls_loss(data_dict, config):
     predicted_size_residual_normalized = torch.sum(data_dict["size_residuals_normalized"] * size_label_one_hot_tiled, 2)
     mean_size_arr_expanded = _const(("mean_size", np.asarray(mean_size_arr, np.float32).tobytes()),
                                     lambda: torch.from_numpy(np.asarray(mean_size_arr, np.float32)),
-                                    pred_center.device).unsqueeze(0).unsqueeze(0)
+                                    pred_center.device).to(pred_center.dtype).unsqueeze(0).unsqueeze(0)
     mean_size_label = torch.sum(size_label_one_hot_tiled * mean_size_arr_expanded, 2)
     size_residual_label_normalized = size_residual_label / mean_size_label
     size_residual_normalized_loss = torch.mean(
@@ -184,8 +186,27 @@ def compute_node_distance_loss(data_dict):
     return (((edge_preds - labels) ** 2) * k).sum() / k.sum()  # nn.MSELoss over the kept edges
 
 
+def _detection_terms_fused(data_dict, config, detection):
+    """The detection part of get_scene_cap_loss on the fused kernel (csrc/loss.cu): one launch for all terms, labels
+    and gradients.  Returns 10 * (vote + 0.5 objectness + box + 0.1 sem_cls) or None when detection is off."""
+    det, terms, objectness_label, objectness_mask, object_assignment = fused_loss.detection_loss(data_dict, config)
+    data_dict["objectness_label"] = objectness_label
+    data_dict["objectness_mask"] = objectness_mask
+    data_dict["object_assignment"] = object_assignment
+    data_dict["pos_ratio"], data_dict["neg_ratio"], data_dict["obj_acc"] = terms["pos_ratio"], terms["neg_ratio"], terms["obj_acc"]
+    zero = torch.zeros((), device=det.device)
+    for n in ("vote_loss", "objectness_loss", "center_loss", "heading_cls_loss", "heading_reg_loss", "size_cls_loss",
+              "size_reg_loss", "sem_cls_loss", "box_loss"):
+        data_dict[n] = terms[n] if detection else zero
+    return det * 10 if detection else None
+
+
 def get_scene_cap_loss(data_dict, device, config, weights, detection=True, caption=True, orientation=False,
                        distance=False, num_bins=CONF.TRAIN.NUM_BINS):
+    if fused_loss.available(data_dict):
+        det10 = _detection_terms_fused(data_dict, config, detection)
+        return _finish_scene_cap_loss(data_dict, device, config, weights, det10, detection, caption, orientation,
+                                      distance, num_bins)
     vote_loss = compute_vote_loss(data_dict)
     objectness_loss, objectness_label, objectness_mask, object_assignment = compute_objectness_loss(data_dict)
     total_num_proposal = objectness_label.shape[0] * objectness_label.shape[1]
@@ -211,6 +232,17 @@ def get_scene_cap_loss(data_dict, device, config, weights, detection=True, capti
     for n, v in zip(names, vals):
         data_dict[n] = v if detection else zero
 
+    det10 = None
+    if detection:
+        det10 = (data_dict["vote_loss"] + 0.5 * data_dict["objectness_loss"] + data_dict["box_loss"]
+                 + 0.1 * data_dict["sem_cls_loss"]) * 10
+    return _finish_scene_cap_loss(data_dict, device, config, weights, det10, detection, caption, orientation, distance,
+                                  num_bins)
+
+
+def _finish_scene_cap_loss(data_dict, device, config, weights, det10, detection, caption, orientation, distance, num_bins):
+    """Caption / orientation / distance terms and the total (lib/loss_helper.py:436-491); det10 = 10 x detection loss."""
+    zero = torch.zeros((), device=device)
     if caption:
         data_dict["cap_loss"], data_dict["cap_acc"] = compute_cap_loss(data_dict, config, weights)
     else:
@@ -222,9 +254,7 @@ def get_scene_cap_loss(data_dict, device, config, weights, detection=True, capti
     data_dict["dist_loss"] = compute_node_distance_loss(data_dict) if distance else zero
 
     if detection:
-        loss = data_dict["vote_loss"] + 0.5 * data_dict["objectness_loss"] + data_dict["box_loss"] \
-            + 0.1 * data_dict["sem_cls_loss"]
-        loss = loss * 10
+        loss = det10
         if caption:
             loss = loss + data_dict["cap_loss"]
     else:

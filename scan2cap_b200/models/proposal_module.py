@@ -77,6 +77,7 @@ class ProposalModule(nn.Module):
             [batch_size, num_proposal, NS, 3])
         sem_cls_scores = net_transposed[:, :, 5 + NH * 2 + NS * 4:]
 
+        data_dict["_head_outputs"] = net_transposed   # (B,K,97) packed head outputs: input of the fused loss kernel
         data_dict["objectness_scores"] = objectness_scores
         data_dict["center"] = center
         data_dict["heading_scores"] = heading_scores

@@ -162,7 +162,8 @@ class DecisionTracker(object):
             keep = (~self.head_risk[head]).float()    # (B, rows)
             self.flips[head] = (int(self.head_risk[head].sum()), keep.numel())
             for d in (o, r):
-                for k in keys:
+                # (the product's fused loss kernel reads the packed head outputs instead of their slices)
+                for k in keys + (("_head_outputs",) if head == "proposal.proposal" and "_head_outputs" in d else ()):
                     t = d[k]
                     if not t.requires_grad:
                         continue

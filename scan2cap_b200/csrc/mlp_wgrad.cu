@@ -4,10 +4,13 @@
 //
 // This is a GEMM whose reduction dimension is the ROW index (R ~ 10^5..10^6) and whose output is tiny, the shape the
 // library handles worst (the reference's cuDNN wgrad / cuBLAS "nt" split-K kernels take ~6 ms per step here).
-// Per 32-row chunk both operands are staged TRANSPOSED into the K-major SWIZZLE_128B layout of the forward kernel
-// (operand row = channel, operand K = the 32 data rows = one 128-byte swizzle row): loads stay coalesced along the
-// channels, and the transposing 4-byte shared-memory stores are made bank-conflict-free by rotating which of its
-// four channels a thread stores at each step.  dY is optionally formed on the fly (BatchNorm-backward affine
+// Both operands are consumed MN-MAJOR: in this GEMM the reduction index K is the data row and the operand "rows" are
+// channels, which is exactly how dY and X lie in memory (channels contiguous).  Per 32-row chunk a thread loads 16
+// bytes (4 channels of one data row) and stores them with ONE 16-byte shared-memory store per hi / lo half into the
+// MN-major SWIZZLE_128B_BASE32B layout (32 channels = one 128-byte line, 4 data rows = one 512-byte swizzle atom); the
+// tensor core transposes through the descriptor (a_major = b_major = MN).  (Round 1 staged the operands transposed into the
+// K-major layout with eight rotated 4-byte stores per 16 loaded bytes: ncu showed the kernel instruction-bound on
+// those stores and their address arithmetic, 22-30 % of its HBM roofline.)  dY is optionally formed on the fly (BatchNorm-backward affine
 // a*g + b*y + c), X' by the BatchNorm + ReLU prologue; fp32 operands are split hi/lo (3xTF32).  Each persistent CTA
 // accumulates its share of the rows in TMEM and adds its [C_l x C_prev] partial to the result with fp32 atomics.
 #include <math.h>
@@ -84,61 +87,32 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// K-major SWIZZLE_128B descriptor / tf32 instruction descriptor (same as the forward kernel, mlp.cu)
+// MN-major shared-memory descriptor.  For 32-bit (tf32) operands the only MN-major layout the tensor core takes is
+// SWIZZLE_128B_BASE32B (layout type 1): 32 channels = one 128-byte line, FOUR data rows 128 bytes apart form a 512-byte
+// swizzle atom in which the 32-byte groups of a line are XOR-permuted by (row & 3); the next 4 data rows lie SBO = 512
+// bytes further, the next 32 channels LBO bytes further (one 4 KB block).
+constexpr uint32_t kLBO = 32 * 32 * 4;  // = BLK
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(kLBO >> 4) << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
 }
+// tf32 x tf32 -> f32 instruction descriptor, A and B both MN-major (bits 15 / 16)
 __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void split_tf32(float v, float &hi, float &lo) {
   hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
   lo = v - hi;
 }
-// byte offset of element (operand row m, k) in a [rows x 32 fp32] K-major SWIZZLE_128B block
-__device__ __forceinline__ uint32_t swz_elem(int m, int k) {
-  return (uint32_t)((m >> 3) * 1024 + (m & 7) * 128 + ((((k >> 2) ^ (m & 7)) & 7) << 4) + (k & 3) * 4);
+// 16-byte store of a thread's 4 consecutive channels (seg = which 4-channel group of the 32-channel block) of data row
+// k, hi / lo split: byte offset  k * 128 + (((seg / 2) ^ (k % 4)) * 32) + (seg % 2) * 16   (SWIZZLE_128B_BASE32B)
+__device__ __forceinline__ uint32_t store_offset(int k, int seg) {
+  return (uint32_t)(k * 128 + ((((seg >> 1) ^ k) & 3) << 5) + ((seg & 1) << 4));
 }
-// transposing store of a thread's 4 consecutive channels (m0..m0+3) of data row k, hi/lo split.  At step e the thread
-// stores channel (e + seg/2) mod 4, which spreads a warp's 32 stores over all 32 banks.
-__device__ __forceinline__ void store_split_t(unsigned char *hi_base, unsigned char *lo_base, int m0, int k, int seg, float4 v) {
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const int ee = (e + (seg >> 1)) & 3;
-    const float val = ee == 0 ? v.x : (ee == 1 ? v.y : (ee == 2 ? v.z : v.w));
-    float h, l;
-    split_tf32(val, h, l);
-    const uint32_t off = swz_elem(m0 + ee, k);
-    *reinterpret_cast<float *>(hi_base + off) = h;
-    *reinterpret_cast<float *>(lo_base + off) = l;
-  }
-}
-// The same store with the thread-constant part of the address hoisted: for a thread (data row k, segment seg) the
-// swizzled offset of channel m0 + ee is  base[e] + (m0 / 32) * 4096  (32 channels = 4 swizzle atoms of 1 KB).
-struct StoreT {
-  uint32_t base[4];  // byte offset of step e inside a 32-channel block
-  int ee[4];         // which of the thread's four channels step e stores
-};
-__device__ __forceinline__ StoreT make_store_t(int k, int seg) {
-  StoreT st;
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    st.ee[e] = (e + (seg >> 1)) & 3;
-    st.base[e] = swz_elem(seg * 4 + st.ee[e], k);
-  }
-  return st;
-}
-__device__ __forceinline__ void store_split_t(unsigned char *hi_base, unsigned char *lo_base, const StoreT &st, int mb, float4 v) {
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const int ee = st.ee[e];
-    const float val = ee == 0 ? v.x : (ee == 1 ? v.y : (ee == 2 ? v.z : v.w));
-    float h, l;
-    split_tf32(val, h, l);
-    const uint32_t off = st.base[e] + (uint32_t)mb * 4096u;
-    *reinterpret_cast<float *>(hi_base + off) = h;
-    *reinterpret_cast<float *>(lo_base + off) = l;
-  }
+__device__ __forceinline__ void store_split(unsigned char *hi_base, unsigned char *lo_base, uint32_t off, float4 v) {
+  float4 h, l;
+  split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+  *reinterpret_cast<float4 *>(hi_base + off) = h;
+  *reinterpret_cast<float4 *>(lo_base + off) = l;
 }
 __device__ __forceinline__ float4 ld4_guard(const float *base, long long ld, long long row, long long R, int col, int ncols) {
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -191,9 +165,9 @@ mlp_wgrad_kernel(WgradArgs g) {
   const long long my_chunks = (num_chunks > (long long)blockIdx.x) ? (num_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (warp < kLoadWarps) {
-    // ===================== load + transform: global -> prologue -> hi/lo split -> transposed K-major operand blocks
+    // ===================== load + transform: global -> prologue -> hi/lo split -> MN-major operand blocks
     const int r = tid >> 3, seg = tid & 7;  // 256 threads = 32 rows x 8 sixteen-byte segments
-    const StoreT st = make_store_t(r, seg);
+    const uint32_t st_off = store_offset(r, seg);
     const int CB = (g.C + 31) / 32;         // real channel blocks of A
     const bool affine = g.a != nullptr;
     const bool xpro = g.xs != nullptr;
@@ -247,7 +221,7 @@ mlp_wgrad_kernel(WgradArgs g) {
             v.z = fmaf(ca[2], v.z, fmaf(cb[2], y.z, cc[2])); v.w = fmaf(ca[3], v.w, fmaf(cb[3], y.w, cc[3]));
             if (row >= g.R) v = make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          store_split_t(a_hi, a_lo, st, mb, v);
+          store_split(a_hi, a_lo, st_off + (uint32_t)mb * BLK, v);
         }
       }
 #pragma unroll
@@ -266,7 +240,7 @@ mlp_wgrad_kernel(WgradArgs g) {
             v.z = fmaxf(fmaf(v.z, xs[2], xh[2]), 0.f); v.w = fmaxf(fmaf(v.w, xs[3], xh[3]), 0.f);
             if (row >= g.R) v = make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          store_split_t(b_hi, b_lo, st, nb, v);
+          store_split(b_hi, b_lo, st_off + (uint32_t)nb * BLK, v);
         }
       }
       fence_async_proxy();
@@ -285,14 +259,14 @@ mlp_wgrad_kernel(WgradArgs g) {
         for (int mh = 0; mh < g.MH; ++mh) {
           const uint32_t d0 = tmem_base + (uint32_t)(mh * NB * 32);
 #pragma unroll
-          for (int ks = 0; ks < CK / 8; ++ks) {  // UMMA K = 8 data rows = 32 bytes inside the 128-byte swizzle row
+          for (int ks = 0; ks < CK / 8; ++ks) {  // UMMA K = 8 data rows = two 512-byte swizzle atoms of every 32-channel block
             const uint32_t acc = (i | ks) ? 1u : 0u;
-            const uint32_t ao = (uint32_t)mh * 128 * 128 + ks * 32, bo = ks * 32;
+            const uint32_t ao = (uint32_t)mh * 4 * BLK + ks * 1024, bo = ks * 1024;
             umma_tf32(d0, make_desc(ah + ao), make_desc(bh + bo), idesc0, acc);
             umma_tf32(d0, make_desc(ah + ao), make_desc(bl + bo), idesc0, 1u);
             umma_tf32(d0, make_desc(al + ao), make_desc(bh + bo), idesc0, 1u);
             if (n1) {
-              const uint32_t bo1 = 256 * 128 + ks * 32;  // operand rows 256.. of B
+              const uint32_t bo1 = 8 * BLK + ks * 1024;  // channels 256.. of B
               umma_tf32(d0 + n0, make_desc(ah + ao), make_desc(bh + bo1), idesc1, acc);
               umma_tf32(d0 + n0, make_desc(ah + ao), make_desc(bl + bo1), idesc1, 1u);
               umma_tf32(d0 + n0, make_desc(al + ao), make_desc(bh + bo1), idesc1, 1u);

@@ -1,22 +1,21 @@
-"""One eager training step bracketed by cudaProfilerStart/Stop, for ncu --profile-from-start off."""
+"""One eager training step bracketed by cudaProfilerStart/Stop, for ncu --profile-from-start off.
+usage: ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv python tools/ncu_step.py [c3|c4]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 import torch
 import bench
 cfg = sys.argv[1] if len(sys.argv) > 1 else "c3"
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 dev = torch.device("cuda:0")
-host, num_words, C = bench.build_inputs(cfg, 42, 0)
-model, DC, loss_fn = bench.build_model("ours", C, dev)
-from scan2cap_b200.engine import TrainStep
-eng = TrainStep(model, DC, use_cuda_graph=False, **bench.LOSS_FLAGS)
-data = bench.to_device(host, dev, num_words)
+torch.cuda.set_device(dev)
+o = bench.Ours(cfg, dev, 0, use_graph=False)
+data = o.resident()
 for _ in range(2):
-    eng.run_eager(dict(data))
+    o.engine.run_eager(dict(data))
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
-eng.run_eager(dict(data))
+o.engine.run_eager(dict(data))
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()

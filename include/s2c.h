@@ -239,6 +239,17 @@ S2C_API int s2c_detection_loss(int B, int S, int N, int K, int G, int NH, int NS
                                long long *objectness_label, float *objectness_mask, long long *object_assignment,
                                float *d_vote_xyz, float *d_net, float *d_center, int *scratch, void *stream);
 
+/* Post-processing of benchmark/predict.py:176-190 (lib/ap_helper.py:40-178 parse_predictions) on the device.
+ * points_in_boxes_count: count[b,k] = number of points of scene b inside the axis-aligned box (min xyz, max xyz; f64)
+ *   -- replaces extract_pc_in_box3d's scipy Delaunay hull per box (data/scannet/model_util_scannet.py:13-22; ScanNet
+ *   boxes have heading 0, :130-134).  xyz_ld = floats between consecutive points (3 for (B,N,3), 3+C for point_clouds).
+ * nms3d: greedy 3-D NMS of utils/nms.py (nms_3d_faster :57-107; same_class_only = nms_3d_faster_samecls :110-150),
+ *   float64, only boxes with valid != 0 take part; keep[b,k] = 1 for the picked boxes. */
+S2C_API int s2c_points_in_boxes_count(const float *xyz, long long xyz_ld, int B, int N, const double *boxes, int K,
+                                      int *count, void *stream);
+S2C_API int s2c_nms3d(const double *boxes, const double *score, const long long *cls, const int *valid, int B, int K,
+                      double iou_threshold, int old_type, int same_class_only, int *keep, void *stream);
+
 /* Tuning knob of the TMA gather epilogue of s2c_query_and_group_grid (ring geometry per warp): 0 = default
  * (8-row tiles x 3 per mover, 10 mover + 10 query warps), 1 = 8x4x8, 2 = 8x4x9, 3 = 8x5x7, 4 = 8x3x12, 5 = 16x3x6; -1 = disable the TMA path (LDG/STG epilogue; used by the
  * tests to cross-check the two epilogues bit for bit).  Process-wide; not part of the reference surface. */

@@ -43,6 +43,8 @@ SIGNATURES = {
     "s2c_caption_decode_fwd": [P, P],
     "s2c_caption_decode_bwd": [P, P],
     "s2c_detection_loss": [c_int] * 8 + [P, P, P, c_ll] + [P] * 22,
+    "s2c_points_in_boxes_count": [P, c_ll, c_int, c_int, P, c_int, P, P],
+    "s2c_nms3d": [P, P, P, P, c_int, c_int, ctypes.c_double, c_int, c_int, P, P],
     "s2c_knn_adjacency": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.c_double, P, P, P],
 }
 

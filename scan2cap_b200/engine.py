@@ -255,3 +255,56 @@ class TrainStep(object):
             g2.replay()
         self.last = out
         return out["loss"]
+
+
+class EvalStep(object):
+    """Inference forward (benchmark/predict.py:170-172: model(data_dict, use_tf=False, is_eval=True) -- detection, graph
+    and the greedy 29-step decode of all 256 proposals) as ONE CUDA-graph replay per input signature.
+
+    The reference decodes with a per-token host loop (.item() + dict lookup + H2D copy per word per proposal,
+    caption_module.py:553-566); the product's decode is batched and sync-free, so the whole forward is capturable.
+    Outputs live in graph-owned memory and stay valid until the next run() of the same signature."""
+
+    def __init__(self, model, use_cuda_graph=True, use_tf=False):
+        self.model = model
+        self.device = next(model.parameters()).device
+        self.use_graph = use_cuda_graph and self.device.type == "cuda"
+        self.use_tf = use_tf
+        self._graphs = {}
+
+    def _forward(self, data):
+        with torch.no_grad():
+            return self.model(data, self.use_tf, True)
+
+    def run(self, data_dict):
+        self.model.eval()
+        if not self.use_graph:
+            return self._forward({k: (v.to(self.device, non_blocking=True) if isinstance(v, torch.Tensor) else v)
+                                  for k, v in data_dict.items()})
+        sig = TrainStep._signature(data_dict)
+        if sig not in self._graphs:
+            static = {k: (torch.empty(v.shape, dtype=v.dtype, device=self.device) if isinstance(v, torch.Tensor) else v)
+                      for k, v in data_dict.items()}
+            pc = data_dict.get("point_clouds")
+            if isinstance(pc, torch.Tensor) and pc.dim() == 3 and pc.shape[-1] > 3:
+                static["point_clouds"] = padded_point_clouds_like(pc.shape, pc.dtype, self.device)
+            for k, v in data_dict.items():
+                if isinstance(v, torch.Tensor):
+                    static[k].copy_(v, non_blocking=True)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._forward(dict(static))
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._forward(dict(static))
+            self._graphs[sig] = (static, g, out)
+        static, g, out = self._graphs[sig]
+        for k, v in data_dict.items():
+            if isinstance(v, torch.Tensor):
+                static[k].copy_(v, non_blocking=True)
+        g.replay()
+        return out

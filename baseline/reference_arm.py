@@ -69,6 +69,7 @@ class GpuReference(object):
         self.loss_fn = get_scene_cap_loss
         self.device = device
         vocab, emb, _ = self.syn.make_vocabulary(vocab_size)
+        self.vocabulary = vocab
         torch.manual_seed(seed)
         self.model = CapNet(self.DC.num_class, vocab, emb, self.DC.num_heading_bin, self.DC.num_size_cluster,
                             self.DC.mean_size_arr, input_feature_dim=input_feature_dim, **MODEL_CFG).to(device)
@@ -89,6 +90,47 @@ class GpuReference(object):
         data_dict["loss"].backward()
         self.opt.step()
         return data_dict["loss"]
+
+
+    def predict_batch(self, data_dict, vocabulary):
+        """benchmark/predict.py:170-227 for one batch: eval forward with greedy decoding of every proposal, detection
+        loss labels, parse_predictions (host-side NMS), decode_caption, the per-scene output lists."""
+        from lib.ap_helper import parse_predictions
+        post = {"remove_empty_box": True, "use_3d_nms": True, "nms_iou": 0.25, "use_old_type_nms": False, "cls_nms": True,
+                "per_class_proposal": True, "conf_thresh": 0.05, "dataset_config": self.DC}
+        self.model.eval()
+        for key in data_dict:
+            data_dict[key] = data_dict[key].to(self.device)
+        with torch.no_grad():
+            data_dict = self.model(data_dict, False, True)
+            data_dict = self.loss_fn(data_dict, self.device, self.DC, weights=None, detection=True, caption=False)
+        pred_captions = data_dict["lang_cap"].argmax(-1)
+        pred_boxes = data_dict["bbox_corner"]
+        parse_predictions(data_dict, post)
+        nms_masks = torch.FloatTensor(data_dict["pred_mask"]).type_as(pred_boxes).long() * data_dict["bbox_mask"]
+        pred_sem_prob = torch.softmax(data_dict["sem_cls_scores"], dim=-1)
+        pred_obj_prob = torch.softmax(data_dict["objectness_scores"], dim=-1)
+        idx2word = vocabulary["idx2word"]
+        outputs = {}
+        for batch_id in range(pred_captions.shape[0]):
+            scene_outputs = []
+            for object_id in range(pred_captions.shape[1]):
+                if nms_masks[batch_id, object_id] == 1:
+                    decoded = ["sos"]
+                    for token_idx in pred_captions[batch_id, object_id]:
+                        token = idx2word[str(token_idx.item())]
+                        decoded.append(token)
+                        if token == "eos":
+                            break
+                    if "eos" not in decoded:
+                        decoded.append("eos")
+                    scene_outputs.append({"caption": " ".join(decoded),
+                                          "box": pred_boxes[batch_id, object_id].cpu().detach().numpy().tolist(),
+                                          "sem_prob": pred_sem_prob[batch_id, object_id].cpu().detach().numpy().tolist(),
+                                          "obj_prob": pred_obj_prob[batch_id, object_id].cpu().detach().numpy().tolist()})
+            outputs[batch_id] = scene_outputs
+        self.model.train()
+        return outputs
 
 
 class CpuPretrainedReference(object):

@@ -317,6 +317,30 @@ def run_ours(args, emit, rank, world, local_rank):
     trace("process group up")
     main = Ours(args.config, device, rank, use_graph=not args.no_graph)
     trace("model built")
+    predict = None
+    if not args.no_predict and rank == 0:
+        # benchmark/predict.py path: eval forward with greedy decoding of all 256 proposals, device-side
+        # NMS, per-scene output lists; wall clock per batch including the device->host transfer and host assembly
+        from scan2cap_b200.lib.predict import CaptionPredictor
+        vocab = main.model.caption.vocabulary
+        pred = CaptionPredictor(main.model, main.engine.DC, vocab)
+        batch = {k: v for k, v in main.resident().items() if isinstance(v, torch.Tensor)}
+        for _ in range(2):
+            pred.predict_batch(dict(batch))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            outp = pred.predict_batch(dict(batch))
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        predict = {"value": main.B / dt, "unit": "scenes/s", "ms_per_batch": 1e3 * dt, "batch": main.B,
+                   "captions_per_batch": int(sum(len(v) for v in outp.values())),
+                   "what": "benchmark/predict.py:170-227 for one batch of %d scenes: eval forward (graph replay) + 256 x 29 "
+                           "greedy decode + device NMS + D2H + per-scene caption lists" % main.B}
+        main.model.train()
+        trace("predict done (freshly initialised weights: before any training step)")
+
     main.timed(timer, args.warmup, False)
     trace("warm-up done (graph captured)")
     sampler = ClockSampler(local_rank)
@@ -392,6 +416,8 @@ def run_ours(args, emit, rank, world, local_rank):
         line["config4"] = second
         if rc132:
             line["roofline_c132"] = rc132
+    if predict is not None:
+        line["predict"] = predict
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline()
     emit(line)
@@ -436,6 +462,19 @@ def run_reference(args, emit, rank, world, local_rank):
             host["ref_box_corner_label"] = probe["bbox_corner"][:, 3].detach().cpu().pin_memory()
         del probe
         resident = {k: v.to(device) for k, v in host.items()}
+        predict = None
+        if cfg_name == args.config and not args.no_predict and rank == 0:
+            # the stock predict loop on a BOUNDED sample (2 scenes: its per-token host loop takes seconds per batch)
+            nb = min(2, B)
+            small = {k: v[:nb].clone() for k, v in resident.items()}
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            outp = ref.predict_batch(dict(small), ref.vocabulary)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            predict = {"value": nb / dt, "unit": "scenes/s", "ms_per_batch": 1e3 * dt, "batch": nb,
+                       "captions_per_batch": int(sum(len(v) for v in outp.values())),
+                       "what": "benchmark/predict.py:170-227 for one batch of %d scenes (bounded sample), stock code" % nb}
         timer.run(W, lambda i: ref.step(dict(resident)))
         sampler = ClockSampler(local_rank)
         if rank == 0:
@@ -450,7 +489,7 @@ def run_reference(args, emit, rank, world, local_rank):
         ms_e2e = timer.run(K, body)
         h2d = int(sum(v.numel() * v.element_size() for v in host.values()))
         return dict(B=B, N=N, F=F, ms=ms, ms_e2e=ms_e2e, clocks=clocks, h2d=h2d, last=last[0],
-                    num_words=int(d["lang_len"].max()))
+                    num_words=int(d["lang_len"].max()), predict=predict)
 
     m = measure(args.config, args.steps, args.warmup)
     second = None
@@ -488,6 +527,8 @@ def run_reference(args, emit, rank, world, local_rank):
     }
     if second is not None:
         line["config4"] = second
+    if m.get("predict") is not None:
+        line["predict"] = m["predict"]
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline()
     emit(line)
@@ -503,6 +544,7 @@ def main():
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config4", action="store_true", help="skip the secondary BASELINE configs[3] measurement")
+    ap.add_argument("--no-predict", action="store_true", help="skip the benchmark/predict.py-shaped measurement")
     ap.add_argument("--no-graph", action="store_true", help="ours: issue the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--ref-device", default="auto", choices=["auto", "cuda", "cpu"])
     args = ap.parse_args()

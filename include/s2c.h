@@ -344,6 +344,32 @@ S2C_API int s2c_mlp_layer_bwd_input(const float *G, long long ldg, const float *
  *   Conv1d layer (ATen's sum(0) under autograd).  out is zero-filled here (fp32 atomics over row chunks). */
 S2C_API int s2c_col_sum(const float *A, long long lda, long long R, int M, float *out, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * edgeconv_fwd / edgeconv_bwd -- one EdgeConv layer of the relational graph (models/graph_module.py:22-115:
+ *   EdgeConv.message :102-109 = Linear(2*Cin, Cout) -> ReLU -> Linear(Cout, Cout) on [x_i, x_j - x_i];
+ *   MessagePassing.propagate :44-100 with aggr = "add") over ONE batched graph.  Replaces, per layer, PyG's
+ *   index_select x2 + cat + two cuBLAS GEMMs + scatter-add and their autograd backward.
+ *     x          (Nn, Cin) fp32 node features; row / col (E) int64 = edge_index[0] / edge_index[1]
+ *                (x_j = x[row[e]], x_i = x[col[e]], the message is aggregated at col[e])
+ *     edge_mask  (E) bytes or NULL: 0 = the slot is not an edge (message 0, no gradient)
+ *     W1 (Cout, 2*Cin), b1 (Cout), W2 (Cout, Cout), b2 (Cout)  = map_edge.0 / map_edge.2 of the reference
+ *     z (E, 2*Cin), Y1 (E, Cout)   out, kept for backward: the gathered edge input and the pre-ReLU hidden layer
+ *     msg (E, Cout)  out: the masked messages (what propagate returns as `message`)
+ *     agg (Nn, Cout) out or NULL: sum of the messages at col[e] (zero-filled here)
+ *   Cout in {64,128,256}; 2*Cin a multiple of 64, <= 512.  workspace: s2c_edgeconv_workspace_bytes(E, Cin, Cout,
+ *   backward) bytes, 256-byte aligned.  GEMMs on the tcgen05 kernels (3xTF32, fp32 accumulate).
+ *   bwd: dagg (Nn, Cout) / dmsg (E, Cout) = gradients of the two outputs (either may be NULL);
+ *        dx (Nn, Cin) or NULL, dW1, db1, dW2, db2 are overwritten. */
+S2C_API long long s2c_edgeconv_workspace_bytes(long long E, int Cin, int Cout, int backward);
+S2C_API int s2c_edgeconv_fwd(const float *x, long long Nn, int Cin, const long long *row, const long long *col,
+                             const unsigned char *edge_mask, long long E, const float *W1, const float *b1,
+                             const float *W2, const float *b2, int Cout, float *z, float *Y1, float *msg, float *agg,
+                             void *workspace, void *stream);
+S2C_API int s2c_edgeconv_bwd(const float *dagg, const float *dmsg, long long Nn, int Cin, const long long *row,
+                             const long long *col, const unsigned char *edge_mask, long long E, const float *W1,
+                             const float *b1, const float *W2, int Cout, const float *z, const float *Y1, float *dx,
+                             float *dW1, float *db1, float *dW2, float *db2, void *workspace, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,8 @@ SIGNATURES = {
     "s2c_points_in_boxes_count": [P, c_ll, c_int, c_int, P, c_int, P, P],
     "s2c_nms3d": [P, P, P, P, c_int, c_int, ctypes.c_double, c_int, c_int, P, P],
     "s2c_knn_adjacency": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.c_double, P, P, P],
+    "s2c_edgeconv_fwd": [P, c_ll, c_int, P, P, P, c_ll, P, P, P, P, c_int, P, P, P, P, P, P],
+    "s2c_edgeconv_bwd": [P, P, c_ll, c_int, P, P, P, c_ll, P, P, P, c_int, P, P, P, P, P, P, P, P, P],
 }
 
 
@@ -75,6 +77,8 @@ def _load():
     lib.s2c_last_error.restype = ctypes.c_char_p
     lib.s2c_ball_query_grid_workspace_bytes.restype = c_ll
     lib.s2c_ball_query_grid_workspace_bytes.argtypes = [c_int, c_int]
+    lib.s2c_edgeconv_workspace_bytes.restype = c_ll
+    lib.s2c_edgeconv_workspace_bytes.argtypes = [c_ll, c_int, c_int, c_int]
     lib.s2c_query_and_group_grid_tune.restype = c_int
     lib.s2c_query_and_group_grid_tune.argtypes = [c_int]
     for name, argtypes in SIGNATURES.items():

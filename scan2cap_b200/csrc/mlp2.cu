@@ -32,6 +32,7 @@ struct Gemm2Args {
   const float *A; long long lda; int K;
   const float *p0, *p1, *p2, *p3, *p4;  // per-K prologue coefficients (see PRO_*); p3/p4 = last layer's scale/shift (PRO_POOL)
   const float *dpool; const int *argmax; int ns;  // PRO_POOL: (G, K) pooled gradient and arg-max sample
+  int GT;  // PRO_POOL: groups one 128-row tile can touch = rows of the (argmax, dpool) slabs staged with every raw chunk
   const unsigned char *wprep;  // KC chunks of [hi: N x 128 B swizzled][lo: N x 128 B swizzled]
   float *C; long long ldc;
   float *dY_out;  // optional (R, K): the staged operand a' written back (the weight-gradient GEMM consumes it)
@@ -181,13 +182,17 @@ __device__ __forceinline__ void tma_load_box(void *dst_smem, const CUtensorMap *
 
 template <int N, int PRO, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
-mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2) {
+mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
+                 const __grid_constant__ CUtensorMap tmap_am, const __grid_constant__ CUtensorMap tmap_dp) {
   extern __shared__ __align__(1024) unsigned char smem[];
   constexpr uint32_t A_BYTES = BM * BK * 4;            // 16 KB per hi / lo / raw block
   constexpr uint32_t W_BYTES = N * BK * 4;             // N x 128 B per hi / lo block
   constexpr uint32_t OP_BYTES = 2 * A_BYTES + 2 * W_BYTES;
   constexpr uint32_t RAW_TILES = (PRO == PRO_AFFINE2) ? 2 : 1;   // raw tiles per chunk (g and y for the affine prologue)
-  constexpr uint32_t RAW_BYTES = RAW_TILES * A_BYTES;
+  // PRO_POOL: every raw stage also carries the [GT groups x 32 channels] slabs of argmax (int32) and dpool (fp32) that
+  // cover the tile's rows, fetched by the TMA engine with the y tile -- the transform warps never touch global memory
+  const uint32_t SLAB_BYTES = (PRO == PRO_POOL) ? (uint32_t)g.GT * 128u : 0u;
+  const uint32_t RAW_BYTES = RAW_TILES * A_BYTES + 2 * SLAB_BYTES;
   constexpr int NPRO = (PRO == PRO_BNRELU) ? 2 : (PRO == PRO_AFFINE2) ? 3 : 5;
   constexpr uint32_t TMEM_COLS = (2 * N <= 32) ? 32 : (2 * N <= 64) ? 64 : (2 * N <= 128) ? 128 : (2 * N <= 256) ? 256 : 512;
   const int RS = g.RS;
@@ -241,8 +246,11 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
           if (lane == 0) {
             mbar_arrive_expect_tx(&raw_full[rs], RAW_BYTES);
             unsigned char *dst = raw_base + (size_t)rs * RAW_BYTES;
-            if (PRO == PRO_POOL) {  // only y comes through TMA; g is rebuilt from the pooled gradient
+            if (PRO == PRO_POOL) {  // y tile + the pooled-gradient slabs of the tile's groups; g is rebuilt from them
+              const int g0 = (int)((ta * BM) / g.ns);
               tma_load_box(dst, &tmap_a2, ka * BK, (int)(ta * BM), &raw_full[rs]);
+              tma_load_box(dst + A_BYTES, &tmap_am, ka * BK, g0, &raw_full[rs]);
+              tma_load_box(dst + A_BYTES + SLAB_BYTES, &tmap_dp, ka * BK, g0, &raw_full[rs]);
             } else {
               tma_load_box(dst, &tmap_a, ka * BK, (int)(ta * BM), &raw_full[rs]);
               if (PRO == PRO_AFFINE2) tma_load_box(dst + A_BYTES, &tmap_a2, ka * BK, (int)(ta * BM), &raw_full[rs]);
@@ -314,29 +322,14 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
           c3 = *reinterpret_cast<const float4 *>(s_pro + 3 * KP + kk);
           c4 = *reinterpret_cast<const float4 *>(s_pro + 4 * KP + kk);
         }
-        // PRO_POOL: (argmax, dpool) depend on the row's GROUP only; consecutive passes (16 rows apart) mostly stay in
-        // one group, so the two global loads are issued once per group change instead of once per pass, and the
-        // group / sample indices advance incrementally (one 64-bit division per chunk instead of one per pass)
-        long long pgrp = 0, pgrp_loaded = -1;
-        int psmp = 0;
-        int4 p_am = make_int4(0, 0, 0, 0), n_am = p_am;     // current group's values / the next group's (one ahead)
-        float4 p_dp = make_float4(0.f, 0.f, 0.f, 0.f), n_dp = p_dp;
-        const long long num_groups = g.ns > 0 ? g.R / g.ns : 0;
+        // PRO_POOL: (argmax, dpool) depend on the row's GROUP only; the slab row (group - first group of the tile) and
+        // the sample index advance incrementally from pass to pass (16 rows apart)
+        int pgrp = 0, psmp = 0;
         if (PRO == PRO_POOL) {
           const long long base = row0 + (tt >> 3);
-          pgrp = base / g.ns;
-          psmp = (int)(base - pgrp * g.ns);
-          if (kk < g.K) {  // first two groups' values: in flight while this warp waits for the raw tile
-            if (pgrp < num_groups) {
-              p_am = __ldg(reinterpret_cast<const int4 *>(g.argmax + pgrp * g.K + kk));
-              p_dp = __ldg(reinterpret_cast<const float4 *>(g.dpool + pgrp * g.K + kk));
-            }
-            if (pgrp + 1 < num_groups) {
-              n_am = __ldg(reinterpret_cast<const int4 *>(g.argmax + (pgrp + 1) * g.K + kk));
-              n_dp = __ldg(reinterpret_cast<const float4 *>(g.dpool + (pgrp + 1) * g.K + kk));
-            }
-            pgrp_loaded = pgrp;
-          }
+          const long long gq = base / g.ns;
+          pgrp = (int)(gq - row0 / g.ns);
+          psmp = (int)(base - gq * g.ns);
         }
         mbar_wait(&raw_full[rs], (uint32_t)((it / RS) & 1));
         if (it >= OS) mbar_wait(&op_empty[os], (uint32_t)(((it / OS) - 1) & 1));
@@ -360,21 +353,8 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
             const float4 y = v;
             float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
             if (row < g.R && kk < g.K) {
-              if (pgrp != pgrp_loaded) {
-                if (pgrp == pgrp_loaded + 1) {  // the prefetched group; fetch the one after it
-                  p_am = n_am; p_dp = n_dp;
-                } else {
-                  p_am = __ldg(reinterpret_cast<const int4 *>(g.argmax + pgrp * g.K + kk));
-                  p_dp = __ldg(reinterpret_cast<const float4 *>(g.dpool + pgrp * g.K + kk));
-                }
-                if (pgrp + 1 < num_groups) {
-                  n_am = __ldg(reinterpret_cast<const int4 *>(g.argmax + (pgrp + 1) * g.K + kk));
-                  n_dp = __ldg(reinterpret_cast<const float4 *>(g.dpool + (pgrp + 1) * g.K + kk));
-                }
-                pgrp_loaded = pgrp;
-              }
-              const int4 am = p_am;
-              const float4 dp = p_dp;
+              const int4 am = *reinterpret_cast<const int4 *>(raw + A_BYTES + pgrp * 128 + seg * 16);
+              const float4 dp = *reinterpret_cast<const float4 *>(raw + A_BYTES + SLAB_BYTES + pgrp * 128 + seg * 16);
               const int smp = psmp;
               gg.x = (am.x == smp && fmaf(y.x, c3.x, c4.x) > 0.f) ? dp.x : 0.f;
               gg.y = (am.y == smp && fmaf(y.y, c3.y, c4.y) > 0.f) ? dp.y : 0.f;
@@ -512,9 +492,9 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-size_t gemm2_smem(int N, int K, int RS, int raw_tiles, int npro) {
+size_t gemm2_smem(int N, int K, int RS, int raw_tiles, int npro, int GT) {
   const int KC = (K + BK - 1) / BK;
-  return (size_t)OS * (2 * BM * BK * 4 + 2 * (size_t)N * BK * 4) + (size_t)RS * raw_tiles * BM * BK * 4 +
+  return (size_t)OS * (2 * BM * BK * 4 + 2 * (size_t)N * BK * 4) + (size_t)RS * (raw_tiles * BM * BK * 4 + 2 * (size_t)GT * 128) +
          (size_t)npro * KC * BK * 4 + 4 * 32 * 36 * 4 + 24 * 8 + 16;
 }
 
@@ -533,8 +513,8 @@ EncodeTiledFn encode_tiled() {  // driver entry point through the runtime: no li
   return fn;
 }
 
-// tensor map of a row-major (R, ld) fp32 matrix with K valid columns, box = [128 rows x 32 columns]
-int make_tmap(CUtensorMap *tmap, const float *base, long long R, int K, long long ld) {
+// tensor map of a row-major (R, ld) matrix of 4-byte elements with K valid columns, box = [box_rows x 32 columns]
+int make_tmap(CUtensorMap *tmap, const void *base, long long R, int K, long long ld, int box_rows = BM, bool i32 = false) {
   EncodeTiledFn enc = encode_tiled();
   if (!enc) {
     set_error("mlp: cuTensorMapEncodeTiled is not available from this driver");
@@ -542,9 +522,9 @@ int make_tmap(CUtensorMap *tmap, const float *base, long long R, int K, long lon
   }
   const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)R};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  const cuuint32_t box[2] = {BK, BM};
+  const cuuint32_t box[2] = {BK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+  const CUresult r = enc(tmap, i32 ? CU_TENSOR_MAP_DATA_TYPE_INT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -559,15 +539,26 @@ int launch_gemm2(const Gemm2Args &g0, const float *A2, long long lda2, cudaStrea
   Gemm2Args g = g0;
   constexpr int raw_tiles = (PRO == PRO_AFFINE2) ? 2 : 1;
   constexpr int npro = (PRO == PRO_BNRELU) ? 2 : (PRO == PRO_AFFINE2) ? 3 : 5;
-  CUtensorMap tmap, tmap2;
+  CUtensorMap tmap, tmap2, tmap_am, tmap_dp;
   int rc = make_tmap(&tmap, g.A ? g.A : A2, g.R, g.K, g.A ? g.lda : lda2);
   if (rc) return rc;
   rc = make_tmap(&tmap2, A2 ? A2 : g.A, g.R, g.K, A2 ? lda2 : g.lda);
   if (rc) return rc;
+  g.GT = 0;
+  if (PRO == PRO_POOL) {  // groups a 128-row tile can touch: 128/ns when ns divides 128 (tiles start on a group boundary)
+    g.GT = (BM % g.ns == 0) ? BM / g.ns : (BM - 1) / g.ns + 2;
+    const long long G = g.R / g.ns;
+    rc = make_tmap(&tmap_am, g.argmax, G, g.K, g.K, g.GT, true);
+    if (rc) return rc;
+    rc = make_tmap(&tmap_dp, g.dpool, G, g.K, g.K, g.GT, false);
+    if (rc) return rc;
+  } else {
+    tmap_am = tmap; tmap_dp = tmap;
+  }
   int RS = 4;  // raw-tile ring depth = bytes the TMA engine keeps in flight per SM (16 KB per stage and raw tile)
   if (const char *e = getenv("S2C_MLP_RS")) RS = atoi(e) >= 1 && atoi(e) <= 8 ? atoi(e) : 4;  // tuning / debugging knob
-  while (RS > 1 && gemm2_smem(N, g.K, RS, raw_tiles, npro) > 227 * 1024) --RS;
-  const size_t smem = gemm2_smem(N, g.K, RS, raw_tiles, npro);
+  while (RS > 1 && gemm2_smem(N, g.K, RS, raw_tiles, npro, g.GT) > 227 * 1024) --RS;
+  const size_t smem = gemm2_smem(N, g.K, RS, raw_tiles, npro, g.GT);
   if (smem > 227 * 1024) {
     set_error("mlp: shared memory %zu B exceeds 227 KB (N=%d K=%d)", smem, N, g.K);
     return S2C_ERR_UNSUPPORTED;
@@ -577,7 +568,7 @@ int launch_gemm2(const Gemm2Args &g0, const float *A2, long long lda2, cudaStrea
   S2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "mlp_gemm2 smem attr");
   const long long tiles = (g.R + BM - 1) / BM;
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-  kern<<<grid, kThreads, smem, st>>>(g, tmap, tmap2);
+  kern<<<grid, kThreads, smem, st>>>(g, tmap, tmap2, tmap_am, tmap_dp);
   S2C_CHECK_LAUNCH("mlp_gemm2 launch");
   return S2C_OK;
 }

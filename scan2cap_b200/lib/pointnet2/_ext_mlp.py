@@ -11,16 +11,19 @@ from ._ext import _guard, _stream
 KERNEL_VERSION = 2
 
 
-def mlp_layer_fwd(A, W, pro_scale=None, pro_shift=None, want_stats=True, K=None, version=None):
+def mlp_layer_fwd(A, W, pro_scale=None, pro_shift=None, want_stats=True, K=None, version=None, out=None, col0=0):
     """A (R, lda) fp32 (row stride lda >= K), W (N, K) -> C (R, N) = relu(A*scale+shift) @ W^T [no prologue when
-    scale is None], plus float64 column sums / sums of squares of C when want_stats."""
+    scale is None], plus float64 column sums / sums of squares of C when want_stats.  With `out` (R, >= col0+N) the
+    result is written to out[:, col0:col0+N]."""
     assert A.is_cuda and A.dtype == torch.float32 and A.dim() == 2 and A.stride(1) == 1
     W = W.contiguous()
     N, Kw = W.shape
     K = Kw if K is None else K
     assert K == Kw and A.shape[1] >= K
     R, lda = A.shape[0], A.stride(0)
-    C = torch.empty((R, N), dtype=torch.float32, device=A.device)
+    C = torch.empty((R, N), dtype=torch.float32, device=A.device) if out is None else out
+    assert C.stride(1) == 1 and C.shape[0] == R and C.shape[1] >= col0 + N and col0 % 4 == 0
+    ldc, cptr = C.stride(0), C.data_ptr() + 4 * col0
     s1 = s2 = None
     if want_stats:
         stats = torch.zeros((2, N), dtype=torch.float64, device=A.device)
@@ -33,14 +36,14 @@ def mlp_layer_fwd(A, W, pro_scale=None, pro_shift=None, want_stats=True, K=None,
             call("s2c_mlp_layer_fwd_v2", A.data_ptr(), lda, R, K,
                  pro_scale.data_ptr() if pro_scale is not None else None,
                  pro_shift.data_ptr() if pro_shift is not None else None,
-                 W.data_ptr(), N, C.data_ptr(), N,
+                 W.data_ptr(), N, cptr, ldc,
                  s1.data_ptr() if want_stats else None, s2.data_ptr() if want_stats else None, wprep.data_ptr(),
                  _stream(A))
         else:
             call("s2c_mlp_layer_fwd", A.data_ptr(), lda, R, K,
                  pro_scale.data_ptr() if pro_scale is not None else None,
                  pro_shift.data_ptr() if pro_shift is not None else None,
-                 W.data_ptr(), N, C.data_ptr(), N,
+                 W.data_ptr(), N, cptr, ldc,
                  s1.data_ptr() if want_stats else None, s2.data_ptr() if want_stats else None, _stream(A))
     return (C, s1, s2) if want_stats else C
 

@@ -30,6 +30,22 @@ def _bn_coefficients(s1, s2, R, bn, training):
     return _ext_mlp.bn_finalize(s1, s2, R, bn, training)
 
 
+def _fold_conv_bias(bias, bn, training, scale, shift):
+    """A conv bias in front of BatchNorm (the Conv1d heads of voting_module.py:27-31 / proposal_module.py:46-50): the
+    GEMM runs without it.  Batch statistics: the normalised output does not depend on it, only the running mean does
+    (+ momentum * bias); running statistics: it moves the folded shift by scale * bias."""
+    batch = training or not bn.track_running_stats
+    if batch:
+        if training and bn.track_running_stats:
+            with torch.no_grad():
+                if bn.momentum is not None:
+                    bn.running_mean.add_(bias, alpha=float(bn.momentum))
+                else:
+                    bn.running_mean.addcdiv_(bias, bn.num_batches_tracked.to(bias.dtype))
+        return scale, shift
+    return scale, torch.addcmul(shift, scale, bias)
+
+
 def _first_layer_weight(W, K, lda, xyz_gap):
     """The first layer's weight in the column layout of `rows` -> (W', K').
     xyz_gap: rows are [x, y, z, 0 | K-3 features | zero pad] (lda floats): W' = [W[:, :3], 0, W[:, 3:], 0];
@@ -71,26 +87,28 @@ def _input_blocks(K, lda, xyz_gap):
 
 class _FusedMLPPool(Function):
     @staticmethod
-    def forward(ctx, rows, K, G, ns, training, bns, xyz_gap, need_xyz_grad, *params):
-        """rows (R, lda) fp32 with K valid columns, R = G*ns; params = (W1, gamma1, beta1, W2, ...);
+    def forward(ctx, rows, K, G, ns, training, bns, xyz_gap, need_xyz_grad, capture, *params):
+        """rows (R, lda) fp32 with K valid columns, R = G*ns; params = (W1, gamma1, beta1, bias1 | None, W2, ...);
         bns = the BatchNorm modules (running statistics / eps / momentum).  Returns pooled (G, C_last)."""
         L = len(bns)
         R = rows.shape[0]
         Ys, coefs = [], []
         A, scale, shift, k = rows, None, None, K
         for l in range(L):
-            W = params[3 * l].reshape(params[3 * l].shape[0], -1)
+            W = params[4 * l].reshape(params[4 * l].shape[0], -1)
             need_stats = training or not bns[l].track_running_stats
             if l == 0:  # the weight in the column layout of the rows (zero columns where the rows are padding)
                 W, k = _first_layer_weight(W, K, A.shape[1], xyz_gap)
             res = _ext_mlp.mlp_layer_fwd(A, W, scale, shift, want_stats=need_stats, K=k)
             Y, s1, s2 = res if need_stats else (res, None, None)
             mean, invstd, scale, shift = _bn_coefficients(s1, s2, R, bns[l], training)
+            if params[4 * l + 3] is not None:
+                scale, shift = _fold_conv_bias(params[4 * l + 3].detach(), bns[l], training, scale, shift)
             Ys.append(Y)
             coefs.append((mean, invstd, scale, shift))
             A, k = Y, W.shape[0]
         pooled, argmax = _ext_mlp.pool_fwd(Ys[-1], G, ns, scale, shift, want_argmax=True)
-        if CAPTURE is not None:
+        if CAPTURE is not None and capture:
             CAPTURE.append(dict(G=G, ns=ns, Ys=list(Ys), affine=[(c[2], c[3]) for c in coefs], argmax=argmax,
                                 pooled=pooled))
         ctx.save_for_backward(rows, argmax, *Ys, *[t for c in coefs for t in c], *params)
@@ -107,16 +125,21 @@ class _FusedMLPPool(Function):
         coefs = [saved[2 + L + 4 * l: 2 + L + 4 * l + 4] for l in range(L)]
         params = saved[2 + 5 * L:]
         R = rows.shape[0]
-        grads = [None] * (3 * L)
+        grads = [None] * (4 * L)
         dpool = dpool.contiguous()
         grad_rows = None
 
         def affine(l, sum_g, sum_gy):
             """BatchNorm backward of layer l as dY = a*g + b*y + c; also its gamma / beta gradients."""
             mean, invstd, _, _ = coefs[l]
-            gamma = params[3 * l + 1]
-            grads[3 * l + 1], grads[3 * l + 2], a, b, c = _ext_mlp.bn_backward_coeffs(
+            gamma = params[4 * l + 1]
+            grads[4 * l + 1], grads[4 * l + 2], a, b, c = _ext_mlp.bn_backward_coeffs(
                 sum_g, sum_gy, mean, invstd, gamma, R, batch_stats[l])
+            if params[4 * l + 3] is not None:
+                # a bias in front of a batch-statistics BatchNorm has an identically zero gradient (sum_r dY = 0);
+                # with running statistics dY = a*g and the bias gradient is a * sum_r g
+                grads[4 * l + 3] = (torch.zeros_like(params[4 * l + 3]) if batch_stats[l]
+                                    else (a.double() * sum_g).to(a.dtype))
             return a, b, c
 
         # last layer: its masked gradient is the pooled gradient at the arg-max sample -> sums straight from dpool
@@ -125,7 +148,7 @@ class _FusedMLPPool(Function):
         sum_g, sum_gy = _ext_mlp.pool_bwd_stats(dpool, argmax, Ys[l], ns, sc_l, sh_l)
         g = None  # dense masked gradient of layer l (None while it is still "pooled")
         while l >= 0:
-            W = params[3 * l].reshape(params[3 * l].shape[0], -1)
+            W = params[4 * l].reshape(params[4 * l].shape[0], -1)
             a, b, c = affine(l, sum_g, sum_gy)
             Y = Ys[l]
             fused = l > 0 and _ext_mlp.bwd_data_supported(Y.shape[1], Ys[l - 1].shape[1])
@@ -138,13 +161,13 @@ class _FusedMLPPool(Function):
                 else:
                     g_prev, dY, sum_g, sum_gy = _ext_mlp.mlp_layer_bwd_data(Y, a, b, c, W, Ys[l - 1], sc_p, sh_p, G=g)
                 if _ext_mlp.bwd_weight_supported(Y.shape[1], Ys[l - 1].shape[1], dY.stride(0), Ys[l - 1].stride(0)):
-                    grads[3 * l] = _ext_mlp.mlp_layer_bwd_weight(dY, Ys[l - 1], Ys[l - 1].shape[1], sc_p, sh_p).view_as(params[3 * l])
+                    grads[4 * l] = _ext_mlp.mlp_layer_bwd_weight(dY, Ys[l - 1], Ys[l - 1].shape[1], sc_p, sh_p).view_as(params[4 * l])
                 elif _ext_mlp.wgrad_blocked_supported(Y.shape[1], Ys[l - 1].shape[1], dY.stride(0), Ys[l - 1].stride(0)):
-                    grads[3 * l] = _ext_mlp.mlp_layer_bwd_weight_blocked(dY, Ys[l - 1], Ys[l - 1].shape[1], sc_p,
-                                                                        sh_p).view_as(params[3 * l])
+                    grads[4 * l] = _ext_mlp.mlp_layer_bwd_weight_blocked(dY, Ys[l - 1], Ys[l - 1].shape[1], sc_p,
+                                                                        sh_p).view_as(params[4 * l])
                 else:
                     Xp = torch.relu_(torch.addcmul(sh_p, Ys[l - 1], sc_p))
-                    grads[3 * l] = (dY.t() @ Xp).view_as(params[3 * l])
+                    grads[4 * l] = (dY.t() @ Xp).view_as(params[4 * l])
                 g = g_prev
             else:
                 if g is None:  # materialise the pooled gradient (ReLU mask of the last layer applied)
@@ -186,7 +209,7 @@ class _FusedMLPPool(Function):
                 if l > 0:
                     _, _, sc_p, sh_p = coefs[l - 1]
                     pre = torch.addcmul(sh_p, Ys[l - 1], sc_p)
-                    grads[3 * l] = (dY.t() @ torch.relu(pre)).view_as(params[3 * l])
+                    grads[4 * l] = (dY.t() @ torch.relu(pre)).view_as(params[4 * l])
                     g = (dY @ W) * (pre > 0)
                     sum_g = g.sum(0, dtype=torch.float64)
                     sum_gy = (g * Ys[l - 1]).sum(0, dtype=torch.float64)
@@ -202,19 +225,20 @@ class _FusedMLPPool(Function):
                         if rows.shape[1] != Kp:
                             grad_rows = torch.nn.functional.pad(grad_rows, (0, rows.shape[1] - Kp))
             l -= 1
-        return (grad_rows, None, None, None, None, None, None, None) + tuple(grads)
+        return (grad_rows, None, None, None, None, None, None, None, None) + tuple(grads)
 
 
-def fused_mlp_maxpool(rows, K, G, ns, layers, training, xyz_gap=False, need_xyz_grad=True):
+def fused_mlp_maxpool(rows, K, G, ns, layers, training, xyz_gap=False, need_xyz_grad=True, capture=True):
     """rows (G*ns, >=K) -> (G, C_last): SharedMLP `layers` = [(conv, bn)] then max over each group's ns rows.
     xyz_gap: the rows are [x, y, z, 0 | K-3 features | zero pad] (the padded layout of the fused query+group kernel);
-    need_xyz_grad=False skips the gradient of the three coordinate columns (no grad flows to xyz / new_xyz)."""
+    need_xyz_grad=False skips the gradient of the three coordinate columns (no grad flows to xyz / new_xyz).
+    capture=False keeps the call out of the CAPTURE test hook (the pointwise heads: they are not SA / FP modules)."""
     params, bns = [], []
     for conv, bn in layers:
-        assert conv.bias is None and bn is not None, "fused path: conv without bias followed by BatchNorm"
-        params += [conv.weight, bn.weight, bn.bias]
+        assert bn is not None, "fused path: conv followed by BatchNorm"
+        params += [conv.weight, bn.weight, bn.bias, conv.bias]
         bns.append(bn)
-    return _FusedMLPPool.apply(rows, K, G, ns, training, bns, xyz_gap, need_xyz_grad, *params)
+    return _FusedMLPPool.apply(rows, K, G, ns, training, bns, xyz_gap, need_xyz_grad, capture, *params)
 
 
 def fusable(layers):
@@ -222,6 +246,89 @@ def fusable(layers):
         return False
     for conv, bn in layers:
         n = conv.weight.shape[0]
-        if conv.bias is not None or bn is None or not bn.affine or n % 16 != 0 or n > 256:
+        if bn is None or not bn.affine or n % 16 != 0 or n > 256:
             return False
     return True
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Final (bias, no BatchNorm, no ReLU) layer of the pointwise heads -- Conv1d(256, 3+256) of VotingModule
+# (models/voting_module.py:31,55), Conv1d(128, 2+3+NH*2+NS*4+NC) of ProposalModule (models/proposal_module.py:52) and
+# Linear(128, num_bins+1) of GraphModule.edge_predict (models/graph_module.py:151) -- on the same tensor-core kernels.
+# The output width is padded to the kernels' tile widths (blocks of 256 / 128 / 64 columns, zero weight rows).
+
+_CONST = {}
+
+
+def _const(device, n, value):
+    key = (str(device), int(n), float(value))
+    t = _CONST.get(key)
+    if t is None:
+        t = _CONST[key] = torch.full((int(n),), float(value), dtype=torch.float32, device=device)
+    return t
+
+
+def _col_blocks(n):
+    """n (multiple of 64) -> [(col0, width)] with widths 256 / 128 / 64."""
+    blocks, c = [], 0
+    while c < n:
+        w = 256 if n - c >= 256 else (128 if n - c >= 128 else 64)
+        blocks.append((c, w))
+        c += w
+    return blocks
+
+
+class _LinearRows(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        """x (R, K) fp32 rows (K multiple of 64), weight (N, K), bias (N) or None -> (R, N) = x W^T + b."""
+        R, K = x.shape
+        N = weight.shape[0]
+        Np = (N + 63) // 64 * 64
+        Wp = torch.nn.functional.pad(weight, (0, 0, 0, Np - N)) if Np != N else weight.contiguous()
+        Y = torch.empty((R, Np), dtype=torch.float32, device=x.device)
+        for n0, w in _col_blocks(Np):
+            _ext_mlp.mlp_layer_fwd(x, Wp[n0:n0 + w], want_stats=False, out=Y, col0=n0)
+        ctx.save_for_backward(x, Wp)
+        ctx.N = N
+        ctx.has_bias = bias is not None
+        out = Y[:, :N]
+        return out + bias if bias is not None else (out if Np == N else out.contiguous())
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, Wp = ctx.saved_tensors
+        R, K = x.shape
+        N, Np = ctx.N, Wp.shape[0]
+        dYp = torch.nn.functional.pad(dy, (0, Np - N)) if Np != N else dy.contiguous()
+        db = _ext_mlp.col_sum(dYp)[:N] if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        dx = dW = None
+        if ctx.needs_input_grad[0]:
+            # dx = dY Wp: the first-layer input-gradient kernel with identity BatchNorm-backward coefficients
+            one, zero = _const(x.device, Np, 1.0), _const(x.device, Np, 0.0)
+            dx = torch.empty_like(x)
+            for c0, w in _col_blocks(K):
+                _ext_mlp.mlp_layer_bwd_input(dYp, dYp, one, zero, zero, Wp, c0, w, dx, want_dY=False)
+        if ctx.needs_input_grad[1]:
+            dWp = torch.zeros((Np, K), dtype=torch.float32, device=x.device)
+            for n0, w in _col_blocks(Np):
+                step = 256 if w <= 128 else 128
+                for c0 in range(0, K, step):
+                    _ext_mlp.mlp_layer_bwd_weight(dYp[:, n0:n0 + w], x, min(step, K - c0), out=dWp[n0:n0 + w], col0=c0)
+            dW = dWp[:N]
+        return dx, dW, db
+
+
+def linear_rows_supported(x, weight):
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] % 64 == 0 and x.stride(1) == 1
+            and x.stride(0) % 4 == 0 and weight.dim() == 2 and weight.shape[1] == x.shape[1])
+
+
+def linear_rows(x, weight, bias=None):
+    """x (R, K) @ weight (N, K)^T + bias on the tcgen05 layer kernels (3xTF32), forward and backward."""
+    if not linear_rows_supported(x, weight):
+        raise RuntimeError("linear_rows: x must be a CUDA fp32 (R, K) matrix with K a multiple of 64 and aligned rows "
+                           "(tensor-core kernels of libs2c); got %s / %s" % (tuple(x.shape), tuple(weight.shape)))
+    if x.data_ptr() % 16 != 0:
+        x = x.contiguous()
+    return _LinearRows.apply(x, weight, bias)

@@ -15,7 +15,6 @@ from typing import List
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import _ext
 from . import fused_mlp
@@ -26,23 +25,6 @@ def point_major(features):
     """(B,C,N) tensor -> (B,N,C) view with unit channel stride (copying only if the storage is channel-major)."""
     f = features.transpose(1, 2)
     return f if f.stride(2) == 1 and f.stride(0) == f.shape[1] * f.stride(1) else f.contiguous()
-
-
-def bn_rows(x, bn, training):
-    """BatchNorm{1d,2d} of a row-major (R, C) matrix: statistics over the R rows (every (scene, point[, sample]))."""
-    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
-    if bn.momentum is not None:
-        mom = bn.momentum
-    else:  # nn.BatchNorm: cumulative moving average, factor 1 / num_batches_tracked (already incremented above)
-        mom = 1.0 / float(bn.num_batches_tracked) if (training and bn.num_batches_tracked is not None) else 0.0
-    return F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias,
-                        training or not bn.track_running_stats, mom, bn.eps)
-
-
-def conv1x1_rows(x, conv):
-    """Pointwise Conv1d/Conv2d applied to a row-major (R, Cin) matrix."""
-    return F.linear(x, conv.weight.view(conv.weight.shape[0], -1), conv.bias)
 
 
 def _require_fusable(layers, what):

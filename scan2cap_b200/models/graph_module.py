@@ -24,8 +24,7 @@ import torch
 import torch.nn as nn
 
 from ..lib.config import CONF
-from ..lib import linear_tc
-from ..lib.pointnet2 import _ext_graph
+from ..lib.pointnet2 import _ext_graph, fused_mlp
 
 
 # Test hook (tests/parity_utils.py): a list that receives (rectified hidden layer, message tensor, edge mask) of every
@@ -33,30 +32,62 @@ from ..lib.pointnet2 import _ext_graph
 CAPTURE = None
 
 
+class _EdgeConvFn(torch.autograd.Function):
+    """(aggregated (Nn, out) or None, masked message (E, out)) of one EdgeConv layer: s2c_edgeconv_fwd / _bwd."""
+
+    @staticmethod
+    def forward(ctx, x, row, col, edge_mask, W1, b1, W2, b2, want_agg):
+        z, Y1, msg, agg, mask8 = _ext_graph.edgeconv_fwd(x.contiguous(), row, col, edge_mask, W1.contiguous(),
+                                                         b1.contiguous(), W2.contiguous(), b2.contiguous(), want_agg)
+        ctx.save_for_backward(row, col, mask8, W1, b1, W2, z, Y1)
+        ctx.num_nodes = x.shape[0]
+        if not want_agg:
+            agg = x.new_zeros(0)
+            ctx.mark_non_differentiable(agg)
+        ctx.want_agg = want_agg
+        return agg, msg
+
+    @staticmethod
+    def backward(ctx, dagg, dmsg):
+        row, col, mask8, W1, b1, W2, z, Y1 = ctx.saved_tensors
+        dagg = dagg.contiguous() if (ctx.want_agg and dagg is not None) else None
+        dmsg = dmsg.contiguous() if dmsg is not None else None
+        if dagg is None and dmsg is None:
+            return (None,) * 9
+        dx, dW1, db1, dW2, db2 = _ext_graph.edgeconv_bwd(dagg, dmsg, ctx.num_nodes, row, col, mask8, W1.contiguous(), b1,
+                                                         W2.contiguous(), z, Y1, ctx.needs_input_grad[0])
+        return dx, None, None, None, dW1, db1, dW2, db2, None
+
+
 class EdgeConv(nn.Module):
     def __init__(self, in_size, out_size, aggregation="add"):
         super().__init__()
         assert aggregation in ("add", "mean", "max")
+        if not _ext_graph.edgeconv_supported(in_size, out_size):
+            raise ValueError("EdgeConv: out_size must be 64/128/256 and 2*in_size a multiple of 64, <= 512 "
+                             "(tile widths of the tensor-core kernels of libs2c)")
         self.in_size = in_size
         self.out_size = out_size
         self.aggr = aggregation
         self.map_edge = nn.Sequential(nn.Linear(2 * in_size, out_size), nn.ReLU(), nn.Linear(out_size, out_size))
 
-    def message(self, x_i, x_j):
-        z = torch.cat([x_i, x_j - x_i], dim=1)
-        # Linear -> ReLU -> Linear over all E edges; the weight gradients run on the tensor-core kernel (lib/linear_tc.py)
-        h = torch.relu(linear_tc.linear(z, self.map_edge[0].weight, self.map_edge[0].bias))
-        msg = linear_tc.linear(h, self.map_edge[2].weight, self.map_edge[2].bias)
+    def forward(self, x, edge_index, edge_mask=None, need_aggregate=True):
+        """x (N,in), edge_index (2,E) long, optional edge_mask (E) bool -> (out (N,out), message (E,out)).
+        message = the masked messages; need_aggregate=False skips the aggregation (out is None)."""
+        row, col = edge_index[0].contiguous(), edge_index[1].contiguous()
+        lin1, lin2 = self.map_edge[0], self.map_edge[2]
+        # the parity tests hook the message gradient (CAPTURE): then the aggregation runs outside the fused call so that
+        # ALL of the message's gradient passes through the hooked tensor
+        fused_add = need_aggregate and self.aggr == "add" and CAPTURE is None
+        out, msg = _EdgeConvFn.apply(x, row, col, edge_mask, lin1.weight, lin1.bias, lin2.weight, lin2.bias, fused_add)
         if CAPTURE is not None:
-            CAPTURE.append({"hidden": h.detach(), "message": msg})
-        return msg
-
-    def forward(self, x, edge_index, edge_mask=None):
-        """x (N,in), edge_index (2,E) long, optional edge_mask (E) bool -> (out (N,out), message (E,out))."""
-        row, col = edge_index[0], edge_index[1]
-        msg = self.message(x.index_select(0, col), x.index_select(0, row))
-        if edge_mask is not None:
-            msg = msg * edge_mask.unsqueeze(-1).to(msg.dtype)
+            saved = msg.grad_fn.saved_tensors if msg.grad_fn is not None else None   # (..., b1 = [4], ..., Y1 = [7])
+            hidden = torch.relu(saved[7] + saved[4]).detach() if saved is not None else None
+            CAPTURE.append({"hidden": hidden, "message": msg})
+        if fused_add:
+            return out, msg
+        if not need_aggregate:
+            return None, msg
         out = x.new_zeros(x.shape[0], self.out_size)
         if self.aggr == "add":
             out = out.index_add(0, col, msg)
@@ -183,8 +214,8 @@ class GraphModule(nn.Module):
             num_sources = torch.where(ok_scene, num_src, torch.zeros_like(num_src))
             num_targets = num_tar
             # extra EdgeConv on the LAST node features, then the orientation / distance head
-            _, edge_feat2 = self.edge_layer(node_feat, edge_g, emask)
-            pred = self.edge_predict(edge_feat2).view(B, K * L, -1)
+            _, edge_feat2 = self.edge_layer(node_feat, edge_g, emask, need_aggregate=False)
+            pred = fused_mlp.linear_rows(edge_feat2, self.edge_predict.weight, self.edge_predict.bias).view(B, K * L, -1)
             pred_ok = (ok_scene & (E == num_src * num_tar)).unsqueeze(1)   # else shape mismatch -> skipped
             dst_p = torch.where(flat_valid & pred_ok, epos, torch.full_like(epos, K * L))
             pbuf = obj_feats.new_zeros(B, K * L + 1, self.num_bins + 1)

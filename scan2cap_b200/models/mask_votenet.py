@@ -7,7 +7,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ..lib.pointnet2.pointnet2_modules import PointnetSAModuleVotes, bn_rows, conv1x1_rows
+from ..lib.pointnet2 import fused_mlp
+from ..lib.pointnet2.pointnet2_modules import PointnetSAModuleVotes
 from .backbone_module import Pointnet2Backbone
 from .voting_module import VotingModule
 
@@ -40,9 +41,9 @@ class ProposalModule(nn.Module):
         head = self.proposal
         B, K = xyz.shape[0], xyz.shape[1]
         rows = data_dict["aggregated_vote_features"].reshape(B * K, -1)
-        rows = F.relu(bn_rows(conv1x1_rows(rows, head[0]), head[1], self.training))
-        rows = F.relu(bn_rows(conv1x1_rows(rows, head[3]), head[4], self.training))
-        net = conv1x1_rows(rows, head[6]).view(B, K, -1)
+        rows = fused_mlp.fused_mlp_maxpool(rows, rows.shape[1], B * K, 1, [(head[0], head[1]), (head[3], head[4])],
+                                           self.training, capture=False)
+        net = fused_mlp.linear_rows(rows, head[6].weight.view(head[6].weight.shape[0], -1), head[6].bias).view(B, K, -1)
         return self.decode_scores(net, data_dict)
 
     def decode_scores(self, net_transposed, data_dict):

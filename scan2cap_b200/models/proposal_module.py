@@ -10,9 +10,9 @@ import torch
 import torch.nn as nn
 
 from ..data.scannet.model_util_scannet import ScannetDatasetConfig
-import torch.nn.functional as F
 
-from ..lib.pointnet2.pointnet2_modules import PointnetSAModuleVotes, bn_rows, conv1x1_rows
+from ..lib.pointnet2 import fused_mlp
+from ..lib.pointnet2.pointnet2_modules import PointnetSAModuleVotes
 from ..utils.box_util import axis_aligned_corners
 
 DC = ScannetDatasetConfig()
@@ -45,13 +45,15 @@ class ProposalModule(nn.Module):
         data_dict["aggregated_vote_xyz"] = xyz
         data_dict["aggregated_vote_features"] = features.permute(0, 2, 1).contiguous()
         data_dict["aggregated_vote_inds"] = fps_inds
-        # the Conv1d/BN/ReLU head on the point-major (B*K, 128) rows (same arithmetic, no transposes)
+        # the Conv1d/BN/ReLU head on the point-major (B*K, 128) rows (same arithmetic, no transposes): the two BatchNorm
+        # layers as a fused stack on the tensor-core layer kernels, the last Conv1d (bias, no BatchNorm) as linear_rows
         head = self.proposal
         B, K = xyz.shape[0], xyz.shape[1]
         rows = data_dict["aggregated_vote_features"].reshape(B * K, -1)
-        rows = F.relu(bn_rows(conv1x1_rows(rows, head[0]), head[1], self.training))
-        rows = F.relu(bn_rows(conv1x1_rows(rows, head[3]), head[4], self.training))
-        net = conv1x1_rows(rows, head[6]).view(B, K, -1).transpose(2, 1)  # (B,97,K) view
+        rows = fused_mlp.fused_mlp_maxpool(rows, rows.shape[1], B * K, 1, [(head[0], head[1]), (head[3], head[4])],
+                                           self.training, capture=False)
+        net = fused_mlp.linear_rows(rows, head[6].weight.view(head[6].weight.shape[0], -1), head[6].bias)
+        net = net.view(B, K, -1).transpose(2, 1)  # (B,97,K) view
         return self.decode_scores(net, data_dict, self.num_class, self.num_heading_bin, self.num_size_cluster,
                                   self.mean_size_arr)
 

@@ -179,16 +179,18 @@ def test_fused_mlp_gap_layout_matches_torch_path(Cf, widths, ns, need_xyz):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("R,IN,OUT,bias", [(20480, 256, 128, True), (20480, 128, 128, True), (4096, 512, 256, False),
-                                           (3000, 64, 8, True)])
-def test_linear_tc_matches_float64(R, IN, OUT, bias):
-    """lib/linear_tc.py: library forward / dgrad, tensor-core weight gradient (column-blocked), column-sum bias grad."""
-    from scan2cap_b200.lib import linear_tc
+@pytest.mark.parametrize("R,IN,OUT,bias", [(8192, 256, 259, True), (2048, 128, 97, True), (20480, 128, 7, True),
+                                           (4096, 512, 256, False), (3000, 64, 8, True), (100, 128, 128, True)])
+def test_linear_rows_matches_float64(R, IN, OUT, bias):
+    """fused_mlp.linear_rows (final layers of the vote / proposal heads, edge_predict): forward, input gradient, weight
+    gradient on the tensor-core kernels, column-sum bias gradient; output widths padded to the kernels' tile widths."""
+    from scan2cap_b200.lib.pointnet2 import fused_mlp
     torch.manual_seed(R + IN)
     x = torch.randn(R, IN, device=DEV, requires_grad=True)
     lin = torch.nn.Linear(IN, OUT, bias=bias).to(DEV)
     g = torch.randn(R, OUT, device=DEV)
-    y = linear_tc.linear(x, lin.weight, lin.bias)
+    y = fused_mlp.linear_rows(x, lin.weight, lin.bias)
+    assert y.shape == (R, OUT)
     y.backward(g)
     xd = x.detach().double().requires_grad_(True)
     lind = torch.nn.Linear(IN, OUT, bias=bias).to(DEV).double()
@@ -200,3 +202,63 @@ def test_linear_tc_matches_float64(R, IN, OUT, bias):
     assert rel(lin.weight.grad, lind.weight.grad) < 2e-5
     if bias:
         assert rel(lin.bias.grad, lind.bias.grad) < 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("R,C,NOUT,conv_bias", [(8192, 256, 259, True), (2048, 128, 97, False)])
+def test_pointwise_head_matches_float64(R, C, NOUT, conv_bias, training):
+    """The Conv1d heads (voting_module.py:27-60 with conv biases in front of BatchNorm; proposal_module.py:46-78 without)
+    on the fused kernels vs a float64 evaluation with nn.Conv1d / nn.BatchNorm1d: outputs, running statistics, all
+    parameter gradients (the bias in front of a batch-statistics BatchNorm has an exactly zero gradient)."""
+    from scan2cap_b200.lib.pointnet2 import fused_mlp
+    torch.manual_seed(R + NOUT)
+    mk = lambda: (torch.nn.Conv1d(C, C, 1, bias=conv_bias), torch.nn.BatchNorm1d(C), torch.nn.Conv1d(C, C, 1, bias=conv_bias),
+                  torch.nn.BatchNorm1d(C), torch.nn.Conv1d(C, NOUT, 1))
+    ours = torch.nn.ModuleList(mk()).to(DEV)
+    for m in ours:
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.weight.data.uniform_(0.5, 1.5); m.bias.data.normal_(0, 0.2)
+            m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
+    ref = torch.nn.ModuleList(mk()).to(DEV).double()
+    ref.load_state_dict({k: (v.double() if v.is_floating_point() else v) for k, v in ours.state_dict().items()})
+    ours.train(training); ref.train(training)
+    x = torch.randn(R, C, device=DEV, requires_grad=True)
+    g = torch.randn(R, NOUT, device=DEV)
+    fused_mlp.CAPTURE = []
+    try:
+        h = fused_mlp.fused_mlp_maxpool(x, C, R, 1, [(ours[0], ours[1]), (ours[2], ours[3])], training)
+        cap = fused_mlp.CAPTURE[0]
+    finally:
+        fused_mlp.CAPTURE = None
+    y = fused_mlp.linear_rows(h, ours[4].weight.view(NOUT, C), ours[4].bias)
+    y.backward(g)
+    # the kernels' own ReLU decisions (an activation within fp32 rounding of zero may take the other branch; one such
+    # unit among 2 M moves the gradients by ~1e-3 relative -- a property of ReLU, not of the kernels)
+    masks = [(Y * sc + sh) > 0 for Y, (sc, sh) in zip(cap["Ys"], cap["affine"])]
+    xd = x.detach().double().requires_grad_(True)
+    t = xd.t().unsqueeze(0)                                   # (1, C, R)
+    pre1 = ref[1](ref[0](t))
+    t = pre1 * masks[0].t().unsqueeze(0).double()
+    pre2 = ref[3](ref[2](t))
+    t = pre2 * masks[1].t().unsqueeze(0).double()
+    for pre, m in ((pre1, masks[0]), (pre2, masks[1])):
+        flipped = (pre.detach().squeeze(0).t() > 0) != m
+        assert int(flipped.sum()) <= 50 and float(pre.detach().squeeze(0).t()[flipped].abs().max() if flipped.any() else 0.0) < 1e-5
+    yd = ref[4](t).squeeze(0).t()
+    yd.backward(g.double())
+    rel = lambda a, b: float((a.double() - b).norm() / b.norm().clamp_min(1e-30))
+    assert rel(y.detach(), yd.detach()) < 1e-5
+    assert rel(x.grad, xd.grad) < 1e-4
+    for (n, po), (_, pr) in zip(ours.named_parameters(), ref.named_parameters()):
+        if conv_bias and training and n in ("0.bias", "2.bias"):
+            # exactly zero in exact arithmetic; the float64 evaluation leaves rounding noise
+            scale = float(ref[4].bias.grad.norm())
+            assert float(po.grad.abs().max()) == 0.0 and float(pr.grad.norm()) < 1e-9 * scale, n
+            continue
+        assert rel(po.grad, pr.grad) < 1e-4, n
+    for (n, bo), (_, br) in zip(ours.named_buffers(), ref.named_buffers()):
+        if bo.is_floating_point():
+            assert rel(bo, br) < 1e-5, n
+        else:
+            assert torch.equal(bo, br), n

@@ -30,10 +30,11 @@ def _bn_coefficients(s1, s2, R, bn, training):
     return _ext_mlp.bn_finalize(s1, s2, R, bn, training)
 
 
-def _fold_conv_bias(bias, bn, training, scale, shift):
+def _fold_conv_bias(bias, bn, training, mean, scale, shift):
     """A conv bias in front of BatchNorm (the Conv1d heads of voting_module.py:27-31 / proposal_module.py:46-50): the
     GEMM runs without it.  Batch statistics: the normalised output does not depend on it, only the running mean does
-    (+ momentum * bias); running statistics: it moves the folded shift by scale * bias."""
+    (+ momentum * bias); running statistics: it moves the folded shift by scale * bias, and the mean the backward pass
+    centres the bias-free output with by -bias."""
     batch = training or not bn.track_running_stats
     if batch:
         if training and bn.track_running_stats:
@@ -42,8 +43,8 @@ def _fold_conv_bias(bias, bn, training, scale, shift):
                     bn.running_mean.add_(bias, alpha=float(bn.momentum))
                 else:
                     bn.running_mean.addcdiv_(bias, bn.num_batches_tracked.to(bias.dtype))
-        return scale, shift
-    return scale, torch.addcmul(shift, scale, bias)
+        return mean, scale, shift
+    return mean - bias.double(), scale, torch.addcmul(shift, scale, bias)
 
 
 def _first_layer_weight(W, K, lda, xyz_gap):
@@ -103,7 +104,7 @@ class _FusedMLPPool(Function):
             Y, s1, s2 = res if need_stats else (res, None, None)
             mean, invstd, scale, shift = _bn_coefficients(s1, s2, R, bns[l], training)
             if params[4 * l + 3] is not None:
-                scale, shift = _fold_conv_bias(params[4 * l + 3].detach(), bns[l], training, scale, shift)
+                mean, scale, shift = _fold_conv_bias(params[4 * l + 3].detach(), bns[l], training, mean, scale, shift)
             Ys.append(Y)
             coefs.append((mean, invstd, scale, shift))
             A, k = Y, W.shape[0]

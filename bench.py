@@ -242,14 +242,15 @@ class Ours(object):
         of a replayed graph).  SA1 (n = 40 000) is the only call of the step that takes the uniform-grid entry."""
         import scan2cap_b200._lib as L
         res = self.resident()
-        names = ("s2c_query_and_group_grid", "s2c_query_and_group")
+        names = ("s2c_query_and_group_grid_prebuilt", "s2c_query_and_group_grid", "s2c_query_and_group")
         L.TIMING = {n: [] for n in names}
         for _ in range(steps):
             timer.flush.zero_()
             self.engine.run_eager(dict(res))
         torch.cuda.synchronize()
         ev, kernel = [], None
-        for n, k in zip(names, ("grid_build_kernel + grid_query_kernel<GROUP>", "ball_query_kernel<GROUP>")):
+        for n, k in zip(names, ("group_rows_tma_kernel / grid_query_kernel<GROUP> (grid built ahead by TrainStep.prefetch)",
+                                "grid_build_kernel + grid_query_kernel<GROUP>", "ball_query_kernel<GROUP>")):
             if L.TIMING[n]:
                 per = len(L.TIMING[n]) // steps
                 ev = [e for i, e in enumerate(L.TIMING[n]) if i % per == 0]  # SA1 = the first call of every step
@@ -380,7 +381,7 @@ def run_ours(args, emit, rank, world, local_rank):
         if qg4_ms:
             rc132["product_layout"] = qg_roofline(
                 float(np.mean(qg4_ms)), qg4_kernel, c4.B, c4.N, c4.F - 3, pk, pk_src,
-                "inside the c4 training step; features are columns 3.. of point_clouds, 540-byte rows",
+                "inside the c4 training step; features = columns 3.. of the engine's 16-byte aligned point_clouds rows",
                 traffic=ncu_traffic("c4"))
         if rank == 0 and world == 1:
             t = standalone_qg(timer, 8, 40000, 132)
@@ -409,13 +410,26 @@ def run_ours(args, emit, rank, world, local_rank):
         "gpu_launches": launches,
         "clocks": clocks,
     }
+    # roofline of the kernel BASELINE.json's metric names (fused ball_query + group_points, nsample = 64).  The primary
+    # block is the shape where its bytes dominate -- BASELINE configs[3] (C = 132), timed inside the c4 training step of
+    # this same run; at the c3 shape (C = 4: 5 MB per scene, byte floor 6.5 us) the kernel is launch / latency bound and
+    # is reported as roofline_c3.
+    r_c3 = None
     if qg_ms:
-        line["roofline"] = qg_roofline(float(np.mean(qg_ms)), qg_kernel, main.B, main.N, main.F - 3, pk, pk_src,
-                                       "inside the training step", traffic=ncu_traffic(args.config))
+        r_c3 = qg_roofline(float(np.mean(qg_ms)), qg_kernel, main.B, main.N, main.F - 3, pk, pk_src,
+                           "inside the c3 training step", traffic=ncu_traffic(args.config))
     if second is not None:
         line["config4"] = second
-        if rc132:
-            line["roofline_c132"] = rc132
+        if rc132.get("product_layout"):
+            line["roofline"] = rc132["product_layout"]
+            if r_c3:
+                line["roofline_c3"] = r_c3
+            if rc132.get("aligned_layout"):
+                line["roofline_standalone"] = rc132["aligned_layout"]
+        elif r_c3:
+            line["roofline"] = r_c3
+    elif r_c3:
+        line["roofline"] = r_c3
     if predict is not None:
         line["predict"] = predict
     if not args.no_cpu_baseline and world == 1:

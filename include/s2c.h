@@ -260,6 +260,19 @@ S2C_API int s2c_query_and_group_grid(const float *xyz, const float *new_xyz, con
                                      int nsample, int normalize_xyz, int out_layout, int *idx, float *grouped,
                                      void *workspace, long long workspace_bytes, void *stream);
 
+/* ball_query_grid_build / query_and_group_grid_prebuilt -- the two halves of s2c_query_and_group_grid.  The uniform grid
+ *   depends only on (xyz, radius), so a caller that has the next batch's coordinates can build it ahead of time (e.g. on
+ *   a copy stream during the previous training step) and keep only the query / gather kernel on the critical path.
+ *   `workspace` (s2c_ball_query_grid_workspace_bytes(B, n) bytes) carries the grid; it holds no absolute pointers and
+ *   may be copied between equally aligned buffers.  Same arguments, same bit-identical results as the one-call form
+ *   (ball_query_gpu.cu:9-44 + group_points_gpu.cu:8-64 + pointnet2_utils.py:317-376). */
+S2C_API int s2c_ball_query_grid_build(const float *xyz, int B, int n, float radius, void *workspace,
+                                      long long workspace_bytes, void *stream);
+S2C_API int s2c_query_and_group_grid_prebuilt(const float *xyz, const float *new_xyz, const float *features, int B, int n,
+                                              int M, int C, int feat_layout, long long feat_stride, float radius,
+                                              int nsample, int normalize_xyz, int out_layout, int *idx, float *grouped,
+                                              void *workspace, long long workspace_bytes, void *stream);
+
 /* bn_finalize -- per-layer BatchNorm bookkeeping of the fused shared-MLP path in ONE launch (replaces nn.BatchNorm2d's
  *   statistics handling, lib/pointnet2/pytorch_utils.py:88-120 / torch batch_norm):
  *   use_batch_stats: mean = sum/R, var = max(sumsq/R - mean^2, 0) from the float64 column sums of the GEMM epilogue,

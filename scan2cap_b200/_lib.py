@@ -34,6 +34,9 @@ SIGNATURES = {
     "s2c_pool_bwd_stats": [P, P, P, c_ll, c_ll, c_int, c_int, P, P, P, P, P],
     "s2c_query_and_group_grid": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_ll, c_float, c_int, c_int, c_int, P, P,
                                  P, c_ll, P],
+    "s2c_ball_query_grid_build": [P, c_int, c_int, c_float, P, c_ll, P],
+    "s2c_query_and_group_grid_prebuilt": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_ll, c_float, c_int, c_int, c_int, P,
+                                          P, P, c_ll, P],
     "s2c_bn_finalize": [P, P, c_ll, c_int, P, P, ctypes.c_double, ctypes.c_double, c_int, c_int, P, P, P, P, P, P, P, P],
     "s2c_bn_backward_coeffs": [P, P, P, P, P, c_ll, c_int, c_int, P, P, P, P, P, P],
     "s2c_group_rows_grad": [P, c_ll, c_int, c_int, P, c_int, c_ll, c_int, c_float, P, P],

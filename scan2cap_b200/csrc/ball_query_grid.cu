@@ -609,11 +609,38 @@ extern "C" long long s2c_ball_query_grid_workspace_bytes(int B, int n) {
          (long long)B * kBuildCluster * 6 * 4 + 64 + 512;
 }
 
-extern "C" int s2c_query_and_group_grid(const float *xyz, const float *new_xyz, const float *features, int B, int n, int M,
-                                        int C, int feat_layout, long long feat_stride, float radius, int nsample,
-                                        int normalize_xyz, int out_layout, int *idx, float *grouped, void *workspace,
-                                        long long workspace_bytes, void *stream) {
-  using namespace s2c;
+namespace s2c {
+namespace {
+struct GridWorkspace {
+  GridParams *params; float4 *sorted; int *cell_start; int *cursor; float *bbox; unsigned int *counter;
+};
+GridWorkspace carve_grid(void *workspace, int B, int n) {
+  GridWorkspace w;
+  unsigned char *ws = (unsigned char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  w.params = (GridParams *)ws;
+  w.sorted = (float4 *)(ws + (size_t)B * 64);
+  w.cell_start = (int *)(w.sorted + (size_t)B * n);
+  w.cursor = w.cell_start + (size_t)B * (kMaxCells + 1);
+  w.bbox = (float *)(w.cursor + (size_t)B * kMaxCells);
+  w.counter = (unsigned int *)(w.bbox + (size_t)B * kBuildCluster * 6);
+  return w;
+}
+int launch_grid_build(const float *xyz, int B, int n, float radius, const GridWorkspace &w, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(B * kBuildCluster));
+  cfg.blockDim = dim3(kBuildThreads);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kBuildCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  S2C_CUDA(cudaLaunchKernelEx(&cfg, grid_build_kernel, xyz, n, radius, w.params, w.cell_start, w.sorted, w.cursor, w.bbox, w.counter), "grid_build launch");
+  return S2C_OK;
+}
+int query_and_group_grid_impl(const float *xyz, const float *new_xyz, const float *features, int B, int n, int M,
+                              int C, int feat_layout, long long feat_stride, float radius, int nsample,
+                              int normalize_xyz, int out_layout, int *idx, float *grouped, void *workspace,
+                              long long workspace_bytes, void *stream, bool prebuilt) {
   S2C_REQUIRE(B >= 0 && n >= 1 && M >= 0 && C >= 0, "query_and_group_grid: bad sizes");
   S2C_REQUIRE(nsample >= 1 && nsample <= 1024, "query_and_group_grid: nsample=%d outside [1,1024]", nsample);
   S2C_REQUIRE(radius > 0.f, "query_and_group_grid: radius must be positive");
@@ -625,23 +652,15 @@ extern "C" int s2c_query_and_group_grid(const float *xyz, const float *new_xyz, 
   S2C_REQUIRE(workspace_bytes >= s2c_ball_query_grid_workspace_bytes(B, n), "query_and_group_grid: workspace too small");
   S2C_REQUIRE(B <= 65535, "query_and_group_grid: B too large");
   cudaStream_t st = (cudaStream_t)stream;
-  unsigned char *ws = (unsigned char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-  GridParams *params = (GridParams *)ws;
-  float4 *sorted = (float4 *)(ws + (size_t)B * 64);
-  int *cell_start = (int *)(sorted + (size_t)B * n);
-  int *cursor = cell_start + (size_t)B * (kMaxCells + 1);
-  float *bbox = (float *)(cursor + (size_t)B * kMaxCells);
-  unsigned int *counter = (unsigned int *)(bbox + (size_t)B * kBuildCluster * 6);
-  {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(B * kBuildCluster));
-    cfg.blockDim = dim3(kBuildThreads);
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kBuildCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    S2C_CUDA(cudaLaunchKernelEx(&cfg, grid_build_kernel, xyz, n, radius, params, cell_start, sorted, cursor, bbox, counter), "grid_build launch");
+  const GridWorkspace gw = carve_grid(workspace, B, n);
+  GridParams *params = gw.params;
+  float4 *sorted = gw.sorted;
+  int *cell_start = gw.cell_start;
+  unsigned int *counter = gw.counter;
+  if (prebuilt) {  // the grid of these points / this radius is already in the workspace: only re-arm the work counter
+    S2C_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st), "query_and_group_grid counter reset");
+  } else {
+    if (int rc = launch_grid_build(xyz, B, n, radius, gw, st)) return rc;
   }
   GroupArgs ga = {};
   ga.features = features; ga.grouped = grouped; ga.C = C;
@@ -700,4 +719,38 @@ extern "C" int s2c_query_and_group_grid(const float *xyz, const float *new_xyz, 
   }
   S2C_CHECK_LAUNCH("grid_query");
   return S2C_OK;
+}
+}  // namespace
+}  // namespace s2c
+
+extern "C" int s2c_query_and_group_grid(const float *xyz, const float *new_xyz, const float *features, int B, int n, int M,
+                                        int C, int feat_layout, long long feat_stride, float radius, int nsample,
+                                        int normalize_xyz, int out_layout, int *idx, float *grouped, void *workspace,
+                                        long long workspace_bytes, void *stream) {
+  return s2c::query_and_group_grid_impl(xyz, new_xyz, features, B, n, M, C, feat_layout, feat_stride, radius, nsample,
+                                        normalize_xyz, out_layout, idx, grouped, workspace, workspace_bytes, stream, false);
+}
+
+// The uniform grid depends only on (xyz, radius): a caller that knows the next batch's coordinates can build it ahead of
+// time (s2c_ball_query_grid_build, e.g. on a copy stream during the previous training step) and run only the
+// query / gather kernel on the critical path (s2c_query_and_group_grid_prebuilt, same arguments and results as
+// s2c_query_and_group_grid; `workspace` must hold the grid built from the same xyz / B / n / radius).
+extern "C" int s2c_ball_query_grid_build(const float *xyz, int B, int n, float radius, void *workspace,
+                                         long long workspace_bytes, void *stream) {
+  using namespace s2c;
+  S2C_REQUIRE(B >= 0 && n >= 1, "ball_query_grid_build: bad sizes");
+  S2C_REQUIRE(radius > 0.f, "ball_query_grid_build: radius must be positive");
+  if (B == 0) return S2C_OK;
+  S2C_REQUIRE(xyz && workspace, "ball_query_grid_build: null pointer");
+  S2C_REQUIRE(workspace_bytes >= s2c_ball_query_grid_workspace_bytes(B, n), "ball_query_grid_build: workspace too small");
+  S2C_REQUIRE(B <= 65535, "ball_query_grid_build: B too large");
+  return launch_grid_build(xyz, B, n, radius, carve_grid(workspace, B, n), (cudaStream_t)stream);
+}
+
+extern "C" int s2c_query_and_group_grid_prebuilt(const float *xyz, const float *new_xyz, const float *features, int B, int n,
+                                                 int M, int C, int feat_layout, long long feat_stride, float radius,
+                                                 int nsample, int normalize_xyz, int out_layout, int *idx, float *grouped,
+                                                 void *workspace, long long workspace_bytes, void *stream) {
+  return s2c::query_and_group_grid_impl(xyz, new_xyz, features, B, n, M, C, feat_layout, feat_stride, radius, nsample,
+                                        normalize_xyz, out_layout, idx, grouped, workspace, workspace_bytes, stream, true);
 }

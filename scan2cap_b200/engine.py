@@ -123,6 +123,8 @@ class TrainStep(object):
             # static buffers of the sampling indices (filled by prefetch() on the copy stream, or by _load_indices())
             static["fps_precomputed"] = [(i.clone(), x.clone()) for i, x in
                                          self.model.backbone_net.sample_indices(static["point_clouds"][..., :3])]
+            # ... and of SA1's ball-query grid (a function of the coordinates only, built by the same prefetch)
+            static["sa1_grid"] = self.model.backbone_net.sa1_grid(static["point_clouds"][..., :3])
         # warm-up on a side stream (allocator / cuBLAS workspaces / lazy kernel loading), as capture requires;
         # no collective (ranks capture independently), and every side effect on the training state is undone
         snap = self._snapshot()
@@ -157,6 +159,11 @@ class TrainStep(object):
         """The same step issued kernel by kernel (used by bench.py to time single kernels with CUDA events)."""
         data = self._to_device(data_dict)
         data["num_words"] = self._words(data_dict)
+        if self.prefetch_indices and isinstance(data.get("point_clouds"), torch.Tensor):
+            # what prefetch() / run() put in front of the graph: sampling indices and SA1's grid from the coordinates
+            xyz = data["point_clouds"][..., :3].contiguous()
+            data["fps_precomputed"] = self.model.backbone_net.sample_indices(xyz)
+            data["sa1_grid"] = self.model.backbone_net.sa1_grid(xyz)
         self.last = self._step_eager(data)
         return self.last["loss"]
 
@@ -174,12 +181,16 @@ class TrainStep(object):
             if isinstance(v, torch.Tensor):
                 static[k].copy_(v, non_blocking=True)
 
-    def _load_indices(self, dst, point_clouds):
-        """FPS of all levels for `point_clouds` into the (inds, xyz) buffers `dst`, on the current stream."""
-        fresh = self.model.backbone_net.sample_indices(point_clouds[..., :3])
+    def _load_indices(self, dst, point_clouds, grid=None):
+        """FPS of all levels for `point_clouds` into the (inds, xyz) buffers `dst` and SA1's ball-query grid into
+        `grid`, on the current stream."""
+        xyz = point_clouds[..., :3].contiguous()
+        fresh = self.model.backbone_net.sample_indices(xyz)
         for (di, dx), (si, sx) in zip(dst, fresh):
             di.copy_(si, non_blocking=True)
             dx.copy_(sx, non_blocking=True)
+        if grid is not None:
+            self.model.backbone_net.sa1_grid(xyz, out=grid)
 
     # ---- public ----------------------------------------------------------------------------------------------
     def prefetch(self, data_dict):
@@ -214,7 +225,8 @@ class TrainStep(object):
                 if isinstance(v, torch.Tensor):
                     self._stage[sig][k].copy_(v, non_blocking=True)
             if self.prefetch_indices:
-                self._load_indices(self._stage[sig]["fps_precomputed"], self._stage[sig]["point_clouds"])
+                self._load_indices(self._stage[sig]["fps_precomputed"], self._stage[sig]["point_clouds"],
+                                   self._stage[sig].get("sa1_grid"))
         self._prefetched = (data_dict, sig)
 
     def run(self, data_dict):
@@ -247,7 +259,7 @@ class TrainStep(object):
         else:
             self._load(static, data_dict)
             if self.prefetch_indices:   # not prefetched: sample inline, in front of the graph
-                self._load_indices(static["fps_precomputed"], static["point_clouds"])
+                self._load_indices(static["fps_precomputed"], static["point_clouds"], static.get("sa1_grid"))
         self._prefetched = None
         g1.replay()
         if g2 is not None:

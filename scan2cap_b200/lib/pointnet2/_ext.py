@@ -190,9 +190,23 @@ def three_interpolate_grad(grad_out, idx, weight, m):
     return out
 
 
+def ball_query_grid_build(xyz, radius, out=None):
+    """The uniform grid of s2c_query_and_group_grid for (xyz (B,n,3), radius), built on the current stream into a uint8
+    workspace tensor (returned; `out` reuses a buffer of the same size).  Pass it to query_and_group(..., grid=ws)."""
+    _chk(xyz, "xyz", torch.float32)
+    B, n, _ = xyz.shape
+    ws_bytes = int(LIB.s2c_ball_query_grid_workspace_bytes(B, n))
+    ws = out if out is not None else torch.empty(ws_bytes, dtype=torch.uint8, device=xyz.device)
+    assert ws.numel() >= ws_bytes and ws.dtype == torch.uint8 and ws.is_contiguous() and ws.data_ptr() % 256 == 0
+    with _guard(xyz):
+        call("s2c_ball_query_grid_build", xyz.data_ptr(), B, n, float(radius), ws.data_ptr(), ws.numel(), _stream(xyz))
+    return ws
+
+
 def query_and_group(xyz, new_xyz, features, radius, nsample, normalize_xyz, feat_point_major=False,
-                    channels_last=False, pad4=False):
+                    channels_last=False, pad4=False, grid=None):
     """Fused QueryAndGroup.forward (use_xyz=True).  Returns (grouped, idx).
+    grid: workspace from ball_query_grid_build(xyz, radius) (the grid was built ahead of time; only the query runs).
 
     features: None, (B,C,n) [default] or, with feat_point_major, a (B,n,C) view whose last dim is
     contiguous (row stride may exceed C).  grouped: (B,3+C,M,ns) contiguous, or with channels_last the
@@ -225,7 +239,12 @@ def query_and_group(xyz, new_xyz, features, radius, nsample, normalize_xyz, feat
         grouped = torch.empty((B, 3 + C, M, int(nsample)), dtype=torch.float32, device=xyz.device)
     layout = (2 if pad4 else 1) if channels_last else 0
     with _guard(xyz):
-        if n >= GRID_MIN_POINTS and radius > 0:
+        if grid is not None:
+            assert grid.dtype == torch.uint8 and grid.data_ptr() % 256 == 0
+            call("s2c_query_and_group_grid_prebuilt", xyz.data_ptr(), new_xyz.data_ptr(), fptr, B, n, M, C, flayout,
+                 fstride, float(radius), int(nsample), 1 if normalize_xyz else 0, layout, idx.data_ptr(),
+                 grouped.data_ptr(), grid.data_ptr(), grid.numel(), _stream(xyz))
+        elif n >= GRID_MIN_POINTS and radius > 0:
             ws_bytes = LIB.s2c_ball_query_grid_workspace_bytes(B, n)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xyz.device)
             call("s2c_query_and_group_grid", xyz.data_ptr(), new_xyz.data_ptr(), fptr, B, n, M, C, flayout, fstride,

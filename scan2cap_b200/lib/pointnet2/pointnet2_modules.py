@@ -63,9 +63,10 @@ class PointnetSAModuleVotes(nn.Module):
         self.mlp_module = pt_utils.SharedMLP(mlp_spec, bn=bn)
 
     def forward(self, xyz: torch.Tensor, features: torch.Tensor = None, inds: torch.Tensor = None,
-                sampled_xyz: torch.Tensor = None):
+                sampled_xyz: torch.Tensor = None, grid: torch.Tensor = None):
         """xyz (B,N,3), features (B,C,N), inds (B,npoint) -> new_xyz (B,npoint,3), new_features (B,C',npoint),
-        inds (B,npoint) int32.  sampled_xyz (extension): xyz[inds] when the caller already has it (no gradient)."""
+        inds (B,npoint) int32.  Extensions: sampled_xyz = xyz[inds] when the caller already has it (no gradient);
+        grid = the ball-query grid of (xyz, self.radius) built ahead of time (_ext.ball_query_grid_build)."""
         layers = self.mlp_module.layer_params()
         if self.npoint is None or not self.use_xyz or self.ret_unique_cnt or self.pooling not in ("max", "avg", "rbf"):
             # GroupAll raises in the reference itself (pointnet2_utils.py:387-390 vs :422, SURVEY Appendix E);
@@ -86,7 +87,7 @@ class PointnetSAModuleVotes(nn.Module):
             new_xyz = torch.gather(xyz, 1, inds.long().unsqueeze(-1).expand(-1, -1, 3))
         feats_pm = point_major(features) if features is not None else None
         grouped, _ = pointnet2_utils.query_and_group(xyz, new_xyz, feats_pm, self.radius, self.nsample,
-                                                     self.normalize_xyz, True, True, True)
+                                                     self.normalize_xyz, True, True, True, grid=grid)
         B, C, M, ns = grouped.shape
         # rows of the 16-byte aligned channels-last buffer the kernel wrote: (R, Cp) = [xyz, 0 | features | pad]
         Cin = 3 + (feats_pm.shape[2] if feats_pm is not None else 0)

@@ -111,9 +111,11 @@ class _FusedQueryAndGroup(Function):
     """grouped (B,3+C,M,ns) = cat([ (xyz[idx]-new_xyz) * (1/r if normalize), features[idx] ]) in one kernel."""
 
     @staticmethod
-    def forward(ctx, xyz, new_xyz, features, radius, nsample, normalize_xyz, feat_point_major, channels_last, pad4):
+    def forward(ctx, xyz, new_xyz, features, radius, nsample, normalize_xyz, feat_point_major, channels_last, pad4,
+                grid=None):
         grouped, idx = _ext.query_and_group(xyz, new_xyz, features, radius, nsample, normalize_xyz,
-                                            feat_point_major=feat_point_major, channels_last=channels_last, pad4=pad4)
+                                            feat_point_major=feat_point_major, channels_last=channels_last, pad4=pad4,
+                                            grid=grid)
         ctx.idx = idx
         ctx.n = xyz.shape[1]
         ctx.scale = (1.0 / radius) if normalize_xyz else 1.0
@@ -142,7 +144,7 @@ class _FusedQueryAndGroup(Function):
                 g_feat = _ext_mlp.group_rows_grad(rows, ctx.feat_col, ctx.C, idx, n)  # (B,n,C)
                 if not ctx.feat_point_major:
                     g_feat = g_feat.transpose(1, 2)
-            return g_xyz, g_new, g_feat, None, None, None, None, None, None
+            return g_xyz, g_new, g_feat, None, None, None, None, None, None, None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             gx = grad[:, :3] * ctx.scale  # (B,3,M,ns)
             if ctx.needs_input_grad[0]:
@@ -153,13 +155,14 @@ class _FusedQueryAndGroup(Function):
             g_feat = _ext.group_points_grad(grad[:, ctx.feat_col:ctx.feat_col + ctx.C].contiguous(), idx, n)  # (B,C,n)
             if ctx.feat_point_major:
                 g_feat = g_feat.transpose(1, 2)
-        return g_xyz, g_new, g_feat, None, None, None, None, None, None
+        return g_xyz, g_new, g_feat, None, None, None, None, None, None, None
 
 
 def query_and_group(xyz, new_xyz, features, radius, nsample, normalize_xyz=False, feat_point_major=False,
-                    channels_last=False, pad4=False):
+                    channels_last=False, pad4=False, grid=None):
+    """grid: the uniform grid of (xyz, radius) built ahead of time (_ext.ball_query_grid_build), or None."""
     return _FusedQueryAndGroup.apply(xyz, new_xyz, features, radius, nsample, normalize_xyz, feat_point_major,
-                                     channels_last, pad4)
+                                     channels_last, pad4, grid)
 
 
 class QueryAndGroup(nn.Module):

@@ -84,6 +84,11 @@ class Pointnet2Backbone(nn.Module):
             out.append((inds, cur))
         return out
 
+    def sa1_grid(self, xyz, out=None):
+        """The uniform ball-query grid SA1 searches (depends only on the coordinates and SA1's radius): like the sampling
+        indices it can be built for batch i+1 while batch i is in flight and passed in as data_dict["sa1_grid"]."""
+        return _ext.ball_query_grid_build(xyz.contiguous(), self.sa1.radius, out=out)
+
     def forward(self, data_dict):
         pointcloud = data_dict["point_clouds"]
         xyz, features = self._break_up_pc(pointcloud)
@@ -93,7 +98,7 @@ class Pointnet2Backbone(nn.Module):
         if pre is not None:
             # sampled ahead of time (same kernels, same result): the 2 ms serial FPS chain is off the step's critical path
             (inds1, xyz1), ahead = pre[0], list(pre[1:])
-            xyz, features, fps_inds = self.sa1(xyz, features, inds1, sampled_xyz=xyz1)
+            xyz, features, fps_inds = self.sa1(xyz, features, inds1, sampled_xyz=xyz1, grid=data_dict.get("sa1_grid"))
         elif SAMPLE_AHEAD and xyz.is_cuda and not xyz.requires_grad:
             # FPS of all four levels up front: level 1 on this stream, levels 2-4 (8 CTAs each) on a side stream that
             # overlaps SA1's grouping and MLP; the streams join before SA2 (a fork/join the CUDA-graph capture keeps)

@@ -320,3 +320,23 @@ def test_ball_query_line_cloud(length, r, ext, oracle):
     new_xyz = xyz[:, rng.permutation(n)[:M]].copy()
     got = N(ext.ball_query(T(new_xyz), T(xyz), r, ns))
     np.testing.assert_array_equal(got, oracle.ball_query(new_xyz, xyz, r, ns))
+
+
+@pytest.mark.parametrize("C,ns", [(4, 64), (132, 64), (132, 16)])
+def test_prebuilt_grid_equals_one_call(C, ns, ext):
+    """s2c_ball_query_grid_build + s2c_query_and_group_grid_prebuilt (the grid built ahead of time, copied between
+    buffers, queried twice) == s2c_query_and_group_grid, bit for bit."""
+    g = torch.Generator().manual_seed(5)
+    B, n, M, r = 3, 20000, 1024, 0.25
+    xyz = (torch.rand(B, n, 3, generator=g) * torch.tensor([6.0, 5.0, 2.5])).to(DEV)
+    feats = torch.randn(B, n, C, generator=g).to(DEV)
+    inds, new_xyz = ext.furthest_point_sampling_with_xyz(xyz, M)
+    want_g, want_i = ext.query_and_group(xyz, new_xyz, feats, r, ns, True, feat_point_major=True, channels_last=True, pad4=True)
+    ws = ext.ball_query_grid_build(xyz, r)
+    ws2 = torch.empty_like(ws)
+    ws2.copy_(ws)                      # position independent: what TrainStep does between its staging and static buffers
+    for _ in range(2):                 # the work counter is re-armed by every prebuilt call
+        got_g, got_i = ext.query_and_group(xyz, new_xyz, feats, r, ns, True, feat_point_major=True, channels_last=True,
+                                           pad4=True, grid=ws2)
+        assert torch.equal(got_i, want_i)
+        assert torch.equal(got_g, want_g)

@@ -383,6 +383,17 @@ S2C_API int s2c_edgeconv_bwd(const float *dagg, const float *dmsg, long long Nn,
                              const float *b1, const float *W2, int Cout, const float *z, const float *Y1, float *dx,
                              float *dW1, float *db1, float *dW2, float *db2, void *workspace, void *stream);
 
+/* adam_step -- torch.optim.Adam (amsgrad=False, maximize=False) over ONE flat fp32 buffer each of parameters, gradients and
+ *   the two moments: the optimizer.step() of the reference's training loop (lib/solver.py:293-300; Adam created at
+ *   scripts/train.py:134) as one streaming pass instead of ~27 multi-tensor launches.
+ *     n        elements (multiple of 4; the caller pads the flat buffers), all four buffers 16-byte aligned
+ *     hyper    device [lr, beta1, beta2, eps, weight_decay] (read at run time: a captured graph follows lr changes)
+ *     steps    device [nsteps] float step counters (torch keeps one per parameter tensor, all equal): incremented here
+ *     coef     device [2] scratch
+ *     grad_scale  multiplies the gradient first (1/world for a summed all-reduce, else 1). */
+S2C_API int s2c_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, long long n,
+                          const float *hyper, float *steps, int nsteps, float *coef, float grad_scale, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

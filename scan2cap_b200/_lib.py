@@ -49,6 +49,7 @@ SIGNATURES = {
     "s2c_points_in_boxes_count": [P, c_ll, c_int, c_int, P, c_int, P, P],
     "s2c_nms3d": [P, P, P, P, c_int, c_int, ctypes.c_double, c_int, c_int, P, P],
     "s2c_knn_adjacency": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.c_double, P, P, P],
+    "s2c_adam_step": [P, P, P, P, c_ll, P, P, c_int, P, c_float, P],
     "s2c_edgeconv_fwd": [P, c_ll, c_int, P, P, P, c_ll, P, P, P, P, c_int, P, P, P, P, P, P],
     "s2c_edgeconv_bwd": [P, P, c_ll, c_int, P, P, P, c_ll, P, P, P, c_int, P, P, P, P, P, P, P, P, P],
 }

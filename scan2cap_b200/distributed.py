@@ -14,7 +14,8 @@ class FlatGradients(object):
         self.params = [p for p in module.parameters() if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
-        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        # padded to a multiple of 4 floats: the fused Adam kernel (optim.FlatAdam) walks the buffer as float4
+        self.flat = torch.zeros((n + 3) // 4 * 4, dtype=torch.float32, device=dev)
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)

@@ -25,6 +25,7 @@ import torch.distributed as dist
 from .distributed import FlatGradients
 from .lib.loss_helper import get_scene_cap_loss
 from .models.backbone_module import padded_point_clouds, padded_point_clouds_like
+from .optim import FlatAdam
 
 
 class TrainStep(object):
@@ -37,7 +38,8 @@ class TrainStep(object):
         self.device = next(model.parameters()).device
         self.flat = FlatGradients(model)
         self.use_graph = use_cuda_graph and self.device.type == "cuda"
-        self.opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay, capturable=self.use_graph)
+        # one fused kernel over flat parameter / gradient / moment buffers (optim.py); same state layout as torch's Adam
+        self.opt = FlatAdam(self.flat, lr=lr, weight_decay=weight_decay)
         self.loss_fn = loss_fn or get_scene_cap_loss
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.word_bucket = max(1, int(word_bucket))
@@ -261,6 +263,8 @@ class TrainStep(object):
             if self.prefetch_indices:   # not prefetched: sample inline, in front of the graph
                 self._load_indices(static["fps_precomputed"], static["point_clouds"], static.get("sa1_grid"))
         self._prefetched = None
+        if hasattr(self.opt, "sync_hyper"):
+            self.opt.sync_hyper()   # a learning-rate change reaches the captured Adam kernel through its device buffer
         g1.replay()
         if g2 is not None:
             self.flat.all_reduce_mean()

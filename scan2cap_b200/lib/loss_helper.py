@@ -160,8 +160,10 @@ def compute_node_orientation_loss(data_dict, num_bins=6):
     E = src.shape[1]
     source_rot = torch.gather(rot, 1, src.view(B, E, 1, 1).expand(-1, -1, 3, 3))
     target_rot = torch.gather(rot, 1, tar.view(B, E, 1, 1).expand(-1, -1, 3, 3))
-    relative_rot = torch.matmul(source_rot, target_rot.transpose(3, 2))
-    relative_rot = torch.acos(torch.clamp(0.5 * (torch.diagonal(relative_rot, dim1=-2, dim2=-1).sum(-1) - 1), -1, 1))
+    # trace(R_s R_t^T) = sum_ij R_s[i,j] R_t[i,j]: the reference forms the 3x3 products with a batched GEMM and sums the
+    # diagonal (loss_helper.py:286-287); one elementwise product + reduction gives the same trace without 20 480 tiny GEMMs
+    trace = (source_rot * target_rot).sum((-1, -2))
+    relative_rot = torch.acos(torch.clamp(0.5 * (trace - 1), -1, 1))
     labels = radian_to_label(relative_rot, num_bins)
     masks = (torch.gather(rot_masks, 1, src) * torch.gather(rot_masks, 1, tar)) * keep.to(rot_masks.dtype)
     loss = F.cross_entropy(edge_preds.reshape(B * E, -1), labels.reshape(-1), reduction="none")

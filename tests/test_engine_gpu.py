@@ -163,3 +163,45 @@ def test_solver_trains_on_synthetic_dataset():
     assert len(log["loss"]) == 12 and all(l == l for l in log["loss"])   # 3 epochs x 4 iterations, no NaN
     assert sum(log["loss"][-4:]) < sum(log["loss"][:4])                   # epoch 3 below epoch 1
     assert len(solver.engine._graphs) == 1
+
+
+def test_flat_adam_matches_torch_adam():
+    """optim.FlatAdam (one s2c_adam_step launch over flat buffers) vs torch.optim.Adam: parameters, moments and step
+    counters over several steps incl. a learning-rate change, weight decay, and a state_dict round trip."""
+    from scan2cap_b200.distributed import FlatGradients
+    from scan2cap_b200.optim import FlatAdam
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(37, 53), torch.nn.BatchNorm1d(53), torch.nn.Linear(53, 7)).to(DEV)
+    ref = copy.deepcopy(net)
+    flat = FlatGradients(net)
+    opt = FlatAdam(flat, lr=1e-3, weight_decay=1e-5)
+    ropt = torch.optim.Adam(ref.parameters(), lr=1e-3, weight_decay=1e-5)
+    assert flat.flat.numel() % 4 == 0 and all(p.data_ptr() >= opt.flat_param.data_ptr() for p in net.parameters())
+    rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-12))
+    for it in range(7):
+        if it == 4:
+            for o in (opt, ropt):
+                o.param_groups[0]["lr"] = 3e-4
+        x = torch.randn(64, 37, device=DEV)
+        for m, o in ((net, opt), (ref, ropt)):
+            o.zero_grad()
+            m(x).square().mean().backward()
+            o.step()
+        for (n, p), q in zip(net.named_parameters(), ref.parameters()):
+            assert rel(p, q) < 2e-6, (it, n)
+            assert p.grad is not None and p.grad.data_ptr() >= flat.flat.data_ptr()
+    for p, q in zip(net.parameters(), ref.parameters()):
+        a, b = opt.state[p], ropt.state[q]
+        assert int(a["step"]) == int(b["step"]) == 7
+        assert rel(a["exp_avg"], b["exp_avg"]) < 1e-5 and rel(a["exp_avg_sq"], b["exp_avg_sq"]) < 1e-5
+    # state_dict round trip: the loaded state lands in the flat buffers again
+    sd = copy.deepcopy(opt.state_dict())
+    before = opt.flat_exp_avg.clone()
+    opt.flat_exp_avg.zero_(); opt.steps.zero_()
+    opt.load_state_dict(sd)
+    assert torch.equal(opt.flat_exp_avg, before) and int(opt.steps[0]) == 7
+    p0 = next(net.parameters())
+    assert opt.state[p0]["exp_avg"].data_ptr() == opt.flat_exp_avg.data_ptr()
+    # a torch.optim.Adam state dict (the reference solver's checkpoints) loads too
+    opt.load_state_dict(copy.deepcopy(ropt.state_dict()))
+    assert int(opt.steps[0]) == 7 and rel(opt.state[p0]["exp_avg"], ropt.state[next(ref.parameters())]["exp_avg"]) == 0.0

@@ -9,18 +9,24 @@ import torch
 import torch.distributed as dist
 
 
+ALIGN = 64  # floats
+
+
 class FlatGradients(object):
     def __init__(self, module):
         self.params = [p for p in module.parameters() if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
-        # padded to a multiple of 4 floats: the fused Adam kernel (optim.FlatAdam) walks the buffer as float4
-        self.flat = torch.zeros((n + 3) // 4 * 4, dtype=torch.float32, device=dev)
-        off = 0
+        # every parameter's slice starts on a 256-byte boundary (the kernels read weights with 16-byte vector loads, and
+        # optim.FlatAdam lays the parameters themselves out the same way); the gaps stay zero.  The total is a multiple
+        # of 4 floats: the fused Adam kernel walks the buffer as float4.
+        self.offsets, off = [], 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
-        self.numel = n
+            self.offsets.append(off)
+            off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        for p, o in zip(self.params, self.offsets):
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
+        self.numel = sum(p.numel() for p in self.params)
 
     def zero_(self):
         self.flat.zero_()

@@ -29,22 +29,18 @@ class FlatAdam(torch.optim.Adam):
         self._coef = torch.zeros(2, dtype=torch.float32, device=dev)
         self._hyper = torch.zeros(5, dtype=torch.float32, device=dev)
         self._hyper_host = None
-        off = 0
         with torch.no_grad():
-            for p in params:
-                n = p.numel()
-                view = self.flat_param[off:off + n].view_as(p)
+            for p, off in zip(params, flat_grads.offsets):
+                view = self.flat_param[off:off + p.numel()].view_as(p)
                 view.copy_(p.data)
                 p.data = view           # the module keeps its Parameter objects; only their storage moves
-                off += n
         self._rehome_state(copy_from=None)
         self.sync_hyper()
 
     # ---- state: views into the flat moment buffers, in the layout torch.optim.Adam exposes ------------------------------
     def _rehome_state(self, copy_from):
-        off = 0
         with torch.no_grad():
-            for i, p in enumerate(self._params):
+            for i, (p, off) in enumerate(zip(self._params, self._flat_grads.offsets)):
                 n = p.numel()
                 views = {"step": self.steps[i], "exp_avg": self.flat_exp_avg[off:off + n].view_as(p),
                          "exp_avg_sq": self.flat_exp_avg_sq[off:off + n].view_as(p)}
@@ -54,7 +50,6 @@ class FlatAdam(torch.optim.Adam):
                         if k in old:
                             v.copy_(torch.as_tensor(old[k]).to(v.device, v.dtype))
                 self.state[p] = views
-                off += n
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)           # casts and copies: the loaded tensors replace the views ...

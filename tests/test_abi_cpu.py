@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared():
     txt = open(os.path.join(ROOT, "include", "s2c.h")).read()
-    return re.findall(r"S2C_API\s+(?:const\s+char\s*\*|int)\s*(s2c_\w+)\s*\(", txt)
+    return re.findall(r"S2C_API\s+(?:const\s+char\s*\*|int|long\s+long)\s*(s2c_\w+)\s*\(", txt)
 
 
 def test_library_exports_every_declared_symbol():
@@ -63,6 +63,24 @@ def test_argument_validation_of_the_fused_entry_points():
     assert L.s2c_gemm_tn(None, 8, None, 8, 4, 0, 8, None, 8, None, None) == 0                                           # M = 0: no-op
     assert L.s2c_col_sum(None, 4, 10, 8, None, None) == 1                                                                # lda < M
     assert L.s2c_ball_query_grid_workspace_bytes(8, 40000) > 8 * 40000 * 16
+    # round-2 entry points: EdgeConv, split grid build / prebuilt query, flat Adam
+    assert L.s2c_edgeconv_workspace_bytes(20480, 128, 128, 1) > 20480 * (128 + 128 + 256) * 4
+    assert L.s2c_edgeconv_workspace_bytes(20480, 128, 128, 0) < 4 * 1024 * 1024
+    rc = L.s2c_edgeconv_fwd(None, 10, 128, None, None, None, 5, None, None, None, None, 100, None, None, None, None, None, None)
+    assert rc == 1 and b"64, 128 or 256" in L.s2c_last_error()
+    rc = L.s2c_edgeconv_fwd(None, 10, 100, None, None, None, 5, None, None, None, None, 128, None, None, None, None, None, None)
+    assert rc == 1 and b"multiple of 64" in L.s2c_last_error()
+    rc = L.s2c_edgeconv_bwd(None, None, 10, 128, None, None, None, 5, None, None, None, 128, None, None, None, None, None, None,
+                            None, None, None)
+    assert rc == 1 and b"null" in L.s2c_last_error()
+    assert L.s2c_ball_query_grid_build(None, 2, 5000, ctypes.c_float(-1.0), None, 0, None) == 1 and b"radius" in L.s2c_last_error()
+    assert L.s2c_ball_query_grid_build(None, 0, 5000, ctypes.c_float(0.2), None, 0, None) == 0                           # B = 0: no-op
+    rc = L.s2c_query_and_group_grid_prebuilt(None, None, None, 1, 5000, 16, 0, 0, 0, ctypes.c_float(0.2), 0, 0, 0, None, None,
+                                             None, 0, None)
+    assert rc == 1 and b"nsample" in L.s2c_last_error()
+    assert L.s2c_adam_step(None, None, None, None, 10, None, None, 1, None, ctypes.c_float(1.0), None) == 1              # n % 4 != 0
+    assert b"multiple of 4" in L.s2c_last_error()
+    assert L.s2c_adam_step(None, None, None, None, 0, None, None, 1, None, ctypes.c_float(1.0), None) == 0               # n = 0: no-op
 
 
 def test_first_layer_weight_layouts_round_trip():

@@ -11,10 +11,12 @@ from ._ext import _guard, _stream
 KERNEL_VERSION = 2
 
 
-def mlp_layer_fwd(A, W, pro_scale=None, pro_shift=None, want_stats=True, K=None, version=None, out=None, col0=0):
+def mlp_layer_fwd(A, W, pro_scale=None, pro_shift=None, want_stats=True, K=None, version=None, out=None, col0=0,
+                  stats=None):
     """A (R, lda) fp32 (row stride lda >= K), W (N, K) -> C (R, N) = relu(A*scale+shift) @ W^T [no prologue when
     scale is None], plus float64 column sums / sums of squares of C when want_stats.  With `out` (R, >= col0+N) the
-    result is written to out[:, col0:col0+N]."""
+    result is written to out[:, col0:col0+N].  stats: a zero-filled float64 (2, >=N) buffer to accumulate the statistics
+    into (the caller zero-fills several layers' buffers with one launch); allocated here otherwise."""
     assert A.is_cuda and A.dtype == torch.float32 and A.dim() == 2 and A.stride(1) == 1
     W = W.contiguous()
     N, Kw = W.shape
@@ -26,8 +28,9 @@ def mlp_layer_fwd(A, W, pro_scale=None, pro_shift=None, want_stats=True, K=None,
     ldc, cptr = C.stride(0), C.data_ptr() + 4 * col0
     s1 = s2 = None
     if want_stats:
-        stats = torch.zeros((2, N), dtype=torch.float64, device=A.device)
-        s1, s2 = stats[0], stats[1]
+        if stats is None:
+            stats = torch.zeros((2, N), dtype=torch.float64, device=A.device)
+        s1, s2 = stats[0, :N], stats[1, :N]
     version = KERNEL_VERSION if version is None else version
     v2_ok = (N in (64, 128, 256) and K % 4 == 0 and lda % 4 == 0 and A.data_ptr() % 16 == 0 and K >= 4)
     with _guard(A):
@@ -60,14 +63,17 @@ def pool_fwd(Y, G, ns, scale, shift, want_argmax=True):
     return out, am
 
 
-def pool_bwd_stats(dpool, argmax, Y, ns, scale, shift):
-    """-> float64 (sum_g [N], sum_gy [N]) of the ReLU-masked pooled gradient routed to the arg-max elements."""
+def pool_bwd_stats(dpool, argmax, Y, ns, scale, shift, stats=None):
+    """-> float64 (sum_g [N], sum_gy [N]) of the ReLU-masked pooled gradient routed to the arg-max elements.
+    stats: optional zero-filled float64 (2, >=N) accumulator."""
     G, N = dpool.shape
-    stats = torch.zeros((2, N), dtype=torch.float64, device=Y.device)
+    if stats is None:
+        stats = torch.zeros((2, N), dtype=torch.float64, device=Y.device)
+    s1, s2 = stats[0, :N], stats[1, :N]
     with _guard(Y):
         call("s2c_pool_bwd_stats", dpool.data_ptr(), argmax.data_ptr(), Y.data_ptr(), Y.stride(0), G, ns, N,
-             scale.data_ptr(), shift.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), _stream(Y))
-    return stats[0], stats[1]
+             scale.data_ptr(), shift.data_ptr(), s1.data_ptr(), s2.data_ptr(), _stream(Y))
+    return s1, s2
 
 
 def bwd_data_supported(K, N):
@@ -75,7 +81,7 @@ def bwd_data_supported(K, N):
 
 
 def mlp_layer_bwd_data(Y, a, b, c, W, Yprev, prev_scale, prev_shift, G=None, dpool=None, argmax=None, ns=1,
-                       last_scale=None, last_shift=None, want_dY=True):
+                       last_scale=None, last_shift=None, want_dY=True, stats=None):
     """One layer's fused backward-data pass (see include/s2c.h).  Y (R,K) pre-BN output of layer l; W (K,N) its
     weight; Yprev (R,N) pre-BN output of layer l-1.  Gradient in: dense G (R,K) or (dpool, argmax) (R/ns, K).
     Returns g_prev (R,N), dY (R,K) or None, sum_g (N) f64, sum_gy (N) f64."""
@@ -85,15 +91,17 @@ def mlp_layer_bwd_data(Y, a, b, c, W, Yprev, prev_scale, prev_shift, G=None, dpo
     assert W.shape == (K, N)
     gprev = torch.empty((R, N), dtype=torch.float32, device=Y.device)
     dY = torch.empty((R, K), dtype=torch.float32, device=Y.device) if want_dY else None
-    stats = torch.zeros((2, N), dtype=torch.float64, device=Y.device)
+    if stats is None:
+        stats = torch.zeros((2, N), dtype=torch.float64, device=Y.device)
+    s1, s2 = stats[0, :N], stats[1, :N]
     wprep = torch.empty(((K + 31) // 32) * N * 256, dtype=torch.uint8, device=Y.device)
     ptr = lambda t: t.data_ptr() if t is not None else None
     with _guard(Y):
         call("s2c_mlp_layer_bwd_data", ptr(G), G.stride(0) if G is not None else 0, Y.data_ptr(), Y.stride(0), R, K,
              a.data_ptr(), b.data_ptr(), c.data_ptr(), ptr(dpool), ptr(argmax), int(ns), ptr(last_scale), ptr(last_shift),
              W.data_ptr(), N, Yprev.data_ptr(), Yprev.stride(0), prev_scale.data_ptr(), prev_shift.data_ptr(),
-             gprev.data_ptr(), N, ptr(dY), stats[0].data_ptr(), stats[1].data_ptr(), wprep.data_ptr(), _stream(Y))
-    return gprev, dY, stats[0], stats[1]
+             gprev.data_ptr(), N, ptr(dY), s1.data_ptr(), s2.data_ptr(), wprep.data_ptr(), _stream(Y))
+    return gprev, dY, s1, s2
 
 
 def mlp_layer_bwd_input(G, Y, a, b, c, W, col0, N, out, want_dY=True):
@@ -134,12 +142,12 @@ def wgrad_blocked_supported(C, P, *lds):
     return KERNEL_VERSION == 2 and C <= 256 and C % 4 == 0 and P % 4 == 0 and all(ld % 4 == 0 for ld in lds)
 
 
-def mlp_layer_bwd_weight_blocked(dY, X, P, xs=None, xh=None):
+def mlp_layer_bwd_weight_blocked(dY, X, P, xs=None, xh=None, out=None):
     """The same weight gradient for any width P: column blocks of the widest shape the tensor-core kernel holds
     (256 columns for C <= 128 output channels, 128 for C <= 256), each one launch over all rows."""
     R, C = dY.shape
     step = 256 if C <= 128 else 128
-    dW = torch.zeros((C, P), dtype=torch.float32, device=dY.device)
+    dW = torch.zeros((C, P), dtype=torch.float32, device=dY.device) if out is None else out
     for c0 in range(0, P, step):
         mlp_layer_bwd_weight(dY, X, min(step, P - c0), xs, xh, out=dW, col0=c0)
     return dW

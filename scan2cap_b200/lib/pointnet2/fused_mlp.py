@@ -64,6 +64,15 @@ def _first_layer_weight(W, K, lda, xyz_gap):
     return W, K
 
 
+def _first_layer_width(K, lda, xyz_gap):
+    """Column count K' of _first_layer_weight(W, K, lda, xyz_gap) without building it."""
+    if xyz_gap:
+        return lda
+    if K % 4 != 0 and lda >= (K + 3) // 4 * 4:
+        return (K + 3) // 4 * 4
+    return K
+
+
 def _first_layer_weight_grad(dWp, K, xyz_gap):
     """inverse column mapping of _first_layer_weight for the gradient."""
     if xyz_gap:
@@ -95,12 +104,13 @@ class _FusedMLPPool(Function):
         R = rows.shape[0]
         Ys, coefs = [], []
         A, scale, shift, k = rows, None, None, K
+        zstats = torch.zeros((L, 2, 256), dtype=torch.float64, device=rows.device)  # all layers' statistics: one fill
         for l in range(L):
             W = params[4 * l].reshape(params[4 * l].shape[0], -1)
             need_stats = training or not bns[l].track_running_stats
             if l == 0:  # the weight in the column layout of the rows (zero columns where the rows are padding)
                 W, k = _first_layer_weight(W, K, A.shape[1], xyz_gap)
-            res = _ext_mlp.mlp_layer_fwd(A, W, scale, shift, want_stats=need_stats, K=k)
+            res = _ext_mlp.mlp_layer_fwd(A, W, scale, shift, want_stats=need_stats, K=k, stats=zstats[l])
             Y, s1, s2 = res if need_stats else (res, None, None)
             mean, invstd, scale, shift = _bn_coefficients(s1, s2, R, bns[l], training)
             if params[4 * l + 3] is not None:
@@ -129,6 +139,17 @@ class _FusedMLPPool(Function):
         grads = [None] * (4 * L)
         dpool = dpool.contiguous()
         grad_rows = None
+        # one zero-fill for every statistics accumulator of this backward pass, one for all weight gradients
+        zstats = torch.zeros((L + 1, 2, 256), dtype=torch.float64, device=rows.device)
+        wshapes = []
+        for l in range(L):
+            Wl = params[4 * l].reshape(params[4 * l].shape[0], -1)
+            wshapes.append((Wl.shape[0], _first_layer_width(K, rows.shape[1], xyz_gap) if l == 0 else Wl.shape[1]))
+        zdw = torch.zeros(sum(c * p for c, p in wshapes), dtype=torch.float32, device=rows.device)
+        woff = [0]
+        for c, p in wshapes:
+            woff.append(woff[-1] + c * p)
+        dw_buf = lambda l: zdw[woff[l]:woff[l + 1]].view(wshapes[l])
 
         def affine(l, sum_g, sum_gy):
             """BatchNorm backward of layer l as dY = a*g + b*y + c; also its gamma / beta gradients."""
@@ -146,7 +167,7 @@ class _FusedMLPPool(Function):
         # last layer: its masked gradient is the pooled gradient at the arg-max sample -> sums straight from dpool
         l = L - 1
         _, _, sc_l, sh_l = coefs[l]
-        sum_g, sum_gy = _ext_mlp.pool_bwd_stats(dpool, argmax, Ys[l], ns, sc_l, sh_l)
+        sum_g, sum_gy = _ext_mlp.pool_bwd_stats(dpool, argmax, Ys[l], ns, sc_l, sh_l, stats=zstats[L])
         g = None  # dense masked gradient of layer l (None while it is still "pooled")
         while l >= 0:
             W = params[4 * l].reshape(params[4 * l].shape[0], -1)
@@ -158,14 +179,16 @@ class _FusedMLPPool(Function):
                 if g is None:
                     g_prev, dY, sum_g, sum_gy = _ext_mlp.mlp_layer_bwd_data(
                         Y, a, b, c, W, Ys[l - 1], sc_p, sh_p, dpool=dpool, argmax=argmax, ns=ns, last_scale=coefs[l][2],
-                        last_shift=coefs[l][3])
+                        last_shift=coefs[l][3], stats=zstats[l - 1])
                 else:
-                    g_prev, dY, sum_g, sum_gy = _ext_mlp.mlp_layer_bwd_data(Y, a, b, c, W, Ys[l - 1], sc_p, sh_p, G=g)
+                    g_prev, dY, sum_g, sum_gy = _ext_mlp.mlp_layer_bwd_data(Y, a, b, c, W, Ys[l - 1], sc_p, sh_p, G=g,
+                                                                            stats=zstats[l - 1])
                 if _ext_mlp.bwd_weight_supported(Y.shape[1], Ys[l - 1].shape[1], dY.stride(0), Ys[l - 1].stride(0)):
-                    grads[4 * l] = _ext_mlp.mlp_layer_bwd_weight(dY, Ys[l - 1], Ys[l - 1].shape[1], sc_p, sh_p).view_as(params[4 * l])
+                    grads[4 * l] = _ext_mlp.mlp_layer_bwd_weight(dY, Ys[l - 1], Ys[l - 1].shape[1], sc_p, sh_p,
+                                                                 out=dw_buf(l)).view_as(params[4 * l])
                 elif _ext_mlp.wgrad_blocked_supported(Y.shape[1], Ys[l - 1].shape[1], dY.stride(0), Ys[l - 1].stride(0)):
                     grads[4 * l] = _ext_mlp.mlp_layer_bwd_weight_blocked(dY, Ys[l - 1], Ys[l - 1].shape[1], sc_p,
-                                                                        sh_p).view_as(params[4 * l])
+                                                                        sh_p, out=dw_buf(l)).view_as(params[4 * l])
                 else:
                     Xp = torch.relu_(torch.addcmul(sh_p, Ys[l - 1], sc_p))
                     grads[4 * l] = (dY.t() @ Xp).view_as(params[4 * l])
@@ -181,7 +204,7 @@ class _FusedMLPPool(Function):
                     if (not ctx.needs_input_grad[0] and
                             _ext_mlp.bwd_weight_supported(Y.shape[1], Kp, g.stride(0), Y.stride(0), rows.stride(0))):
                         # no gradient w.r.t. the input (SA1): dY is formed inside the weight-gradient kernel
-                        dWp = _ext_mlp.mlp_layer_bwd_weight(g, rows, Kp, a=a, b=b, c=c, Y=Y)
+                        dWp = _ext_mlp.mlp_layer_bwd_weight(g, rows, Kp, a=a, b=b, c=c, Y=Y, out=dw_buf(0))
                         grads[0] = _first_layer_weight_grad(dWp, K, xyz_gap).reshape(params[0].shape)
                         break
                     if blocks is not None and _ext_mlp.bwd_data_supported(Y.shape[1], 64):
@@ -199,9 +222,9 @@ class _FusedMLPPool(Function):
                             if rows.shape[1] > 4 + K - 3:
                                 grad_rows[:, 4 + K - 3:] = 0.0
                         if _ext_mlp.bwd_weight_supported(Y.shape[1], Kp, dY.stride(0), rows.stride(0)):
-                            dWp = _ext_mlp.mlp_layer_bwd_weight(dY, rows, Kp)
+                            dWp = _ext_mlp.mlp_layer_bwd_weight(dY, rows, Kp, out=dw_buf(0))
                         elif _ext_mlp.wgrad_blocked_supported(Y.shape[1], Kp, dY.stride(0), rows.stride(0)):
-                            dWp = _ext_mlp.mlp_layer_bwd_weight_blocked(dY, rows, Kp)
+                            dWp = _ext_mlp.mlp_layer_bwd_weight_blocked(dY, rows, Kp, out=dw_buf(0))
                         else:
                             dWp = dY.t() @ rows[:, :Kp]
                         grads[0] = _first_layer_weight_grad(dWp, K, xyz_gap).reshape(params[0].shape)

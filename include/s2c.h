@@ -184,6 +184,12 @@ S2C_API int s2c_mlp_layer_fwd_v2(const float *A, long long lda, long long R, int
                                  const float *pro_shift, const float *W, int N, float *C, long long ldc,
                                  double *stat_sum, double *stat_sumsq, void *wprep, void *stream);
 
+/* mlp_probe -- profiling aid of the layer kernels (mlp_layer_fwd_v2 / bwd_data / bwd_input): CTA 0 of every following
+ *   launch stamps clock64() at its pipeline hand-offs (loader / transform / MMA / epilogue warps) into buf (device memory,
+ *   `capacity` 8-byte slots; slot layout at S2C_PROBE in csrc/mlp2.cu).  buf = NULL switches it off (the default).
+ *   No reference counterpart; used by tools/mlp_pipe_probe.py. */
+S2C_API int s2c_mlp_probe(unsigned long long *buf, int capacity);
+
 /* mlp_layer_bwd_data -- backward "data" pass of one shared-MLP layer l on the tensor cores (same pipeline as
  *   mlp_layer_fwd_v2), fusing BatchNorm backward, the 1x1-conv data gradient, the previous layer's ReLU mask and the
  *   reductions of the previous layer's BatchNorm backward:
@@ -342,6 +348,14 @@ S2C_API int s2c_caption_decode_bwd(const s2c_caption_params *params, void *strea
  *   recurrence (caption_module.py:428-500).  colsum (M), optional: column sums of A (the bias gradients). */
 S2C_API int s2c_gemm_tn(const float *A, long long lda, const float *X, long long ldx, int R, int M, int N, float *out,
                         long long ldo, float *colsum, void *stream);
+
+/* gemm -- C (M,N; ldc) = A (M,K) * B (K,N) [+ bias[n]] [ReLU], plain fp32 FMAs, operands as strided views
+ *   A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn].  The nn.Linear layers of the caption module whose widths
+ *   (300 / 812 / 3500) are not multiples of the tensor-core tiles -- map_feat, the word / target terms of map_topdown,
+ *   classifier (models/caption_module.py:216-240) -- forward (B = W^T: sbk = 1, sbn = ldw) and input gradient
+ *   (B = W: sbk = ldw, sbn = 1); their weight gradients are s2c_gemm_tn.  Replaces the framework's cuBLAS calls. */
+S2C_API int s2c_gemm(const float *A, long long sam, long long sak, const float *B, long long sbk, long long sbn,
+                     const float *bias, int relu, int M, int N, int K, float *C, long long ldc, void *stream);
 
 /* mlp_layer_bwd_input -- input gradient of the FIRST layer of a shared MLP on the tensor cores:
  *       C (R, N; ldc) = (a*G + b*Y + c) * W[:, block of N columns]

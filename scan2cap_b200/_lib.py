@@ -27,6 +27,7 @@ SIGNATURES = {
                             P, P, P],
     "s2c_mlp_layer_fwd": [P, c_ll, c_ll, c_int, P, P, P, c_int, P, c_ll, P, P, P],
     "s2c_mlp_layer_fwd_v2": [P, c_ll, c_ll, c_int, P, P, P, c_int, P, c_ll, P, P, P, P],
+    "s2c_mlp_probe": [P, c_int],
     "s2c_mlp_layer_bwd_data": [P, c_ll, P, c_ll, c_ll, c_int, P, P, P, P, P, c_int, P, P, P, c_int, P, c_ll, P, P, P, c_ll,
                                P, P, P, P, P],
     "s2c_mlp_layer_bwd_weight": [P, c_ll, P, c_ll, P, P, P, P, c_ll, P, P, c_ll, c_int, c_int, P, c_ll, P],
@@ -43,6 +44,7 @@ SIGNATURES = {
     "s2c_mlp_layer_bwd_input": [P, c_ll, P, c_ll, c_ll, c_int, P, P, P, P, c_ll, c_int, P, c_ll, P, P, P],
     "s2c_col_sum": [P, c_ll, c_ll, c_int, P, P],
     "s2c_gemm_tn": [P, c_ll, P, c_ll, c_int, c_int, c_int, P, c_ll, P, P],
+    "s2c_gemm": [P, c_ll, c_ll, P, c_ll, c_ll, P, c_int, c_int, c_int, c_int, P, c_ll, P],
     "s2c_caption_decode_fwd": [P, P],
     "s2c_caption_decode_bwd": [P, P],
     "s2c_detection_loss": [c_int] * 8 + [P, P, P, c_ll] + [P] * 22,

@@ -16,7 +16,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 32;
-constexpr int OS = 2;  // operand stages
+constexpr int kMaxOS = 4, kMaxWS = 8, kMaxRS = 8;  // ring depths are chosen per shape by the host (choose_pipe)
 constexpr int kLoaderWarp = 0, kMmaWarp = 1, kFirstTransformWarp = 2, kFirstEpilogueWarp = 6;
 constexpr int kThreads = 10 * 32;
 
@@ -39,8 +39,21 @@ struct Gemm2Args {
   const float *Yprev; long long ldyp; const float *e_scale, *e_shift;  // EPI_MASK_STATS
   double *stat_sum; double *stat_sumsq;
   long long R;
-  int RS;  // raw stages
+  int RS;    // raw-tile ring depth (TMA -> transform warps)
+  int OS;    // A-operand ring depth (transform warps -> MMA)
+  int WS;    // weight-chunk ring depth (TMA -> MMA); decoupled from the A ring so weight chunks are prefetched WS chunks
+             // ahead instead of only after the MMAs that last used their operand stage have retired
+  int wres;  // 1: WS == number of K chunks, every chunk is loaded ONCE and stays resident for all tiles of the CTA
+  unsigned long long *probe; int probe_cap;  // optional profiling aid (s2c_mlp_probe): clock64 stamps of CTA 0's roles
 };
+
+// probe slots: [0] kernel start; chunk i (i < 64): 16 + 16*i + {0: transform begins waiting, 1: raw tile landed, 2: operand
+// stage free, 3: operand staged, 4: MMA warp saw operand + weights, 5: MMAs issued, 6: raw TMA issued, 7: weight TMA issued};
+// tile t: 16 + 16*t + {8: accumulator complete (epilogue), 9: epilogue done}
+#define S2C_PROBE(slot)                                                                                   \
+  do {                                                                                                    \
+    if (g.probe != nullptr && blockIdx.x == 0 && (slot) < g.probe_cap) g.probe[(slot)] = (unsigned long long)clock64(); \
+  } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -113,6 +126,35 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// the same load without the wait: the registers are valid only after tmem_ld_wait(v) -- lets the epilogue fetch the next
+// column block from TMEM while it transposes / stores the current one
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float *v) {
+  uint32_t *u = reinterpret_cast<uint32_t *>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+        "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+        "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+      : "r"(taddr)
+      : "memory");
+}
+// wait for the outstanding tcgen05.ld; the "+r" operands tie the loaded registers to the wait so that no use of them
+// can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(float *v) {
+  uint32_t *u = reinterpret_cast<uint32_t *>(v);
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(u[0]), "+r"(u[1]), "+r"(u[2]), "+r"(u[3]), "+r"(u[4]), "+r"(u[5]), "+r"(u[6]), "+r"(u[7]), "+r"(u[8]),
+                 "+r"(u[9]), "+r"(u[10]), "+r"(u[11]), "+r"(u[12]), "+r"(u[13]), "+r"(u[14]), "+r"(u[15])
+               :
+               : "memory");
+  asm volatile(""
+               : "+r"(u[16]), "+r"(u[17]), "+r"(u[18]), "+r"(u[19]), "+r"(u[20]), "+r"(u[21]), "+r"(u[22]), "+r"(u[23]),
+                 "+r"(u[24]), "+r"(u[25]), "+r"(u[26]), "+r"(u[27]), "+r"(u[28]), "+r"(u[29]), "+r"(u[30]), "+r"(u[31])
+               :
+               : "memory");
 }
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {  // K-major SWIZZLE_128B, SBO = 1024 B, version 1
   return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
@@ -187,7 +229,6 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
   extern __shared__ __align__(1024) unsigned char smem[];
   constexpr uint32_t A_BYTES = BM * BK * 4;            // 16 KB per hi / lo / raw block
   constexpr uint32_t W_BYTES = N * BK * 4;             // N x 128 B per hi / lo block
-  constexpr uint32_t OP_BYTES = 2 * A_BYTES + 2 * W_BYTES;
   constexpr uint32_t RAW_TILES = (PRO == PRO_AFFINE2) ? 2 : 1;   // raw tiles per chunk (g and y for the affine prologue)
   // PRO_POOL: every raw stage also carries the [GT groups x 32 channels] slabs of argmax (int32) and dpool (fp32) that
   // cover the tile's rows, fetched by the TMA engine with the y tile -- the transform warps never touch global memory
@@ -195,22 +236,25 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
   const uint32_t RAW_BYTES = RAW_TILES * A_BYTES + 2 * SLAB_BYTES;
   constexpr int NPRO = (PRO == PRO_BNRELU) ? 2 : (PRO == PRO_AFFINE2) ? 3 : 5;
   constexpr uint32_t TMEM_COLS = (2 * N <= 32) ? 32 : (2 * N <= 64) ? 64 : (2 * N <= 128) ? 128 : (2 * N <= 256) ? 256 : 512;
-  const int RS = g.RS;
+  const int RS = g.RS, OS = g.OS, WS = g.WS;
+  const bool wres = g.wres != 0;
   const int KC = (g.K + BK - 1) / BK;
-  unsigned char *op_base = smem;
-  unsigned char *raw_base = smem + OS * OP_BYTES;
+  unsigned char *a_base = smem;                                  // OS x [A hi | A lo]
+  unsigned char *w_base = smem + (size_t)OS * 2 * A_BYTES;      // WS x [W hi | W lo]
+  unsigned char *raw_base = w_base + (size_t)WS * 2 * W_BYTES;  // RS x raw stage
   float *s_pro = reinterpret_cast<float *>(raw_base + (size_t)RS * RAW_BYTES);  // [NPRO][KC*BK] coefficients
   float *s_epi = s_pro + NPRO * KC * BK;                                         // [4 warps][32 rows][36] epilogue staging
   uint64_t *bars = reinterpret_cast<uint64_t *>(s_epi + 4 * 32 * 36);
-  uint64_t *raw_full = bars, *raw_empty = bars + 8, *op_full = bars + 16, *op_empty = bars + 18, *acc_full = bars + 20,
-           *acc_empty = bars + 22;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 24);
+  uint64_t *raw_full = bars, *raw_empty = bars + 8, *op_full = bars + 16, *op_empty = bars + 20, *acc_full = bars + 24,
+           *acc_empty = bars + 26, *w_full = bars + 28, *w_empty = bars + 36;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 44);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool has_pro = g.p0 != nullptr;
   if (tid == 0) {
     for (int s = 0; s < RS; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 128); }
-    for (int s = 0; s < OS; ++s) { mbar_init(&op_full[s], 129); mbar_init(&op_empty[s], 1); }
+    for (int s = 0; s < OS; ++s) { mbar_init(&op_full[s], 128); mbar_init(&op_empty[s], 1); }
+    for (int s = 0; s < WS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -227,23 +271,30 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (tid == 0) S2C_PROBE(0);
   const uint32_t tmem_base = *tmem_slot;
   const long long num_tiles = (g.R + BM - 1) / BM;
   const long long my_tiles = (num_tiles > (long long)blockIdx.x) ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const long long total_chunks = my_tiles * KC;
 
   if (warp == kLoaderWarp) {
-    // ===================== loader: raw activation rows (ring of RS) and weight chunks (into the operand stage)
+    // ===================== loader: raw activation rows (ring of RS) and weight chunks (ring of WS, or resident)
     if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
     long long ia = 0, iw = 0;          // next raw chunk / next weight chunk to issue
     long long ta = blockIdx.x; int ka = 0;  // (tile, kc) of chunk ia
     int kw = 0;
-    while (ia < total_chunks || iw < total_chunks) {
+    const long long w_total = wres ? (total_chunks < KC ? total_chunks : (long long)KC) : total_chunks;
+    // The warp shares its scheduler with a transform and an epilogue warp: it must not spin.  When only raw chunks are
+    // left to issue (always, once resident weights are in) it blocks on the stage's mbarrier (try_wait suspends the warp
+    // in hardware); while both rings are being fed it polls them alternately with a sleep between unsuccessful rounds.
+    while (ia < total_chunks || iw < w_total) {
+      bool progressed = false;
       if (ia < total_chunks) {
         const int rs = (int)(ia % RS);
         // lane 0 polls and broadcasts: the decision (and the counters below) must be warp-uniform
         if (ia < RS || __shfl_sync(0xffffffffu, lane == 0 ? (int)mbar_test(&raw_empty[rs], (uint32_t)(((ia / RS) - 1) & 1)) : 0, 0)) {
           if (lane == 0) {
+            S2C_PROBE(16 + 16 * (int)ia + 6);
             mbar_arrive_expect_tx(&raw_full[rs], RAW_BYTES);
             unsigned char *dst = raw_base + (size_t)rs * RAW_BYTES;
             if (PRO == PRO_POOL) {  // y tile + the pooled-gradient slabs of the tile's groups; g is rebuilt from them
@@ -259,37 +310,49 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
           __syncwarp();
           ++ia;
           if (++ka == KC) { ka = 0; ta += gridDim.x; }
+          progressed = true;
         }
       }
-      if (iw < total_chunks) {
-        const int os = (int)(iw % OS);
-        if (iw < OS || __shfl_sync(0xffffffffu, lane == 0 ? (int)mbar_test(&op_empty[os], (uint32_t)(((iw / OS) - 1) & 1)) : 0, 0)) {
+      if (iw < w_total) {
+        const int ws = (int)(iw % WS);
+        if (iw < WS || __shfl_sync(0xffffffffu, lane == 0 ? (int)mbar_test(&w_empty[ws], (uint32_t)(((iw / WS) - 1) & 1)) : 0, 0)) {
           if (lane == 0) {
-            unsigned char *dst = op_base + (size_t)os * OP_BYTES + 2 * A_BYTES;
-            mbar_arrive_expect_tx(&op_full[os], 2 * W_BYTES);
-            bulk_g2s(dst, g.wprep + (size_t)kw * 2 * W_BYTES, 2 * W_BYTES, &op_full[os]);
+            S2C_PROBE(16 + 16 * (int)iw + 7);
+            unsigned char *dst = w_base + (size_t)ws * 2 * W_BYTES;
+            mbar_arrive_expect_tx(&w_full[ws], 2 * W_BYTES);
+            bulk_g2s(dst, g.wprep + (size_t)kw * 2 * W_BYTES, 2 * W_BYTES, &w_full[ws]);
           }
           __syncwarp();
           ++iw;
           if (++kw == KC) kw = 0;
+          progressed = true;
         }
+      }
+      if (!progressed) {
+        if (iw >= w_total) mbar_wait(&raw_empty[(int)(ia % RS)], (uint32_t)(((ia / RS) - 1) & 1));
+        else if (ia >= total_chunks) mbar_wait(&w_empty[(int)(iw % WS)], (uint32_t)(((iw / WS) - 1) & 1));
+        else __nanosleep(64);
       }
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer
     const uint32_t idesc = make_idesc(BM, N);
-    long long it = 0;
+    int os = 0, ws = 0;
+    uint32_t oph = 0, wph = 0;  // phase parities of the A-operand / weight rings
+    int pit = 0;
     for (long long t = 0; t < my_tiles; ++t) {
       const int ab = (int)(t & 1);
       if (t >= 2) mbar_wait(&acc_empty[ab], (uint32_t)(((t >> 1) - 1) & 1));
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(ab * N);
-      for (int kc = 0; kc < KC; ++kc, ++it) {
-        const int os = (int)(it % OS);
-        mbar_wait(&op_full[os], (uint32_t)((it / OS) & 1));
+      for (int kc = 0; kc < KC; ++kc) {
+        mbar_wait(&op_full[os], oph);
+        mbar_wait(&w_full[ws], wres ? 0u : wph);  // resident chunks complete phase 0 once and stay valid
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t ah = smem_u32(op_base + (size_t)os * OP_BYTES), al = ah + A_BYTES, bh = al + A_BYTES, bl = bh + W_BYTES;
+          S2C_PROBE(16 + 16 * pit + 4);
+          const uint32_t ah = smem_u32(a_base + (size_t)os * 2 * A_BYTES), al = ah + A_BYTES;
+          const uint32_t bh = smem_u32(w_base + (size_t)ws * 2 * W_BYTES), bl = bh + W_BYTES;
 #pragma unroll
           for (int j = 0; j < BK / 8; ++j) {
             const uint32_t o = j * 32;
@@ -298,9 +361,14 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
             umma_tf32(d_tmem, make_desc(al + o), make_desc(bh + o), idesc, 1u);
           }
           umma_commit(&op_empty[os]);
+          if (!wres) umma_commit(&w_empty[ws]);
           if (kc == KC - 1) umma_commit(&acc_full[ab]);
+          S2C_PROBE(16 + 16 * pit + 5);
         }
         __syncwarp();
+        ++pit;
+        if (++os == OS) { os = 0; oph ^= 1u; }
+        if (++ws == WS) { ws = 0; wph ^= 1u; }
       }
     }
   } else if (warp < kFirstEpilogueWarp) {
@@ -308,10 +376,11 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
     const int tt = tid - kFirstTransformWarp * 32;  // 0..127
     const int seg = tt & 7;
     long long it = 0;
+    int rs = 0, os = 0;
+    uint32_t rph = 0, oph = 0;  // phase parities of the raw / A-operand rings
     for (long long t = 0; t < my_tiles; ++t) {
       const long long row0 = ((long long)blockIdx.x + t * gridDim.x) * BM;
       for (int kc = 0; kc < KC; ++kc, ++it) {
-        const int rs = (int)(it % RS), os = (int)(it % OS);
         const int kk = kc * BK + seg * 4;
         const int KP = KC * BK;
         const float4 c0 = *reinterpret_cast<const float4 *>(s_pro + kk);
@@ -331,39 +400,38 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
           pgrp = (int)(gq - row0 / g.ns);
           psmp = (int)(base - gq * g.ns);
         }
-        mbar_wait(&raw_full[rs], (uint32_t)((it / RS) & 1));
-        if (it >= OS) mbar_wait(&op_empty[os], (uint32_t)(((it / OS) - 1) & 1));
+        if (tt == 0) S2C_PROBE(16 + 16 * (int)it + 0);
+        mbar_wait(&raw_full[rs], rph);
+        if (tt == 0) S2C_PROBE(16 + 16 * (int)it + 1);
+        if (it >= OS) mbar_wait(&op_empty[os], oph ^ 1u);
+        if (tt == 0) S2C_PROBE(16 + 16 * (int)it + 2);
         const unsigned char *raw = raw_base + (size_t)rs * RAW_BYTES;
-        unsigned char *a_hi = op_base + (size_t)os * OP_BYTES, *a_lo = a_hi + A_BYTES;
+        unsigned char *a_hi = a_base + (size_t)os * 2 * A_BYTES, *a_lo = a_hi + A_BYTES;
+        // The shared-memory loads of PB passes are issued together, then the arithmetic and the operand stores follow:
+        // the raw ring and the operand stages are carved out of one array, so the compiler must keep every load behind
+        // the stores that precede it in program order -- with one pass per iteration each pass exposed a full
+        // shared-memory round trip (s2c_mlp_probe: 650-750 ns of staging per 16 KB chunk, the slowest pipeline stage).
+        constexpr int PB = (PRO == PRO_BNRELU) ? 8 : 4;
 #pragma unroll
-        for (int pass = 0; pass < BM / 16; ++pass) {
-          const int r = pass * 16 + (tt >> 3);
-          const long long row = row0 + r;
-          float4 v = *reinterpret_cast<const float4 *>(raw + r * 128 + seg * 16);
-          if (PRO == PRO_BNRELU) {
-            if (has_pro) {
-              v.x = fmaxf(fmaf(v.x, c0.x, c1.x), 0.f); v.y = fmaxf(fmaf(v.y, c0.y, c1.y), 0.f);
-              v.z = fmaxf(fmaf(v.z, c0.z, c1.z), 0.f); v.w = fmaxf(fmaf(v.w, c0.w, c1.w), 0.f);
-            }
-          } else if (PRO == PRO_AFFINE2) {
-            const float4 y = *reinterpret_cast<const float4 *>(raw + A_BYTES + r * 128 + seg * 16);
-            v.x = fmaf(c0.x, v.x, fmaf(c1.x, y.x, c2.x)); v.y = fmaf(c0.y, v.y, fmaf(c1.y, y.y, c2.y));
-            v.z = fmaf(c0.z, v.z, fmaf(c1.z, y.z, c2.z)); v.w = fmaf(c0.w, v.w, fmaf(c1.w, y.w, c2.w));
-          } else {  // PRO_POOL: v holds y
-            const float4 y = v;
-            float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < g.R && kk < g.K) {
-              const int4 am = *reinterpret_cast<const int4 *>(raw + A_BYTES + pgrp * 128 + seg * 16);
-              const float4 dp = *reinterpret_cast<const float4 *>(raw + A_BYTES + SLAB_BYTES + pgrp * 128 + seg * 16);
-              const int smp = psmp;
-              gg.x = (am.x == smp && fmaf(y.x, c3.x, c4.x) > 0.f) ? dp.x : 0.f;
-              gg.y = (am.y == smp && fmaf(y.y, c3.y, c4.y) > 0.f) ? dp.y : 0.f;
-              gg.z = (am.z == smp && fmaf(y.z, c3.z, c4.z) > 0.f) ? dp.z : 0.f;
-              gg.w = (am.w == smp && fmaf(y.w, c3.w, c4.w) > 0.f) ? dp.w : 0.f;
-            }
-            {  // the next pass is 16 rows further
-              const int nx = psmp + 16;
-              if (g.ns >= 16) {  // at most one group boundary per pass: no division
+        for (int p0 = 0; p0 < BM / 16; p0 += PB) {
+          float4 vv[PB], yy[PB], dpv[PB];
+          int4 amv[PB];
+          int smpv[PB];
+#pragma unroll
+          for (int j = 0; j < PB; ++j) {
+            const int r = (p0 + j) * 16 + (tt >> 3);
+            vv[j] = *reinterpret_cast<const float4 *>(raw + r * 128 + seg * 16);
+            if (PRO == PRO_AFFINE2) yy[j] = *reinterpret_cast<const float4 *>(raw + A_BYTES + r * 128 + seg * 16);
+            if (PRO == PRO_POOL) {
+              smpv[j] = psmp;
+              amv[j] = make_int4(-1, -1, -1, -1);  // never equals a sample index: rows / columns outside the matrix
+              dpv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (row0 + r < g.R && kk < g.K) {
+                amv[j] = *reinterpret_cast<const int4 *>(raw + A_BYTES + pgrp * 128 + seg * 16);
+                dpv[j] = *reinterpret_cast<const float4 *>(raw + A_BYTES + SLAB_BYTES + pgrp * 128 + seg * 16);
+              }
+              const int nx = psmp + 16;  // the next pass is 16 rows further
+              if (g.ns >= 16) {          // at most one group boundary per pass: no division
                 const bool wrap = nx >= g.ns;
                 pgrp += wrap ? 1 : 0;
                 psmp = wrap ? nx - g.ns : nx;
@@ -373,21 +441,50 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
                 psmp = nx - q * g.ns;
               }
             }
-            v.x = fmaf(c0.x, gg.x, fmaf(c1.x, y.x, c2.x)); v.y = fmaf(c0.y, gg.y, fmaf(c1.y, y.y, c2.y));
-            v.z = fmaf(c0.z, gg.z, fmaf(c1.z, y.z, c2.z)); v.w = fmaf(c0.w, gg.w, fmaf(c1.w, y.w, c2.w));
           }
-          const bool row_ok = row < g.R;  // TMA zero-fills out-of-range elements, but the prologue may map 0 to non-zero
-          if (!row_ok || kk + 0 >= g.K) v.x = 0.f;
-          if (!row_ok || kk + 1 >= g.K) v.y = 0.f;
-          if (!row_ok || kk + 2 >= g.K) v.z = 0.f;
-          if (!row_ok || kk + 3 >= g.K) v.w = 0.f;
-          store_split(a_hi, a_lo, swz(r, seg), v);
-          if (PRO != PRO_BNRELU && g.dY_out != nullptr && row_ok && kk < g.K)
-            *reinterpret_cast<float4 *>(g.dY_out + row * g.K + kk) = v;
+#pragma unroll
+          for (int j = 0; j < PB; ++j) {
+            const int r = (p0 + j) * 16 + (tt >> 3);
+            const long long row = row0 + r;
+            float4 v = vv[j];
+            if (PRO == PRO_BNRELU) {
+              if (has_pro) {
+                v.x = fmaxf(fmaf(v.x, c0.x, c1.x), 0.f); v.y = fmaxf(fmaf(v.y, c0.y, c1.y), 0.f);
+                v.z = fmaxf(fmaf(v.z, c0.z, c1.z), 0.f); v.w = fmaxf(fmaf(v.w, c0.w, c1.w), 0.f);
+              }
+            } else if (PRO == PRO_AFFINE2) {
+              const float4 y = yy[j];
+              v.x = fmaf(c0.x, v.x, fmaf(c1.x, y.x, c2.x)); v.y = fmaf(c0.y, v.y, fmaf(c1.y, y.y, c2.y));
+              v.z = fmaf(c0.z, v.z, fmaf(c1.z, y.z, c2.z)); v.w = fmaf(c0.w, v.w, fmaf(c1.w, y.w, c2.w));
+            } else {  // PRO_POOL: v holds y; g is the pooled gradient at the arg-max sample where the ReLU was active
+              const float4 y = v;
+              const int4 am = amv[j];
+              const float4 dp = dpv[j];
+              const int smp = smpv[j];
+              float4 gg;
+              gg.x = (am.x == smp && fmaf(y.x, c3.x, c4.x) > 0.f) ? dp.x : 0.f;
+              gg.y = (am.y == smp && fmaf(y.y, c3.y, c4.y) > 0.f) ? dp.y : 0.f;
+              gg.z = (am.z == smp && fmaf(y.z, c3.z, c4.z) > 0.f) ? dp.z : 0.f;
+              gg.w = (am.w == smp && fmaf(y.w, c3.w, c4.w) > 0.f) ? dp.w : 0.f;
+              v.x = fmaf(c0.x, gg.x, fmaf(c1.x, y.x, c2.x)); v.y = fmaf(c0.y, gg.y, fmaf(c1.y, y.y, c2.y));
+              v.z = fmaf(c0.z, gg.z, fmaf(c1.z, y.z, c2.z)); v.w = fmaf(c0.w, gg.w, fmaf(c1.w, y.w, c2.w));
+            }
+            const bool row_ok = row < g.R;  // TMA zero-fills out-of-range elements, but the prologue may map 0 to non-zero
+            if (!row_ok || kk + 0 >= g.K) v.x = 0.f;
+            if (!row_ok || kk + 1 >= g.K) v.y = 0.f;
+            if (!row_ok || kk + 2 >= g.K) v.z = 0.f;
+            if (!row_ok || kk + 3 >= g.K) v.w = 0.f;
+            store_split(a_hi, a_lo, swz(r, seg), v);
+            if (PRO != PRO_BNRELU && g.dY_out != nullptr && row_ok && kk < g.K)
+              *reinterpret_cast<float4 *>(g.dY_out + row * g.K + kk) = v;
+          }
         }
         fence_async_proxy();
         mbar_arrive(&op_full[os]);
         mbar_arrive(&raw_empty[rs]);
+        if (tt == 0) S2C_PROBE(16 + 16 * (int)it + 3);
+        if (++rs == RS) { rs = 0; rph ^= 1u; }
+        if (++os == OS) { os = 0; oph ^= 1u; }
       }
     }
   } else {
@@ -422,10 +519,22 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
       if (EPI == EPI_MASK_STATS) load_y(0, row_base);
       mbar_wait(&acc_full[ab], (uint32_t)((t >> 1) & 1));
       tc_fence_after();
+      if (q == 0 && lane == 0) S2C_PROBE(16 + 16 * (int)t + 8);
+      // column block cb + 1 is fetched from TMEM while block cb is transposed and stored (not in the 128-wide ReLU-mask
+      // epilogue: with the mask operand's own prefetch registers it would spill)
+      constexpr bool kPipeTmem = (EPI == EPI_STORE_STATS) || N == 64;
+      float vbuf[kPipeTmem ? 2 : 1][32];
+      if (kPipeTmem) tmem_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * N), vbuf[0]);
 #pragma unroll
       for (int cb = 0; cb < N / 32; ++cb) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * N + cb * 32), v);
+        float *v = vbuf[kPipeTmem ? (cb & 1) : 0];
+        if (kPipeTmem) {
+          tmem_ld_wait(v);
+          if (cb + 1 < N / 32)
+            tmem_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * N + (cb + 1) * 32), vbuf[(cb + 1) & 1]);
+        } else {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * N + cb * 32), v);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           *reinterpret_cast<float4 *>(sE + lane * 36 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -467,6 +576,7 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[ab]);
+      if (q == 0 && lane == 0) S2C_PROBE(16 + 16 * (int)t + 9);
     }
     if (has_stats) {
 #pragma unroll
@@ -492,10 +602,49 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-size_t gemm2_smem(int N, int K, int RS, int raw_tiles, int npro, int GT) {
+struct PipeCfg { int OS, WS, RS, wres; size_t smem; };
+
+unsigned long long *g_probe_buf = nullptr;  // s2c_mlp_probe(): device buffer the next launches stamp (null = off)
+int g_probe_cap = 0;
+
+size_t gemm2_smem(int N, int K, int OS, int WS, int RS, int raw_tiles, int npro, int GT) {
   const int KC = (K + BK - 1) / BK;
-  return (size_t)OS * (2 * BM * BK * 4 + 2 * (size_t)N * BK * 4) + (size_t)RS * (raw_tiles * BM * BK * 4 + 2 * (size_t)GT * 128) +
-         (size_t)npro * KC * BK * 4 + 4 * 32 * 36 * 4 + 24 * 8 + 16;
+  return (size_t)OS * (2 * BM * BK * 4) + (size_t)WS * (2 * (size_t)N * BK * 4) +
+         (size_t)RS * (raw_tiles * BM * BK * 4 + 2 * (size_t)GT * 128) + (size_t)npro * KC * BK * 4 + 4 * 32 * 36 * 4 + 44 * 8 + 16;
+}
+
+// Ring depths for one launch.  Measured with s2c_mlp_probe / tools/mlp_pipe_sweep.py (profiles/r02_mlp_pipe_probe.txt):
+// the layer kernel is bound by SHARED-MEMORY BANDWIDTH, not by a latency the rings could hide -- per 128 x 32 chunk the
+// transform warps move 48 KB (16 KB raw in, 32 KB hi/lo out), the twelve 3xTF32 MMAs read 12 x (4 KB of A + N x 32 B of
+// B) and the epilogue stages every output tile through shared memory once more, ~1500 cycles of the SM's 128 B/clk in
+// total (measured: 0.95 us per chunk at any depth of the weight ring, resident weights included).  What the depths do
+// change is the number of raw bytes the TMA engine keeps in flight, which the HBM-bound backward kernels need: so the
+// weight ring stays at two stages and every remaining byte goes to the raw ring.
+PipeCfg choose_pipe(int N, int K, int raw_tiles, int npro, int GT) {
+  const size_t budget = 227 * 1024;
+  const int KC = (K + BK - 1) / BK;
+  const int rs_cap = 4;
+  auto fits = [&](int OS, int WS, int RS) { return gemm2_smem(N, K, OS, WS, RS, raw_tiles, npro, GT) <= budget; };
+  auto fill_rs = [&](int OS, int WS) { int RS = 0; while (RS < rs_cap && fits(OS, WS, RS + 1)) ++RS; return RS; };
+  const int ws0 = KC < 2 ? KC : 2;
+  PipeCfg c = {2, ws0, fill_rs(2, ws0), KC <= 2 ? 1 : 0, 0};
+  // tuning / debugging knobs (tools/mlp_pipe_sweep.py): S2C_MLP_OS, S2C_MLP_WS (0 = resident), S2C_MLP_RS
+  const char *eo = getenv("S2C_MLP_OS"), *ew = getenv("S2C_MLP_WS"), *er = getenv("S2C_MLP_RS");
+  if (eo || ew || er) {
+    const PipeCfg chosen = c;
+    if (eo && atoi(eo) >= 1 && atoi(eo) <= kMaxOS) c.OS = atoi(eo);
+    if (ew) {
+      const int w = atoi(ew);
+      if (w == 0 && KC <= kMaxWS) { c.WS = KC; c.wres = 1; }
+      else if (w >= 1 && w <= kMaxWS) { c.WS = w; c.wres = (w == KC) ? 1 : 0; if (w > KC) { c.WS = KC; c.wres = 1; } }
+    }
+    c.RS = fill_rs(c.OS, c.WS);
+    if (er && atoi(er) >= 1 && atoi(er) <= kMaxRS && atoi(er) < c.RS) c.RS = atoi(er);
+    if (c.RS < 1) c = chosen;  // the requested rings do not fit: keep the automatic choice
+  }
+  if (c.RS < 1) c.RS = 1;
+  c.smem = gemm2_smem(N, K, c.OS, c.WS, c.RS, raw_tiles, npro, GT);
+  return c;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -555,15 +704,14 @@ int launch_gemm2(const Gemm2Args &g0, const float *A2, long long lda2, cudaStrea
   } else {
     tmap_am = tmap; tmap_dp = tmap;
   }
-  int RS = 4;  // raw-tile ring depth = bytes the TMA engine keeps in flight per SM (16 KB per stage and raw tile)
-  if (const char *e = getenv("S2C_MLP_RS")) RS = atoi(e) >= 1 && atoi(e) <= 8 ? atoi(e) : 4;  // tuning / debugging knob
-  while (RS > 1 && gemm2_smem(N, g.K, RS, raw_tiles, npro, g.GT) > 227 * 1024) --RS;
-  const size_t smem = gemm2_smem(N, g.K, RS, raw_tiles, npro, g.GT);
+  const PipeCfg pc = choose_pipe(N, g.K, raw_tiles, npro, g.GT);
+  const size_t smem = pc.smem;
   if (smem > 227 * 1024) {
     set_error("mlp: shared memory %zu B exceeds 227 KB (N=%d K=%d)", smem, N, g.K);
     return S2C_ERR_UNSUPPORTED;
   }
-  g.RS = RS;
+  g.RS = pc.RS; g.OS = pc.OS; g.WS = pc.WS; g.wres = pc.wres;
+  g.probe = g_probe_buf; g.probe_cap = g_probe_cap;
   auto kern = mlp_gemm2_kernel<N, PRO, EPI>;
   S2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "mlp_gemm2 smem attr");
   const long long tiles = (g.R + BM - 1) / BM;
@@ -575,6 +723,14 @@ int launch_gemm2(const Gemm2Args &g0, const float *A2, long long lda2, cudaStrea
 
 }  // namespace
 }  // namespace s2c
+
+// Profiling aid: CTA 0 of every following layer-kernel launch stamps clock64() at its pipeline hand-offs into `buf`
+// (`capacity` 8-byte slots, device memory; layout at S2C_PROBE in this file).  buf = null switches it off.
+extern "C" int s2c_mlp_probe(unsigned long long *buf, int capacity) {
+  s2c::g_probe_buf = buf;
+  s2c::g_probe_cap = buf ? capacity : 0;
+  return S2C_OK;
+}
 
 // Pipelined layer kernel.  Extra requirements over s2c_mlp_layer_fwd: N in {64,128,256}; K, lda, ldc multiples of 4;
 // A and C 16-byte aligned; `wprep` = caller-provided workspace of ceil(K/32) * N * 256 bytes (16-byte aligned).

@@ -72,6 +72,83 @@ extern "C" int s2c_gemm_tn(const float *A, long long lda, const float *X, long l
   return S2C_OK;
 }
 
+// C (M, N) = A (M, K) * B (K, N) [+ bias[n]] [relu] in plain fp32 FMAs, both operands as generic strided views:
+//     A(m, k) = A[m * sam + k * sak],   B(k, n) = B[k * sbk + n * sbn]
+// so the same kernel is the Linear forward (x W^T: B(k, n) = W[n * ldw + k]) and its input gradient (dY W:
+// B(k, n) = W[k * ldw + n]) for the caption module's nn.Linear layers (models/caption_module.py:216-240: map_feat,
+// the hoisted word / target terms of map_topdown, classifier), whose widths (300, 812, 3500) are not multiples of the
+// tensor-core kernels' 64-column tiles.  A few hundred rows x a few thousand columns: one 64x64 tile per CTA, the
+// library's SIMT sgemm kernels these replace take 28-52 us per call here.
+namespace s2c {
+namespace {
+
+constexpr int GK = 32;
+
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const float *__restrict__ A, long long sam, long long sak, const float *__restrict__ B, long long sbk,
+                 long long sbn, const float *__restrict__ bias, int relu, int M, int N, int K, float *__restrict__ C,
+                 long long ldc) {
+  __shared__ float As[GK][TM + 4], Bs[GK][TN + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  const bool a_kfast = sak == 1, b_kfast = sbk == 1;  // which index is contiguous in memory: coalesce along it
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += GK) {
+#pragma unroll 8
+    for (int i = threadIdx.x; i < GK * TM; i += 256) {
+      const int ka = a_kfast ? (i % GK) : (i / TM), ma = a_kfast ? (i / GK) : (i % TM);
+      As[ka][ma] = (k0 + ka < K && m0 + ma < M) ? A[(long long)(m0 + ma) * sam + (long long)(k0 + ka) * sak] : 0.f;
+      const int kb = b_kfast ? (i % GK) : (i / TN), nb = b_kfast ? (i / GK) : (i % TN);
+      Bs[kb][nb] = (k0 + kb < K && n0 + nb < N) ? B[(long long)(k0 + kb) * sbk + (long long)(n0 + nb) * sbn] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 16
+    for (int kk = 0; kk < GK; ++kk) {
+      const float4 a = *reinterpret_cast<const float4 *>(&As[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias != nullptr ? bias[n] : 0.f);
+      if (relu) v = fmaxf(v, 0.f);
+      C[(long long)m * ldc + n] = v;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace s2c
+
+extern "C" int s2c_gemm(const float *A, long long sam, long long sak, const float *B, long long sbk, long long sbn,
+                        const float *bias, int relu, int M, int N, int K, float *C, long long ldc, void *stream) {
+  using namespace s2c;
+  S2C_REQUIRE(M >= 0 && N >= 0 && K >= 0 && ldc >= N, "gemm: bad sizes");
+  if (M == 0 || N == 0) return S2C_OK;
+  S2C_REQUIRE(C && (K == 0 || (A && B)), "gemm: null pointer");
+  dim3 grid((unsigned)ceil_div(N, TN), (unsigned)ceil_div(M, TM));
+  S2C_REQUIRE(grid.y <= 65535u, "gemm: M=%d exceeds 65535 row tiles", M);
+  gemm_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, sam, sak, B, sbk, sbn, bias, relu, M, N, K, C, ldc);
+  S2C_CHECK_LAUNCH("gemm");
+  return S2C_OK;
+}
+
 // Column sums of a tall matrix (bias gradients of the Linear / Conv1d layers): out[c] = sum_r A[r, c].
 namespace s2c {
 namespace {

@@ -24,12 +24,43 @@ class FlatGradients(object):
             self.offsets.append(off)
             off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
         self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
-        for p, o in zip(self.params, self.offsets):
-            p.grad = self.flat[o:o + p.numel()].view_as(p)
+        self.views = [self.flat[o:o + p.numel()].view_as(p) for p, o in zip(self.params, self.offsets)]
+        for p, v in zip(self.params, self.views):
+            p.grad = v
         self.numel = sum(p.numel() for p in self.params)
 
     def zero_(self):
         self.flat.zero_()
+
+    # ---- one step without per-parameter accumulation kernels ---------------------------------------------------------------
+    # With .grad pointing at a zeroed view, autograd's AccumulateGrad issues one `grad += new` kernel per parameter
+    # (106 launches per CapNet step).  release() drops the views before backward, so AccumulateGrad simply keeps the
+    # tensor each backward function returned; collect() then moves all of them into the flat buffer with ONE multi-tensor
+    # copy, zero-fills the slices of parameters that received nothing, and re-installs the views as .grad.
+    def release(self):
+        for p in self.params:
+            p.grad = None
+
+    def collect(self):
+        srcs, dsts, strided, missing = [], [], [], []
+        for p, v in zip(self.params, self.views):
+            g = p.grad
+            if g is None:
+                missing.append(v)
+            elif g is not v and g.data_ptr() != v.data_ptr():
+                if g.is_contiguous() and g.dtype == v.dtype and g.shape == v.shape:
+                    srcs.append(g)
+                    dsts.append(v)
+                else:
+                    strided.append((v, g))
+            p.grad = v
+        with torch.no_grad():
+            if missing:
+                torch._foreach_zero_(missing)
+            if srcs:
+                torch._foreach_copy_(dsts, srcs)
+            for v, g in strided:
+                v.copy_(g)
 
     def all_reduce_mean(self, group=None):
         """Mean over ranks in ONE collective: ncclAllReduce(avg) (the 1/world scale is applied inside NCCL's reduction,

@@ -57,9 +57,10 @@ class TrainStep(object):
 
     # ---- the step, eager -------------------------------------------------------------------------------
     def _fwd_bwd(self, data):
-        self.flat.zero_()
+        self.flat.release()   # no zero-fill and no per-parameter `grad += new` kernels: see FlatGradients.collect
         out = self.loss_fn(self.model(data), self.device, self.DC, None, **self.flags)
         out["loss"].backward()
+        self.flat.collect()
         return out
 
     def _step_eager(self, data, collective=True):

@@ -16,6 +16,7 @@ import torch
 from torch.autograd import Function
 
 from . import _ext_mlp
+from ..linear_simt import gemm
 
 # Test hook (tests/parity_utils.py): when set to a list, every forward call appends the tensors that define its
 # discontinuous decisions -- pre-BatchNorm outputs + folded BatchNorm affine of every layer (ReLU masks) and the
@@ -95,6 +96,14 @@ def _input_blocks(K, lda, xyz_gap):
     return blocks
 
 
+def _w0(ctx, W, K, lda, xyz_gap):
+    """The first layer's weight in the rows' column layout: the forward pass's copy when it is still there."""
+    w0 = getattr(ctx, "w0", None)
+    if w0 is not None:
+        return w0, w0.shape[1]
+    return _first_layer_weight(W, K, lda, xyz_gap)
+
+
 class _FusedMLPPool(Function):
     @staticmethod
     def forward(ctx, rows, K, G, ns, training, bns, xyz_gap, need_xyz_grad, capture, *params):
@@ -104,12 +113,26 @@ class _FusedMLPPool(Function):
         R = rows.shape[0]
         Ys, coefs = [], []
         A, scale, shift, k = rows, None, None, K
-        zstats = torch.zeros((L, 2, 256), dtype=torch.float64, device=rows.device)  # all layers' statistics: one fill
+        # ONE zero-fill per call for every accumulator of the forward AND the backward pass: the float64 statistics of
+        # all layers (forward: L x (sum, sumsq); backward: (L + 1) x (sum g, sum g*y)) and the weight gradients the
+        # tensor-core kernels reduce into with red.global.add
+        wshapes = []
+        for l in range(L):
+            Wl = params[4 * l]
+            wshapes.append((Wl.shape[0], _first_layer_width(K, rows.shape[1], xyz_gap) if l == 0 else Wl[0].numel()))
+        need_bwd = any(ctx.needs_input_grad)
+        ndw = sum(c * p for c, p in wshapes) if need_bwd else 0
+        nst = (2 * L + 1 if need_bwd else L) * 512
+        zall = torch.zeros(nst + (ndw + 1) // 2, dtype=torch.float64, device=rows.device)
+        zstats = zall[:L * 512].view(L, 2, 256)
+        ctx.zero_ws = (zall[L * 512:nst].view(L + 1, 2, 256), zall[nst:].view(torch.float32)[:ndw]) if need_bwd else None
+        W0 = None
         for l in range(L):
             W = params[4 * l].reshape(params[4 * l].shape[0], -1)
             need_stats = training or not bns[l].track_running_stats
             if l == 0:  # the weight in the column layout of the rows (zero columns where the rows are padding)
                 W, k = _first_layer_weight(W, K, A.shape[1], xyz_gap)
+                W0 = W.detach()
             res = _ext_mlp.mlp_layer_fwd(A, W, scale, shift, want_stats=need_stats, K=k, stats=zstats[l])
             Y, s1, s2 = res if need_stats else (res, None, None)
             mean, invstd, scale, shift = _bn_coefficients(s1, s2, R, bns[l], training)
@@ -123,6 +146,7 @@ class _FusedMLPPool(Function):
             CAPTURE.append(dict(G=G, ns=ns, Ys=list(Ys), affine=[(c[2], c[3]) for c in coefs], argmax=argmax,
                                 pooled=pooled))
         ctx.save_for_backward(rows, argmax, *Ys, *[t for c in coefs for t in c], *params)
+        ctx.w0 = W0  # the first layer's weight in the rows' column layout (the backward pass multiplies by it again)
         ctx.meta = (K, G, ns, L, bool(training), [bool(training or not b.track_running_stats) for b in bns],
                     bool(xyz_gap), bool(need_xyz_grad))
         return pooled
@@ -139,13 +163,18 @@ class _FusedMLPPool(Function):
         grads = [None] * (4 * L)
         dpool = dpool.contiguous()
         grad_rows = None
-        # one zero-fill for every statistics accumulator of this backward pass, one for all weight gradients
-        zstats = torch.zeros((L + 1, 2, 256), dtype=torch.float64, device=rows.device)
         wshapes = []
         for l in range(L):
             Wl = params[4 * l].reshape(params[4 * l].shape[0], -1)
             wshapes.append((Wl.shape[0], _first_layer_width(K, rows.shape[1], xyz_gap) if l == 0 else Wl.shape[1]))
-        zdw = torch.zeros(sum(c * p for c, p in wshapes), dtype=torch.float32, device=rows.device)
+        # statistics accumulators and weight-gradient buffers: zero-filled by the forward pass together with its own
+        # (a second backward through the same graph allocates fresh ones)
+        ws, ctx.zero_ws = getattr(ctx, "zero_ws", None), None
+        if ws is not None:
+            zstats, zdw = ws
+        else:
+            zstats = torch.zeros((L + 1, 2, 256), dtype=torch.float64, device=rows.device)
+            zdw = torch.zeros(sum(c * p for c, p in wshapes), dtype=torch.float32, device=rows.device)
         woff = [0]
         for c, p in wshapes:
             woff.append(woff[-1] + c * p)
@@ -199,7 +228,7 @@ class _FusedMLPPool(Function):
                     g.scatter_(1, argmax.long().unsqueeze(1), dpool.unsqueeze(1))
                     g = g.view(R, -1) * (torch.addcmul(coefs[l][3], Y, coefs[l][2]) > 0)
                 if l == 0:
-                    Wp, Kp = _first_layer_weight(W, K, rows.shape[1], xyz_gap)
+                    Wp, Kp = _w0(ctx, W, K, rows.shape[1], xyz_gap)
                     blocks = _input_blocks(K, rows.shape[1], xyz_gap) if ctx.needs_input_grad[0] else None
                     if (not ctx.needs_input_grad[0] and
                             _ext_mlp.bwd_weight_supported(Y.shape[1], Kp, g.stride(0), Y.stride(0), rows.stride(0))):
@@ -215,8 +244,8 @@ class _FusedMLPPool(Function):
                             d = _ext_mlp.mlp_layer_bwd_input(g, Y, a, b, c, Wp, c0, w, grad_rows, want_dY=(i == 0))
                             dY = d if i == 0 else dY
                         if xyz_gap:
-                            if need_xyz_grad:
-                                grad_rows[:, :4] = dY @ Wp[:, :4]
+                            if need_xyz_grad:   # the four coordinate columns: a skinny fp32 GEMM (s2c_gemm)
+                                gemm(dY, (Wp.stride(0), Wp.stride(1)), Wp, dY.shape[0], 4, dY.shape[1], out=grad_rows[:, :4])
                             else:
                                 grad_rows[:, :4] = 0.0
                             if rows.shape[1] > 4 + K - 3:
@@ -238,7 +267,7 @@ class _FusedMLPPool(Function):
                     sum_g = g.sum(0, dtype=torch.float64)
                     sum_gy = (g * Ys[l - 1]).sum(0, dtype=torch.float64)
                 else:
-                    Wp, Kp = _first_layer_weight(W, K, rows.shape[1], xyz_gap)
+                    Wp, Kp = _w0(ctx, W, K, rows.shape[1], xyz_gap)
                     if _ext_mlp.bwd_weight_supported(Y.shape[1], Kp, dY.stride(0), rows.stride(0)):
                         dWp = _ext_mlp.mlp_layer_bwd_weight(dY, rows, Kp)
                     else:

@@ -20,6 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..lib import caption_decoder
+from ..lib.linear_simt import linear
 from ..lib.config import CONF
 from ..lib.pointnet2 import _ext_graph
 from ..utils.box_util import box3d_iou_batch_tensor
@@ -230,10 +231,11 @@ class TopDownSceneCaptionModule(nn.Module):
         #   classifier(h2)                           -- one (B*T, 512) x (512, V) GEMM after the loop
         T = max(num_words - 1, 1)
         E, H = self.emb_size, self.hidden_size
-        mapped = self.map_feat(obj_feats)
+        # (the Linear layers around the recurrence run on libs2c's fp32 GEMM kernels, lib/linear_simt.py: no library GEMM)
+        mapped = linear(obj_feats, self.map_feat.weight)
         w_td, b_td = self.map_topdown[0].weight, self.map_topdown[0].bias
-        pre_word = F.linear(word_embs[:, :T], w_td[:, :E])                 # (B,T,emb)
-        pre_tgt = F.linear(target_feats, w_td[:, E + H:], b_td)            # (B,emb)
+        pre_word = linear(word_embs[:, :T], w_td[:, :E])                   # (B,T,emb)
+        pre_tgt = linear(target_feats, w_td[:, E + H:], b_td)              # (B,emb)
         w_td_h = w_td[:, E:E + H]
         # the whole recurrence in one launch (and one for its backward): csrc/caption.cu / caption_grid.cu.  There is
         # no framework-kernel alternative in the product: shapes the kernels do not take raise.
@@ -243,7 +245,7 @@ class TopDownSceneCaptionModule(nn.Module):
                                                    self.recurrent_cell_1, self.map_hidd, self.attend,
                                                    self.map_lang[0], self.recurrent_cell_2)
         good_bbox_masks = target_ious > min_iou
-        data_dict["lang_cap"] = self.classifier(hid)            # (B,T,V)
+        data_dict["lang_cap"] = linear(hid, self.classifier.weight, self.classifier.bias)   # (B,T,V)
         data_dict["pred_ious"] = _masked_mean(target_ious, good_bbox_masks)
         data_dict["topdown_attn"] = attn                        # (B,K,T)
         data_dict["valid_masks"] = valid_masks

@@ -66,3 +66,33 @@ def test_shard_batch_requires_divisible_batch():
     from scan2cap_b200.distributed import shard_batch
     with pytest.raises(AssertionError):
         shard_batch({"x": torch.zeros(5, 2)}, 0, 2)
+
+
+def test_release_collect_equals_accumulation_into_the_views():
+    """FlatGradients.release() / collect() (no per-parameter accumulation kernels) leaves the flat buffer exactly as
+    backward into zeroed .grad views does: twice-used parameters summed, unused parameters zero, .grad = the views."""
+    from scan2cap_b200.distributed import FlatGradients
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 5), torch.nn.Linear(5, 2))
+    flat = FlatGradients(model)
+    x = torch.randn(7, 6)
+
+    def loss():
+        h = model[1](model[0](x))
+        return (model[2](model[2](h)) ** 2).mean()   # model[2] used twice, model[3] not at all
+
+    flat.flat.fill_(3.0)                              # stale content must not survive
+    flat.zero_()
+    loss().backward()
+    want = flat.flat.clone()
+    flat.flat.fill_(7.0)                              # stale content again: collect() must overwrite every slice
+    flat.release()
+    assert all(p.grad is None for p in model.parameters())
+    loss().backward()
+    flat.collect()
+    for p, v in zip(flat.params, flat.views):
+        assert p.grad is v
+    got = torch.cat([v.reshape(-1) for v in flat.views])
+    ref = torch.cat([want[o:o + p.numel()] for p, o in zip(flat.params, flat.offsets)])
+    assert torch.equal(got, ref)
+    assert float(model[3].weight.grad.abs().sum()) == 0.0 and float(model[2].weight.grad.abs().sum()) > 0.0

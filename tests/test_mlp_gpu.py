@@ -205,6 +205,38 @@ def test_linear_rows_matches_float64(R, IN, OUT, bias):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("lead,IN,OUT,bias,sliced", [((8, 27), 300, 300, False, True), ((8,), 128, 300, True, True),
+                                                     ((8, 256), 128, 512, False, False), ((8, 27), 512, 3500, True, False),
+                                                     ((3, 5), 7, 9, True, False), ((1,), 64, 64, True, False)])
+def test_linear_simt_matches_float64(lead, IN, OUT, bias, sliced):
+    """lib/linear_simt.linear (the caption module's Linear layers on s2c_gemm / s2c_gemm_tn): forward, input gradient,
+    weight and bias gradients vs float64, with a strided input view and -- as for the map_topdown terms -- a weight
+    that is a column slice of a wider matrix."""
+    from scan2cap_b200.lib.linear_simt import linear
+    torch.manual_seed(IN + OUT)
+    full = torch.randn(*lead[:-1], lead[-1] + 3, IN, device=DEV) if len(lead) > 1 else torch.randn(lead[0] + 3, IN, device=DEV)
+    x = (full[..., :lead[-1], :] if len(lead) > 1 else full[:lead[0]]).detach().requires_grad_(True)
+    wide = torch.randn(OUT, IN + (40 if sliced else 0), device=DEV, requires_grad=True)
+    b = torch.randn(OUT, device=DEV, requires_grad=True) if bias else None
+    w = wide[:, 17:17 + IN] if sliced else wide
+    y = linear(x, w, b)
+    assert y.shape == tuple(lead) + (OUT,)
+    g = torch.randn_like(y)
+    y.backward(g)
+    xd = x.detach().double().requires_grad_(True)
+    wd = wide.detach().double().requires_grad_(True)
+    bd = b.detach().double().requires_grad_(True) if bias else None
+    yd = torch.nn.functional.linear(xd, wd[:, 17:17 + IN] if sliced else wd, bd)
+    yd.backward(g.double())
+    rel = lambda a, c: float((a.double() - c).abs().max() / c.abs().max().clamp_min(1e-12))
+    assert rel(y.detach(), yd.detach()) < 1e-5
+    assert rel(x.grad, xd.grad) < 1e-5
+    assert rel(wide.grad, wd.grad) < 1e-5
+    if bias:
+        assert rel(b.grad, bd.grad) < 1e-5
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("training", [True, False])
 @pytest.mark.parametrize("R,C,NOUT,conv_bias", [(8192, 256, 259, True), (2048, 128, 97, False)])
 def test_pointwise_head_matches_float64(R, C, NOUT, conv_bias, training):

@@ -353,8 +353,12 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
           S2C_PROBE(16 + 16 * pit + 4);
           const uint32_t ah = smem_u32(a_base + (size_t)os * 2 * A_BYTES), al = ah + A_BYTES;
           const uint32_t bh = smem_u32(w_base + (size_t)ws * 2 * W_BYTES), bl = bh + W_BYTES;
+          // only the 8-column steps that hold columns of the matrix: a first layer over [xyz, 0 | features] rows has
+          // K = 8, 132 or 260 valid columns, i.e. one step in its last (or only) chunk instead of four
+          const int steps = min(BK / 8, (g.K - kc * BK + 7) / 8);
 #pragma unroll
           for (int j = 0; j < BK / 8; ++j) {
+            if (j >= steps) break;
             const uint32_t o = j * 32;
             umma_tf32(d_tmem, make_desc(ah + o), make_desc(bh + o), idesc, (kc | j) ? 1u : 0u);
             umma_tf32(d_tmem, make_desc(ah + o), make_desc(bl + o), idesc, 1u);
@@ -412,8 +416,10 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
         // the stores that precede it in program order -- with one pass per iteration each pass exposed a full
         // shared-memory round trip (s2c_mlp_probe: 650-750 ns of staging per 16 KB chunk, the slowest pipeline stage).
         constexpr int PB = (PRO == PRO_BNRELU) ? 8 : 4;
+        const bool staged = kk < ((g.K + 7) & ~7);  // columns beyond the last 8-column MMA step are never read
 #pragma unroll
         for (int p0 = 0; p0 < BM / 16; p0 += PB) {
+          if (!staged) break;
           float4 vv[PB], yy[PB], dpv[PB];
           int4 amv[PB];
           int smpv[PB];

@@ -111,6 +111,41 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// the same with the A operand in tensor memory (M = 128: lane = row, one 32-bit column per K element)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// 32 columns of this thread's TMEM lane (lane = 32 * (warp % 4) + lane id)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float *v) {
+  const uint32_t *u = reinterpret_cast<const uint32_t *>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(u[8]), "r"(u[9]), "r"(u[10]),
+      "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15]), "r"(u[16]), "r"(u[17]), "r"(u[18]), "r"(u[19]), "r"(u[20]),
+      "r"(u[21]), "r"(u[22]), "r"(u[23]), "r"(u[24]), "r"(u[25]), "r"(u[26]), "r"(u[27]), "r"(u[28]), "r"(u[29]), "r"(u[30]),
+      "r"(u[31])
+      : "memory");
+}
+// one elected lane of a converged warp: unlike `lane == 0`, the compiler keeps the region's operands in UNIFORM registers,
+// so every tcgen05.mma below is one UTCHMMA.  Behind `if (lane == 0)` each MMA was wrapped in an ELECT / R2UR.BROADCAST x5 /
+// BRA.U.ANY waterfall (descriptors moved from vector to uniform registers per instruction): ~100 cycles per MMA, which
+// s2c_mlp_probe showed as 0.7 us of MMA issue per 32-column chunk whatever the tile width or the operand source.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -222,7 +257,12 @@ __device__ __forceinline__ void tma_load_box(void *dst_smem, const CUtensorMap *
       : "memory");
 }
 
-template <int N, int PRO, int EPI>
+// ATM: the A operand travels through TENSOR memory instead of shared memory (forward kernels).  Measured with
+// s2c_mlp_probe, the layer kernel is bound by shared-memory bandwidth: per 128 x 32 chunk the hi / lo operand costs 32 KB
+// of stores and 12 x 4 KB of MMA operand reads, 40 % of all shared-memory traffic.  With ATM the transform warps own one
+// tile row per thread (row = TMEM lane), read it from the TMA-swizzled raw tile, and hand hi / lo to the tensor core with
+// two tcgen05.st; the MMAs read A from TMEM (tcgen05.mma [d], [a], b_desc) and only B from shared memory.
+template <int N, int PRO, int EPI, bool ATM>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
                  const __grid_constant__ CUtensorMap tmap_am, const __grid_constant__ CUtensorMap tmap_dp) {
@@ -235,12 +275,16 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
   const uint32_t SLAB_BYTES = (PRO == PRO_POOL) ? (uint32_t)g.GT * 128u : 0u;
   const uint32_t RAW_BYTES = RAW_TILES * A_BYTES + 2 * SLAB_BYTES;
   constexpr int NPRO = (PRO == PRO_BNRELU) ? 2 : (PRO == PRO_AFFINE2) ? 3 : 5;
-  constexpr uint32_t TMEM_COLS = (2 * N <= 32) ? 32 : (2 * N <= 64) ? 64 : (2 * N <= 128) ? 128 : (2 * N <= 256) ? 256 : 512;
+  constexpr uint32_t ACC_COLS = 2 * N, A_COLS = ATM ? 2 * 64 : 0;  // accumulators (double-buffered) | two [hi | lo] A stages
+  constexpr uint32_t TMEM_COLS = (ACC_COLS + A_COLS <= 32) ? 32 : (ACC_COLS + A_COLS <= 64) ? 64 : (ACC_COLS + A_COLS <= 128) ? 128
+                                 : (ACC_COLS + A_COLS <= 256) ? 256 : 512;
+  static_assert(!ATM || PRO == PRO_BNRELU, "the tensor-memory operand path is built for the forward prologue");
+  static_assert(ACC_COLS + A_COLS <= 512, "tensor memory");
   const int RS = g.RS, OS = g.OS, WS = g.WS;
   const bool wres = g.wres != 0;
   const int KC = (g.K + BK - 1) / BK;
   unsigned char *a_base = smem;                                  // OS x [A hi | A lo]
-  unsigned char *w_base = smem + (size_t)OS * 2 * A_BYTES;      // WS x [W hi | W lo]
+  unsigned char *w_base = smem + (ATM ? 0 : (size_t)OS * 2 * A_BYTES);  // WS x [W hi | W lo]
   unsigned char *raw_base = w_base + (size_t)WS * 2 * W_BYTES;  // RS x raw stage
   float *s_pro = reinterpret_cast<float *>(raw_base + (size_t)RS * RAW_BYTES);  // [NPRO][KC*BK] coefficients
   float *s_epi = s_pro + NPRO * KC * BK;                                         // [4 warps][32 rows][36] epilogue staging
@@ -337,6 +381,7 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer
     const uint32_t idesc = make_idesc(BM, N);
+    const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);  // warp-uniform by construction (see elect_one)
     int os = 0, ws = 0;
     uint32_t oph = 0, wph = 0;  // phase parities of the A-operand / weight rings
     int pit = 0;
@@ -344,25 +389,32 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
       const int ab = (int)(t & 1);
       if (t >= 2) mbar_wait(&acc_empty[ab], (uint32_t)(((t >> 1) - 1) & 1));
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(ab * N);
+      const uint32_t d_tmem = tbase + (uint32_t)(ab * N);
       for (int kc = 0; kc < KC; ++kc) {
         mbar_wait(&op_full[os], oph);
         mbar_wait(&w_full[ws], wres ? 0u : wph);  // resident chunks complete phase 0 once and stay valid
         tc_fence_after();
-        if (lane == 0) {
+        const uint32_t ah = smem_u32(a_base + (size_t)os * 2 * A_BYTES), al = ah + A_BYTES;
+        const uint32_t bh = smem_u32(w_base + (size_t)ws * 2 * W_BYTES), bl = bh + W_BYTES;
+        const uint32_t ath = tbase + ACC_COLS + (uint32_t)os * 64u, atl = ath + 32u;  // ATM: A stage in tensor memory
+        // only the 8-column steps that hold columns of the matrix: a first layer over [xyz, 0 | features] rows has
+        // K = 8, 132 or 260 valid columns, i.e. one step in its last (or only) chunk instead of four
+        const int steps = min(BK / 8, (g.K - kc * BK + 7) / 8);
+        if (elect_one()) {
           S2C_PROBE(16 + 16 * pit + 4);
-          const uint32_t ah = smem_u32(a_base + (size_t)os * 2 * A_BYTES), al = ah + A_BYTES;
-          const uint32_t bh = smem_u32(w_base + (size_t)ws * 2 * W_BYTES), bl = bh + W_BYTES;
-          // only the 8-column steps that hold columns of the matrix: a first layer over [xyz, 0 | features] rows has
-          // K = 8, 132 or 260 valid columns, i.e. one step in its last (or only) chunk instead of four
-          const int steps = min(BK / 8, (g.K - kc * BK + 7) / 8);
 #pragma unroll
           for (int j = 0; j < BK / 8; ++j) {
             if (j >= steps) break;
             const uint32_t o = j * 32;
-            umma_tf32(d_tmem, make_desc(ah + o), make_desc(bh + o), idesc, (kc | j) ? 1u : 0u);
-            umma_tf32(d_tmem, make_desc(ah + o), make_desc(bl + o), idesc, 1u);
-            umma_tf32(d_tmem, make_desc(al + o), make_desc(bh + o), idesc, 1u);
+            if (ATM) {
+              umma_tf32_ts(d_tmem, ath + j * 8, make_desc(bh + o), idesc, (kc | j) ? 1u : 0u);
+              umma_tf32_ts(d_tmem, ath + j * 8, make_desc(bl + o), idesc, 1u);
+              umma_tf32_ts(d_tmem, atl + j * 8, make_desc(bh + o), idesc, 1u);
+            } else {
+              umma_tf32(d_tmem, make_desc(ah + o), make_desc(bh + o), idesc, (kc | j) ? 1u : 0u);
+              umma_tf32(d_tmem, make_desc(ah + o), make_desc(bl + o), idesc, 1u);
+              umma_tf32(d_tmem, make_desc(al + o), make_desc(bh + o), idesc, 1u);
+            }
           }
           umma_commit(&op_empty[os]);
           if (!wres) umma_commit(&w_empty[ws]);
@@ -411,6 +463,45 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
         if (tt == 0) S2C_PROBE(16 + 16 * (int)it + 2);
         const unsigned char *raw = raw_base + (size_t)rs * RAW_BYTES;
         unsigned char *a_hi = a_base + (size_t)os * 2 * A_BYTES, *a_lo = a_hi + A_BYTES;
+        if constexpr (ATM) {
+          // one tile row per thread: row = TMEM lane = 32 * (warp % 4) + lane.  The raw tile was written by the TMA engine
+          // with the 128-byte swizzle (16-byte chunk c of row r sits at chunk c ^ (r & 7)), so the eight lanes of a
+          // shared-memory wavefront -- eight consecutive rows, same chunk -- hit eight different bank groups.
+          tc_fence_after();
+          const int q = warp & 3, r = q * 32 + lane;
+          const bool row_ok = row0 + r < g.R;
+          float4 v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4 *>(raw + r * 128 + ((j ^ (r & 7)) << 4));
+          float hi[32], lo[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k4 = kc * BK + j * 4;
+            if (has_pro) {
+              const float4 s0 = *reinterpret_cast<const float4 *>(s_pro + k4);            // warp-wide broadcast
+              const float4 s1 = *reinterpret_cast<const float4 *>(s_pro + KC * BK + k4);
+              v[j].x = fmaxf(fmaf(v[j].x, s0.x, s1.x), 0.f); v[j].y = fmaxf(fmaf(v[j].y, s0.y, s1.y), 0.f);
+              v[j].z = fmaxf(fmaf(v[j].z, s0.z, s1.z), 0.f); v[j].w = fmaxf(fmaf(v[j].w, s0.w, s1.w), 0.f);
+            }
+            if (!row_ok || k4 + 0 >= g.K) v[j].x = 0.f;
+            if (!row_ok || k4 + 1 >= g.K) v[j].y = 0.f;
+            if (!row_ok || k4 + 2 >= g.K) v[j].z = 0.f;
+            if (!row_ok || k4 + 3 >= g.K) v[j].w = 0.f;
+            split_tf32(v[j].x, hi[4 * j + 0], lo[4 * j + 0]); split_tf32(v[j].y, hi[4 * j + 1], lo[4 * j + 1]);
+            split_tf32(v[j].z, hi[4 * j + 2], lo[4 * j + 2]); split_tf32(v[j].w, hi[4 * j + 3], lo[4 * j + 3]);
+          }
+          const uint32_t at = tmem_base + ((uint32_t)(q * 32) << 16) + ACC_COLS + (uint32_t)os * 64u;
+          tmem_st32(at, hi);
+          tmem_st32(at + 32u, lo);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&op_full[os]);
+          mbar_arrive(&raw_empty[rs]);
+          if (tt == 0) S2C_PROBE(16 + 16 * (int)it + 3);
+          if (++rs == RS) { rs = 0; rph ^= 1u; }
+          if (++os == OS) { os = 0; oph ^= 1u; }
+          continue;
+        }
         // The shared-memory loads of PB passes are issued together, then the arithmetic and the operand stores follow:
         // the raw ring and the operand stages are carved out of one array, so the compiler must keep every load behind
         // the stores that precede it in program order -- with one pass per iteration each pass exposed a full
@@ -626,9 +717,22 @@ size_t gemm2_smem(int N, int K, int OS, int WS, int RS, int raw_tiles, int npro,
 // total (measured: 0.95 us per chunk at any depth of the weight ring, resident weights included).  What the depths do
 // change is the number of raw bytes the TMA engine keeps in flight, which the HBM-bound backward kernels need: so the
 // weight ring stays at two stages and every remaining byte goes to the raw ring.
-PipeCfg choose_pipe(int N, int K, int raw_tiles, int npro, int GT) {
+PipeCfg choose_pipe(int N, int K, int raw_tiles, int npro, int GT, bool atm = false) {
   const size_t budget = 227 * 1024;
   const int KC = (K + BK - 1) / BK;
+  if (atm) {
+    // A operand in tensor memory (two stages there): shared memory holds only weights and raw tiles.  Weights stay
+    // resident when four raw stages still fit beside them, else three streamed stages; raw ring up to six deep.
+    auto fits = [&](int WS, int RS) { return gemm2_smem(N, K, 0, WS, RS, raw_tiles, npro, GT) <= budget; };
+    auto fill = [&](int WS) { int RS = 0; while (RS < 6 && fits(WS, RS + 1)) ++RS; return RS; };
+    PipeCfg c = {2, 0, 0, 0, 0};
+    if (KC <= kMaxWS && fill(KC) >= 4) { c.WS = KC; c.wres = 1; }
+    else { c.WS = KC < 3 ? KC : 3; c.wres = KC <= 3 ? 1 : 0; }
+    c.RS = fill(c.WS);
+    if (c.RS < 1) c.RS = 1;
+    c.smem = gemm2_smem(N, K, 0, c.WS, c.RS, raw_tiles, npro, GT);
+    return c;
+  }
   const int rs_cap = 4;
   auto fits = [&](int OS, int WS, int RS) { return gemm2_smem(N, K, OS, WS, RS, raw_tiles, npro, GT) <= budget; };
   auto fill_rs = [&](int OS, int WS) { int RS = 0; while (RS < rs_cap && fits(OS, WS, RS + 1)) ++RS; return RS; };
@@ -669,7 +773,8 @@ EncodeTiledFn encode_tiled() {  // driver entry point through the runtime: no li
 }
 
 // tensor map of a row-major (R, ld) matrix of 4-byte elements with K valid columns, box = [box_rows x 32 columns]
-int make_tmap(CUtensorMap *tmap, const void *base, long long R, int K, long long ld, int box_rows = BM, bool i32 = false) {
+int make_tmap(CUtensorMap *tmap, const void *base, long long R, int K, long long ld, int box_rows = BM, bool i32 = false,
+              bool swizzle128 = false) {
   EncodeTiledFn enc = encode_tiled();
   if (!enc) {
     set_error("mlp: cuTensorMapEncodeTiled is not available from this driver");
@@ -680,7 +785,8 @@ int make_tmap(CUtensorMap *tmap, const void *base, long long R, int K, long long
   const cuuint32_t box[2] = {BK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(tmap, i32 ? CU_TENSOR_MAP_DATA_TYPE_INT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("mlp: cuTensorMapEncodeTiled failed (%d) for R=%lld K=%d ld=%lld", (int)r, R, K, ld);
@@ -689,13 +795,13 @@ int make_tmap(CUtensorMap *tmap, const void *base, long long R, int K, long long
   return S2C_OK;
 }
 
-template <int N, int PRO, int EPI>
+template <int N, int PRO, int EPI, bool ATM = false>
 int launch_gemm2(const Gemm2Args &g0, const float *A2, long long lda2, cudaStream_t st) {
   Gemm2Args g = g0;
   constexpr int raw_tiles = (PRO == PRO_AFFINE2) ? 2 : 1;
   constexpr int npro = (PRO == PRO_BNRELU) ? 2 : (PRO == PRO_AFFINE2) ? 3 : 5;
   CUtensorMap tmap, tmap2, tmap_am, tmap_dp;
-  int rc = make_tmap(&tmap, g.A ? g.A : A2, g.R, g.K, g.A ? g.lda : lda2);
+  int rc = make_tmap(&tmap, g.A ? g.A : A2, g.R, g.K, g.A ? g.lda : lda2, BM, false, ATM);
   if (rc) return rc;
   rc = make_tmap(&tmap2, A2 ? A2 : g.A, g.R, g.K, A2 ? lda2 : g.lda);
   if (rc) return rc;
@@ -710,7 +816,7 @@ int launch_gemm2(const Gemm2Args &g0, const float *A2, long long lda2, cudaStrea
   } else {
     tmap_am = tmap; tmap_dp = tmap;
   }
-  const PipeCfg pc = choose_pipe(N, g.K, raw_tiles, npro, g.GT);
+  const PipeCfg pc = choose_pipe(N, g.K, raw_tiles, npro, g.GT, ATM);
   const size_t smem = pc.smem;
   if (smem > 227 * 1024) {
     set_error("mlp: shared memory %zu B exceeds 227 KB (N=%d K=%d)", smem, N, g.K);
@@ -718,7 +824,7 @@ int launch_gemm2(const Gemm2Args &g0, const float *A2, long long lda2, cudaStrea
   }
   g.RS = pc.RS; g.OS = pc.OS; g.WS = pc.WS; g.wres = pc.wres;
   g.probe = g_probe_buf; g.probe_cap = g_probe_cap;
-  auto kern = mlp_gemm2_kernel<N, PRO, EPI>;
+  auto kern = mlp_gemm2_kernel<N, PRO, EPI, ATM>;
   S2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "mlp_gemm2 smem attr");
   const long long tiles = (g.R + BM - 1) / BM;
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
@@ -761,8 +867,13 @@ extern "C" int s2c_mlp_layer_fwd_v2(const float *A, long long lda, long long R, 
   Gemm2Args g = {};
   g.A = A; g.lda = lda; g.K = K; g.p0 = pro_scale; g.p1 = pro_shift; g.wprep = (const unsigned char *)wprep;
   g.C = C; g.ldc = ldc; g.stat_sum = stat_sum; g.stat_sumsq = stat_sumsq; g.R = R;
-  if (N == 64) return launch_gemm2<64, PRO_BNRELU, EPI_STORE_STATS>(g, nullptr, 0, st);
-  if (N == 128) return launch_gemm2<128, PRO_BNRELU, EPI_STORE_STATS>(g, nullptr, 0, st);
+  // forward: A operand through tensor memory (S2C_MLP_ATM=0: the shared-memory operand path, for A/B measurements)
+  const char *atm_env = getenv("S2C_MLP_ATM");
+  const bool atm = !(atm_env && atoi(atm_env) == 0);
+  if (N == 64) return atm ? launch_gemm2<64, PRO_BNRELU, EPI_STORE_STATS, true>(g, nullptr, 0, st)
+                          : launch_gemm2<64, PRO_BNRELU, EPI_STORE_STATS>(g, nullptr, 0, st);
+  if (N == 128) return atm ? launch_gemm2<128, PRO_BNRELU, EPI_STORE_STATS, true>(g, nullptr, 0, st)
+                           : launch_gemm2<128, PRO_BNRELU, EPI_STORE_STATS>(g, nullptr, 0, st);
   // N = 256: two passes over 128 output channels each (the operand + staging footprint of a 256-wide tile does not
   // leave room for a double-buffered pipeline in 227 KB); w_prep wrote the chunks of all 256 rows, so prepare per half
   for (int h = 0; h < 2; ++h) {
@@ -772,7 +883,8 @@ extern "C" int s2c_mlp_layer_fwd_v2(const float *A, long long lda, long long R, 
     Gemm2Args gh = g;
     gh.wprep = wp; gh.C = C + h * 128;
     if (stat_sum) { gh.stat_sum = stat_sum + h * 128; gh.stat_sumsq = stat_sumsq + h * 128; }
-    const int rc = launch_gemm2<128, PRO_BNRELU, EPI_STORE_STATS>(gh, nullptr, 0, st);
+    const int rc = atm ? launch_gemm2<128, PRO_BNRELU, EPI_STORE_STATS, true>(gh, nullptr, 0, st)
+                       : launch_gemm2<128, PRO_BNRELU, EPI_STORE_STATS>(gh, nullptr, 0, st);
     if (rc) return rc;
   }
   return S2C_OK;

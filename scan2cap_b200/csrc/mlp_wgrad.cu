@@ -99,6 +99,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// one elected lane of a converged warp (keeps the MMA operands in uniform registers: see elect_one in mlp2.cu)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void split_tf32(float v, float &hi, float &lo) {
   hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
   lo = v - hi;
@@ -250,14 +260,15 @@ mlp_wgrad_kernel(WgradArgs g) {
     // ===================== MMA issuer: D[128 x N] (per M half) += A[128 ch x 8 rows] * B[N ch x 8 rows]^T
     const int n0 = (NB > 8 ? 8 : NB) * 32, n1 = (NB > 8 ? NB - 8 : 0) * 32;
     const uint32_t idesc0 = make_idesc(128, n0), idesc1 = n1 ? make_idesc(128, n1) : 0u;
+    const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);  // warp-uniform by construction
     for (long long i = 0; i < my_chunks; ++i) {
       const int s = (int)(i % OS);
       mbar_wait(&bars[s], (uint32_t)((i / OS) & 1));
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t ah = smem_u32(smem + (size_t)s * stage_bytes), al = ah + a_bytes, bh = al + a_bytes, bl = bh + b_bytes;
+      const uint32_t ah = smem_u32(smem + (size_t)s * stage_bytes), al = ah + a_bytes, bh = al + a_bytes, bl = bh + b_bytes;
+      if (elect_one()) {
         for (int mh = 0; mh < g.MH; ++mh) {
-          const uint32_t d0 = tmem_base + (uint32_t)(mh * NB * 32);
+          const uint32_t d0 = tbase + (uint32_t)(mh * NB * 32);
 #pragma unroll
           for (int ks = 0; ks < CK / 8; ++ks) {  // UMMA K = 8 data rows = two 512-byte swizzle atoms of every 32-channel block
             const uint32_t acc = (i | ks) ? 1u : 0u;

@@ -28,6 +28,11 @@ variants["library GEMMs in the caption module"] = bench.Ours(cfg, dev, 0)
 variants["library GEMMs in the caption module"].timed(timer, 3, False)
 caption_module.linear = linear_simt.linear
 
+os.environ["S2C_MLP_ATM"] = "0"
+variants["forward A operand through shared memory"] = bench.Ours(cfg, dev, 0)
+variants["forward A operand through shared memory"].timed(timer, 3, False)
+del os.environ["S2C_MLP_ATM"]
+
 rel, col = distributed.FlatGradients.release, distributed.FlatGradients.collect
 distributed.FlatGradients.release = lambda self: self.zero_()
 distributed.FlatGradients.collect = lambda self: None

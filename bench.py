@@ -243,6 +243,10 @@ class Ours(object):
         import scan2cap_b200._lib as L
         res = self.resident()
         names = ("s2c_query_and_group_grid_prebuilt", "s2c_query_and_group_grid", "s2c_query_and_group")
+        for _ in range(2):   # untimed: the first eager steps of a process that has only replayed graphs so far pay lazy
+            timer.flush.zero_()   # initialisation (allocator growth, module loading) inside the bracketed call
+            self.engine.run_eager(dict(res))
+        torch.cuda.synchronize()
         L.TIMING = {n: [] for n in names}
         for _ in range(steps):
             timer.flush.zero_()
@@ -367,7 +371,7 @@ def run_ours(args, emit, rank, world, local_rank):
         k4 = max(3, min(args.steps, 10))
         c4.timed(timer, max(3, min(args.warmup, 5)), False)
         ms4, _ = c4.timed(timer, k4, False)
-        qg4_ms, qg4_kernel = c4.query_group_events(timer, 3)
+        qg4_ms, qg4_kernel = c4.query_group_events(timer, 5)
         c4.timed(timer, 2, True)
         ms4_e2e, loss4 = c4.timed(timer, k4, True)
         second = {

@@ -17,8 +17,13 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 32;
 constexpr int kMaxOS = 4, kMaxWS = 8, kMaxRS = 8;  // ring depths are chosen per shape by the host (choose_pipe)
-constexpr int kLoaderWarp = 0, kMmaWarp = 1, kFirstTransformWarp = 2, kFirstEpilogueWarp = 6;
-constexpr int kThreads = 10 * 32;
+constexpr int kLoaderWarp = 0, kMmaWarp = 1, kFirstTransformWarp = 2;
+// warps: loader, MMA issuer, TW transform warps, 4 epilogue warps.  TW = 4 with the operand staged through shared memory;
+// 8 on the tensor-memory operand path, where staging a chunk (one tile row per thread) was the slowest pipeline stage
+// (s2c_mlp_probe: 0.65-0.85 us per chunk, half of it barrier / tcgen05.st round trips): two groups of four warps take
+// the even and the odd chunks, so two chunks are being staged at any time.
+constexpr int transform_warps(bool atm) { return atm ? 8 : 4; }
+constexpr int block_threads(bool atm) { return (6 + transform_warps(atm)) * 32; }
 
 // operand prologues (applied by the transform warps while staging the A tile)
 constexpr int PRO_BNRELU = 1;   // a' = relu(a*p0[k] + p1[k])             (p0 == null: identity)         -- forward
@@ -263,7 +268,7 @@ __device__ __forceinline__ void tma_load_box(void *dst_smem, const CUtensorMap *
 // tile row per thread (row = TMEM lane), read it from the TMA-swizzled raw tile, and hand hi / lo to the tensor core with
 // two tcgen05.st; the MMAs read A from TMEM (tcgen05.mma [d], [a], b_desc) and only B from shared memory.
 template <int N, int PRO, int EPI, bool ATM>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(block_threads(ATM), 1)
 mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
                  const __grid_constant__ CUtensorMap tmap_am, const __grid_constant__ CUtensorMap tmap_dp) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -280,6 +285,7 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
                                  : (ACC_COLS + A_COLS <= 256) ? 256 : 512;
   static_assert(!ATM || PRO == PRO_BNRELU, "the tensor-memory operand path is built for the forward prologue");
   static_assert(ACC_COLS + A_COLS <= 512, "tensor memory");
+  constexpr int TW = transform_warps(ATM), kFirstEpilogueWarp = kFirstTransformWarp + TW, kThreads = block_threads(ATM);
   const int RS = g.RS, OS = g.OS, WS = g.WS;
   const bool wres = g.wres != 0;
   const int KC = (g.K + BK - 1) / BK;
@@ -296,7 +302,7 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool has_pro = g.p0 != nullptr;
   if (tid == 0) {
-    for (int s = 0; s < RS; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 128); }
+    for (int s = 0; s < RS; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 128); }  // four warps stage a chunk
     for (int s = 0; s < OS; ++s) { mbar_init(&op_full[s], 128); mbar_init(&op_empty[s], 1); }
     for (int s = 0; s < WS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
@@ -456,11 +462,16 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
           pgrp = (int)(gq - row0 / g.ns);
           psmp = (int)(base - gq * g.ns);
         }
-        if (tt == 0) S2C_PROBE(16 + 16 * (int)it + 0);
+        if (ATM && ((int)(it & 1) != ((warp - kFirstTransformWarp) >> 2))) {  // the other group's chunk
+          if (++rs == RS) { rs = 0; rph ^= 1u; }
+          if (++os == OS) { os = 0; oph ^= 1u; }
+          continue;
+        }
+        if ((tt & 127) == 0) S2C_PROBE(16 + 16 * (int)it + 0);
         mbar_wait(&raw_full[rs], rph);
-        if (tt == 0) S2C_PROBE(16 + 16 * (int)it + 1);
+        if ((tt & 127) == 0) S2C_PROBE(16 + 16 * (int)it + 1);
         if (it >= OS) mbar_wait(&op_empty[os], oph ^ 1u);
-        if (tt == 0) S2C_PROBE(16 + 16 * (int)it + 2);
+        if ((tt & 127) == 0) S2C_PROBE(16 + 16 * (int)it + 2);
         const unsigned char *raw = raw_base + (size_t)rs * RAW_BYTES;
         unsigned char *a_hi = a_base + (size_t)os * 2 * A_BYTES, *a_lo = a_hi + A_BYTES;
         if constexpr (ATM) {
@@ -497,7 +508,7 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
           tc_fence_before();
           mbar_arrive(&op_full[os]);
           mbar_arrive(&raw_empty[rs]);
-          if (tt == 0) S2C_PROBE(16 + 16 * (int)it + 3);
+          if ((tt & 127) == 0) S2C_PROBE(16 + 16 * (int)it + 3);
           if (++rs == RS) { rs = 0; rph ^= 1u; }
           if (++os == OS) { os = 0; oph ^= 1u; }
           continue;
@@ -579,7 +590,7 @@ mlp_gemm2_kernel(Gemm2Args g, const __grid_constant__ CUtensorMap tmap_a, const 
         fence_async_proxy();
         mbar_arrive(&op_full[os]);
         mbar_arrive(&raw_empty[rs]);
-        if (tt == 0) S2C_PROBE(16 + 16 * (int)it + 3);
+        if ((tt & 127) == 0) S2C_PROBE(16 + 16 * (int)it + 3);
         if (++rs == RS) { rs = 0; rph ^= 1u; }
         if (++os == OS) { os = 0; oph ^= 1u; }
       }
@@ -721,7 +732,7 @@ PipeCfg choose_pipe(int N, int K, int raw_tiles, int npro, int GT, bool atm = fa
   const size_t budget = 227 * 1024;
   const int KC = (K + BK - 1) / BK;
   if (atm) {
-    // A operand in tensor memory (two stages there): shared memory holds only weights and raw tiles.  Weights stay
+    // A operand in tensor memory (two stages there, one per group of transform warps): shared memory holds only weights and raw tiles.  Weights stay
     // resident when four raw stages still fit beside them, else three streamed stages; raw ring up to six deep.
     auto fits = [&](int WS, int RS) { return gemm2_smem(N, K, 0, WS, RS, raw_tiles, npro, GT) <= budget; };
     auto fill = [&](int WS) { int RS = 0; while (RS < 6 && fits(WS, RS + 1)) ++RS; return RS; };
@@ -828,7 +839,7 @@ int launch_gemm2(const Gemm2Args &g0, const float *A2, long long lda2, cudaStrea
   S2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "mlp_gemm2 smem attr");
   const long long tiles = (g.R + BM - 1) / BM;
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-  kern<<<grid, kThreads, smem, st>>>(g, tmap, tmap2, tmap_am, tmap_dp);
+  kern<<<grid, block_threads(ATM), smem, st>>>(g, tmap, tmap2, tmap_am, tmap_dp);
   S2C_CHECK_LAUNCH("mlp_gemm2 launch");
   return S2C_OK;
 }

@@ -178,6 +178,8 @@ S2C_API int s2c_pool_bwd_stats(const float *dpool, const int *argmax, const floa
 
 /* mlp_layer_fwd_v2 -- same contract as s2c_mlp_layer_fwd, warp-specialised and fed by the TMA engine
  *   (cp.async.bulk + mbarrier pipeline: loader / transform / MMA / epilogue warps, double-buffered TMEM).
+ *   The A operand reaches the tensor core through TENSOR memory (transform warps: tcgen05.st, MMA: tcgen05.mma [d],[a],b);
+ *   the environment variable S2C_MLP_ATM=0 selects the shared-memory operand path instead (A/B measurements only).
  *   Extra requirements: N in {64,128,256}; K, lda, ldc multiples of 4; A, C 16-byte aligned;
  *   wprep = workspace of ceil(K/32)*N*256 bytes (16-byte aligned) for the split / swizzled weights. */
 S2C_API int s2c_mlp_layer_fwd_v2(const float *A, long long lda, long long R, int K, const float *pro_scale,

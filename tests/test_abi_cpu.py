@@ -81,6 +81,11 @@ def test_argument_validation_of_the_fused_entry_points():
     assert L.s2c_adam_step(None, None, None, None, 10, None, None, 1, None, ctypes.c_float(1.0), None) == 1              # n % 4 != 0
     assert b"multiple of 4" in L.s2c_last_error()
     assert L.s2c_adam_step(None, None, None, None, 0, None, None, 1, None, ctypes.c_float(1.0), None) == 0               # n = 0: no-op
+    # fp32 GEMM of the caption Linear layers, pipeline probe of the layer kernels
+    assert L.s2c_gemm(None, 8, 1, None, 1, 8, None, 0, 4, 16, 8, None, 8, None) == 1 and b"bad sizes" in L.s2c_last_error()   # ldc < N
+    assert L.s2c_gemm(None, 8, 1, None, 1, 8, None, 0, 0, 16, 8, None, 16, None) == 0                                    # M = 0: no-op
+    assert L.s2c_gemm(None, 8, 1, None, 1, 8, None, 0, 4, 16, 8, None, 16, None) == 1 and b"null" in L.s2c_last_error()
+    assert L.s2c_mlp_probe(None, 0) == 0                                                                                # switches it off
 
 
 def test_first_layer_weight_layouts_round_trip():

@@ -34,7 +34,7 @@ def setenv(cfg):
         os.environ["S2C_MLP_OS"], os.environ["S2C_MLP_WS"], os.environ["S2C_MLP_RS"] = [str(c) for c in cfg]
 
 
-CFGS = [None]
+CFGS = [None, (2, 2, 4), (3, 0, 4), (2, 3, 2)]  # (the knobs act on the shared-memory operand path: backward kernels, or forward with S2C_MLP_ATM=0)
 FWD = [(1048576, 8, 64), (1048576, 64, 64), (1048576, 64, 128), (262144, 132, 128), (262144, 128, 128), (65536, 260, 128),
        (65536, 128, 128), (32768, 128, 128), (8192, 256, 128), (20480, 256, 128), (2048, 128, 128)]
 print("# us per launch (median of 7, L2 flushed); columns = (OS, WS, RS) request, 0 = resident weights; 'auto' = choose_pipe()")

@@ -6,7 +6,7 @@
  *
  * Parity status: PINNED.  Every function here is checked bit-for-bit against the
  * UNMODIFIED reference CUDA kernels (oracle/_ref/pointnet2_ref_ext.so, built from
- * /root/reference by oracle/build_ref.py) on a B200 by tests/test_oracle_vs_ref_gpu.py,
+ * /root/reference by oracle/build_ref.py) on a B200 by tests/test_native_ops_gpu.py (every case also runs oracle/_ref),
  * and against the golden vectors those kernels produced (tests/golden/*.npz, made by
  * tests/golden/make_golden_gpu.py), plus the reference's only known-answer test
  * (lib/pointnet2/pointnet2_test.py:18-30).

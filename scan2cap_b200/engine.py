@@ -31,7 +31,7 @@ from .optim import FlatAdam
 class TrainStep(object):
     def __init__(self, model, dataset_config, lr=1e-3, weight_decay=1e-5, detection=True, caption=True,
                  orientation=False, distance=False, use_cuda_graph=True, loss_fn=None, word_bucket=4,
-                 collective_in_graph=True, prefetch_indices=True):
+                 collective_in_graph=True, prefetch_indices=True, early_xyz_min_width=32):
         self.model = model
         self.DC = dataset_config
         self.flags = dict(detection=detection, caption=caption, orientation=orientation, distance=distance)
@@ -52,6 +52,8 @@ class TrainStep(object):
         self._prefetched = None    # (data_dict object, signature) whose inputs are in flight / in the staging buffers
         self._copy_stream = None
         self._stage_free = None    # event: the staging buffers have been copied into the static inputs
+        self.early_xyz_min_width = int(early_xyz_min_width)  # floats per point from which prefetch() sends the coordinates first
+        self._xyz_host = {}        # signature -> [pinned (B,N,3) buffer, its device copy, event of the last H2D out of it]
         self.kernels_per_step = None
         self.last = None  # data_dict of the last step (outputs live in graph-owned memory when graphed)
 
@@ -184,10 +186,10 @@ class TrainStep(object):
             if isinstance(v, torch.Tensor):
                 static[k].copy_(v, non_blocking=True)
 
-    def _load_indices(self, dst, point_clouds, grid=None):
-        """FPS of all levels for `point_clouds` into the (inds, xyz) buffers `dst` and SA1's ball-query grid into
-        `grid`, on the current stream."""
-        xyz = point_clouds[..., :3].contiguous()
+    def _load_indices(self, dst, point_clouds, grid=None, xyz=None):
+        """FPS of all levels for `point_clouds` (or for the contiguous coordinates `xyz`) into the (inds, xyz) buffers
+        `dst` and SA1's ball-query grid into `grid`, on the current stream."""
+        xyz = point_clouds[..., :3].contiguous() if xyz is None else xyz
         fresh = self.model.backbone_net.sample_indices(xyz)
         for (di, dx), (si, sx) in zip(dst, fresh):
             di.copy_(si, non_blocking=True)
@@ -219,15 +221,39 @@ class TrainStep(object):
                 if self.prefetch_indices:
                     self._stage[sig]["fps_precomputed"] = [(torch.empty_like(i), torch.empty_like(x))
                                                            for i, x in static["fps_precomputed"]]
+        # Host inputs: the sampling chain needs only the coordinates (12 of a row's 28..540 bytes).  They are gathered
+        # into a small pinned buffer and sent FIRST, so FPS / the grid build start at the beginning of the running step --
+        # as with device-resident inputs -- instead of behind the whole point-cloud transfer (2.8 ms at c4), where the
+        # sampling clusters would meet the caption decoder's cooperative grid and the two wait for each other's SMs.
+        # (Only for wide rows: with 7 floats per point the whole transfer is 0.7 ms, and the framework's host-side strided
+        # copy of 12 out of every 28 bytes is slow -- 43 ms for 8 x 40 000 points against 0.3 ms for 135-float rows.)
+        pc = data_dict.get("point_clouds")
+        early = (self.prefetch_indices and isinstance(pc, torch.Tensor) and not pc.is_cuda and pc.dim() == 3
+                 and pc.shape[-1] >= self.early_xyz_min_width)
+        if early:
+            xh = self._xyz_host.get(sig)
+            if xh is None:
+                buf = torch.empty(tuple(pc.shape[:2]) + (3,), dtype=pc.dtype).pin_memory()
+                with torch.cuda.stream(self._copy_stream):
+                    dev = torch.empty(buf.shape, dtype=pc.dtype, device=self.device)
+                xh = self._xyz_host[sig] = [buf, dev, None]
+            if xh[2] is not None:
+                xh[2].synchronize()          # the previous transfer out of the pinned buffer (a step ago) has completed
+            xh[0].copy_(pc[..., :3])
         if self._stage_free is not None:
             # wait only for the staging -> static copies of the step that consumed the staging buffers last (an event
             # recorded before that step's graph replay), NOT for the step itself: the transfer overlaps its compute
             self._copy_stream.wait_event(self._stage_free)
         with torch.cuda.stream(self._copy_stream):
+            if early:
+                xh[1].copy_(xh[0], non_blocking=True)
+                xh[2] = torch.cuda.Event()
+                xh[2].record(self._copy_stream)
+                self._load_indices(self._stage[sig]["fps_precomputed"], None, self._stage[sig].get("sa1_grid"), xyz=xh[1])
             for k, v in data_dict.items():
                 if isinstance(v, torch.Tensor):
                     self._stage[sig][k].copy_(v, non_blocking=True)
-            if self.prefetch_indices:
+            if self.prefetch_indices and not early:
                 self._load_indices(self._stage[sig]["fps_precomputed"], self._stage[sig]["point_clouds"],
                                    self._stage[sig].get("sa1_grid"))
         self._prefetched = (data_dict, sig)

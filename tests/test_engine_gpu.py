@@ -100,7 +100,8 @@ def test_trainstep_prefetch_double_buffer_same_result():
     model, DC, batches = _setup()
     m_a, m_b = copy.deepcopy(model), copy.deepcopy(model)
     a = TrainStep(m_a, DC, use_cuda_graph=True, **FLAGS)
-    b = TrainStep(m_b, DC, use_cuda_graph=True, **FLAGS)
+    # early_xyz_min_width=0: also exercise the coordinates-first transfer prefetch() uses for wide point rows (c4)
+    b = TrainStep(m_b, DC, use_cuda_graph=True, early_xyz_min_width=0, **FLAGS)
     seq = [0, 0, 1, 0, 1, 1]
     nxt = dict(batches[seq[0]])
     b.prefetch(nxt)

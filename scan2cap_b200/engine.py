@@ -31,7 +31,7 @@ from .optim import FlatAdam
 class TrainStep(object):
     def __init__(self, model, dataset_config, lr=1e-3, weight_decay=1e-5, detection=True, caption=True,
                  orientation=False, distance=False, use_cuda_graph=True, loss_fn=None, word_bucket=4,
-                 collective_in_graph=True, prefetch_indices=True, early_xyz_min_width=32):
+                 collective_in_graph=True, prefetch_indices=True, early_xyz_min_width=64):
         self.model = model
         self.DC = dataset_config
         self.flags = dict(detection=detection, caption=caption, orientation=orientation, distance=distance)
@@ -226,7 +226,7 @@ class TrainStep(object):
         # as with device-resident inputs -- instead of behind the whole point-cloud transfer (2.8 ms at c4), where the
         # sampling clusters would meet the caption decoder's cooperative grid and the two wait for each other's SMs.
         # (Only for wide rows: with 7 floats per point the whole transfer is 0.7 ms, and the framework's host-side strided
-        # copy of 12 out of every 28 bytes is slow -- 43 ms for 8 x 40 000 points against 0.3 ms for 135-float rows.)
+        # copy of 12 out of every 28 bytes is slow -- 43 ms for 8 x 40 000 points against 0.2-0.35 ms for rows of 64..135 floats.)
         pc = data_dict.get("point_clouds")
         early = (self.prefetch_indices and isinstance(pc, torch.Tensor) and not pc.is_cuda and pc.dim() == 3
                  and pc.shape[-1] >= self.early_xyz_min_width)

@@ -216,21 +216,6 @@ __device__ __forceinline__ void store_split(unsigned char *hi_base, unsigned cha
   *reinterpret_cast<float4 *>(lo_base + off) = l;
 }
 
-// lane l ends with the sum over the warp's 32 lanes of v[l] (transpose-reduce, 31 shuffles); v is clobbered
-__device__ __forceinline__ float warp_colsum32(float *v, int lane) {
-#pragma unroll
-  for (int w = 16; w >= 1; w >>= 1) {
-    const bool up = (lane & w) != 0;
-#pragma unroll
-    for (int i = 0; i < w; ++i) {
-      const float keep = up ? v[i + w] : v[i];
-      const float send = up ? v[i] : v[i + w];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
-    }
-  }
-  return v[0];
-}
-
 // weight preparation: W (N, K) fp32 -> per K-chunk [hi | lo] blocks in the operand layout (done once per call)
 // kmajor = 1: operand row n, column k = W[n*ld + k]   (forward: W is (N, K))
 // kmajor = 0: operand row n, column k = W[k*ld + n]   (backward data: the operand is W^T of a (K, N) weight)
